@@ -1,0 +1,247 @@
+/*
+ * quadsim_abi.h -- C ABI of libquadsim (sm_100a), the drop-in boundary of the
+ * batched quadrotor env step / rollout / GAE hot path.
+ *
+ * The reference has no FFI for this path: the boundary is two Python duck-typed
+ * protocols (Brax Env: train_brax_ppo.py:232-356; Gymnasium Env:
+ * envs/hover_env.py:159-238).  Each entry point below states which reference
+ * interface it replaces.  All pointers are DEVICE pointers unless the name ends in
+ * _host; all buffers are caller-owned; `stream` is a cudaStream_t passed as void*
+ * (NULL = legacy default stream).  Every call returns 0 on success or a negative
+ * QS_E* code, never throws, never falls back to the CPU.  One handle per
+ * (device, env shard); a handle is not thread-safe, distinct handles are independent.
+ *
+ * Data layout.  Env state is planar struct-of-arrays, float32/int32, `QS_NPLANES`
+ * planes of `num_envs` elements each: plane p of env i is state[p * num_envs + i].
+ *   0..10  qpos  (x y z | qw qx qy qz | rotor angles 1..4)      reference: data.qpos
+ *   11..20 qvel  (vx vy vz world | wx wy wz body | rotor rates)  reference: data.qvel
+ *   21..23 target position                                       hover_env.py:227
+ *   24     step_count (int32)            train_brax_ppo.py:319 / hover_env.py:182
+ *   25     battery voltage                                       hover_env.py:102-109
+ *   26     episode index (uint32, Philox counter word)
+ *   27     ep_steps (int32, Brax EpisodeWrapper info["steps"])
+ *   28     waypoint index (int32)                                evaluate.py:496,551
+ *   29     waypoints reached (int32)                             evaluate.py:550
+ *   30     laps completed (int32)                                evaluate.py:553
+ *   31     done flag of the previous step (float32 0/1; Brax AutoResetWrapper)
+ * Actions are [num_envs][4] float32 (row-major, 16 B per env); observations are
+ * [num_envs][obs_dim] float32 row-major; reward/done/truncated are [num_envs] float32.
+ */
+#ifndef QUADSIM_ABI_H
+#define QUADSIM_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_ABI_VERSION 1
+#define QS_NPLANES 32
+#define QS_NQ 11
+#define QS_NV 10
+#define QS_MAX_WP 64
+#define QS_MAX_SHAPES 4
+
+/* error codes */
+#define QS_OK 0
+#define QS_EINVAL (-1)     /* bad argument / inconsistent config            */
+#define QS_ECUDA (-2)      /* CUDA runtime error, see qs_last_error_string  */
+#define QS_ENOMEM (-3)
+#define QS_EUNSUPPORTED (-4)
+
+/* env semantics selector (SURVEY 8a "Env variants") */
+enum QsMode {
+    QS_MODE_MJX_BRAX = 0,       /* JaxMJXQuadBraxEnv     train_brax_ppo.py:179-368 */
+    QS_MODE_HOVER_GYM = 1,      /* HoverEnv              envs/hover_env.py          */
+    QS_MODE_TRAJ_GYM = 2,       /* TrajectoryFollowEnv   envs/trajectory_follow_env.py */
+    QS_MODE_HOVER_BRAX = 3,     /* QuadHoverBraxEnv      train_brax_ppo.py:39-176   */
+    QS_MODE_MJX_PLAYGROUND = 4  /* JaxMJXQuadEnv         envs/jax_mjx_quad_env.py   */
+};
+
+enum QsAutoReset {
+    QS_RESET_NONE = 0,
+    QS_RESET_RESTORE_FIRST = 1, /* Brax AutoResetWrapper: restore the episode-0 state */
+    QS_RESET_RESAMPLE = 2       /* VecEnv semantics: fresh Philox sample per episode  */
+};
+
+/*
+ * Plain-old-data parameter block: model constants (derived in float64 from the MJCF
+ * by the host, stored as float32) + env semantics.  It is passed BY VALUE to every
+ * kernel, i.e. it lives in the constant bank for the lifetime of the launch.
+ */
+typedef struct QsParams {
+    /* --- integrator / composite body ------------------------------------ */
+    float dt, gz, mass, inv_mass;
+    float com[3];            /* composite COM in the base frame                  */
+    float I_C[9];            /* composite inertia about the COM (row-major)       */
+    float Ieff_inv[9];       /* inv(I_C - zz^T sum J^2/Js)                       */
+    float rotor_J[4], rotor_invJs[4], rotor_rho[4] /* J/Js */, rotor_damp[4];
+    float rotor_r[12];       /* rotor COM in base frame, [k][3]                   */
+    float rotor_d[12];       /* rotor COM relative to composite COM, [k][3]       */
+    float wrench[24];        /* [6][4]: body force ; torque about COM, per N      */
+    float ctrl_lo[4], ctrl_hi[4];
+    /* --- fluid ------------------------------------------------------------ */
+    float base_lin_visc, base_ang_visc;
+    float base_lin_quad[3], base_ang_quad[3];
+    float rot_lin_visc[4], rot_lin_quad_ax[4], rot_lin_quad_lat[4];
+    float rot_ang_visc[4], rot_ang_quad_ax[4], rot_ang_quad_lat[4];
+    /* --- action path (utils/drone_config.py, hover_env.py:60-65,94-100) ---- */
+    float act_lo[4], act_hi[4];       /* physical action bounds                 */
+    float mix_inv[16];                /* A^-1, row-major                          */
+    float max_motor_thrust;
+    int32_t pre_clip_action;          /* Q1: Brax variants clip the denormalised action */
+    /* --- battery (hover_env.py:102-109) ------------------------------------ */
+    int32_t battery;
+    float v_nominal, v_min, v_drop_base, v_drop_load;
+    /* --- observation / reward / termination -------------------------------- */
+    int32_t mode, obs_dim;
+    float obs_lo[12], obs_scale[12];  /* obs = (x - lo) * scale - 1, scale = 2/(hi-lo) */
+    float term_lo[12], term_hi[12];   /* gym modes: inclusive box on the 12-D state */
+    float pos_limit_xy, z_low, z_high, vel_limit;   /* brax modes                 */
+    float reward_k;                   /* exp(-k e^2): 1, or 2 for hover_brax (Q2)  */
+    float action_penalty;             /* 0.001 for mjx_brax, else 0               */
+    float fixed_target[3];            /* hover_brax (0,0,h)                       */
+    /* --- episode handling -------------------------------------------------- */
+    int32_t max_episode_steps;        /* gym truncation / length of the mjx target table */
+    int32_t episode_length;           /* Brax EpisodeWrapper; 0 = wrapper off     */
+    int32_t auto_reset;               /* enum QsAutoReset                         */
+    /* --- reset distribution ------------------------------------------------ */
+    float init_lo[12], init_hi[12];   /* hover_env.py:42-45                       */
+    float target_lo[3], target_hi[3]; /* hover_env.py:48-51                       */
+    float reset_noise;                /* brax modes: U(-n, n) on all qpos/qvel    */
+    float reset_z;                    /* brax modes: nominal height               */
+    uint32_t seed_lo, seed_hi;
+    uint32_t env_id_offset;           /* global id of local env 0 (sharding)      */
+    /* --- waypoint tracking (evaluate.py:440-557) --------------------------- */
+    int32_t waypoint_mode;            /* 0 off */
+    int32_t wp_num_shapes;
+    int32_t wp_count[QS_MAX_SHAPES];
+    float wp_reach_radius;
+    int32_t reserved[7];
+} QsParams;
+
+typedef struct QsEngine* QsHandle;
+
+/* library identity / diagnostics */
+int qs_abi_version(void);
+const char* qs_last_error_string(void);
+/* sizeof(QsParams) as compiled, so a binding can verify its mirror of the struct */
+int qs_params_size(void);
+
+/*
+ * qs_create: replaces the env constructors (train_brax_ppo.py:180-230,
+ * envs/hover_env.py:15-100): binds a parameter block to a device and `num_envs`.
+ *   target_table_host : [max_episode_steps][3] float32 target positions for the mjx
+ *                       modes (train_brax_ppo.py:358-364), may be NULL otherwise.
+ *   waypoints_host    : [wp_num_shapes][QS_MAX_WP][3] float64 (utils/trajectories.py),
+ *                       may be NULL when waypoint_mode == 0.
+ */
+int qs_create(const QsParams* params, int32_t num_envs, int32_t device,
+              const float* target_table_host, const double* waypoints_host, QsHandle* out);
+int qs_destroy(QsHandle h);
+int qs_num_envs(QsHandle h);
+int qs_get_params(QsHandle h, QsParams* out);
+
+/*
+ * qs_reset: replaces Env.reset (train_brax_ppo.py:244-289; hover_env.py:200-238).
+ * Re-initialises every env whose mask entry is non-zero (mask == NULL: all) with the
+ * Philox draw for (seed, global env id, episode index); writes obs for those envs.
+ * first_state (optional, [21][num_envs]) receives the qpos/qvel of the new episode
+ * (Brax AutoResetWrapper info["first_pipeline_state"]).
+ */
+int qs_reset(QsHandle h, float* state, const uint8_t* mask, float* obs, float* first_state, void* stream);
+
+/*
+ * qs_step: replaces Env.step (train_brax_ppo.py:307-356; hover_env.py:159-198) fused
+ * with the vectorising wrappers' episode logic (Brax Episode/AutoReset wrappers; SB3
+ * VecEnv auto-reset) as configured in QsParams.  In place on `state`.
+ *   metrics      : optional [4][num_envs]: pos_error, reward_hover, reward_action, reward
+ *   truncated    : optional [num_envs]
+ *   terminal_obs : optional [num_envs][obs_dim], written only for envs that finished
+ *   first_state  : required when auto_reset == QS_RESET_RESTORE_FIRST
+ */
+int qs_step(QsHandle h, float* state, const float* action, float* obs, float* reward, float* done,
+            float* truncated, float* metrics, float* terminal_obs, const float* first_state, void* stream);
+
+/*
+ * qs_observe: obs / reward / done of the CURRENT state without stepping
+ * (hover_env.py:126-157 _get_obs/_get_reward/_is_terminated; train_brax_ppo.py:324-338).
+ * `action` may be NULL (action penalty = 0).  Used for injected-state parity.
+ */
+int qs_observe(QsHandle h, const float* state, const float* action, float* obs, float* reward,
+               float* done, void* stream);
+
+/*
+ * qs_physics_step: the bare mjx.step / mj_step replacement (train_brax_ppo.py:317,
+ * hover_env.py:180): ctrl [num_envs][4] motor forces in N -> advances planes 0..20 only.
+ */
+int qs_physics_step(QsHandle h, float* state, const float* ctrl, void* stream);
+
+/*
+ * qs_rollout_random: state-resident dynamics-only rollout, T env steps per launch with
+ * in-kernel Philox actions U(-1,1)^4 (stream 2), auto-reset per QsParams.  Accumulates
+ * per-env sums: stats [4][num_envs] += (sum reward, episodes finished, obs checksum, steps).
+ * `t0` is the global step index of the first step (Philox counter word).
+ */
+int qs_rollout_random(QsHandle h, float* state, int32_t T, uint32_t t0, float* stats, const float* first_state,
+                      void* stream);
+
+/*
+ * Policy rollout (replaces brax acting.generate_unroll / SB3 collect_rollouts around the
+ * env, train_brax_ppo.py:589-620, train.py:133-137).  See qs_policy.h section below.
+ */
+typedef struct QsPolicyDesc {
+    int32_t obs_dim;        /* 12 or 21 */
+    int32_t hidden;         /* 128 */
+    int32_t act_dim;        /* 4 */
+    int32_t dist;           /* 0 = SB3 diagonal Gaussian with state-independent log_std,
+                               1 = Brax tanh-normal, actor head emits loc|raw_scale (8) */
+    int32_t deterministic;  /* 1: action = mean (tanh(mean) for dist 1) */
+    float bootstrap_gamma;  /* > 0: SB3 timeout bootstrap, reward += gamma * V(terminal_obs) on truncation */
+    int32_t reserved[2];
+} QsPolicyDesc;
+
+/* number of float32 in the packed parameter vector for a policy description:
+ * actor W1[obs][H] b1[H] W2[H][H] b2[H] W3[H][A'] b3[A'] (A' = act_dim or 2*act_dim),
+ * critic W1[obs][H] b1[H] W2[H][H] b2[H] W3[H] b3[1], log_std[act_dim] (dist 0 only),
+ * obs_mean[obs] obs_inv_std[obs].  Weights are [in][out] row-major. */
+int qs_policy_param_count(const QsPolicyDesc* desc);
+
+/*
+ * qs_rollout_policy: T steps of {policy forward -> sample -> env step} with env state
+ * resident on chip.  Trajectory buffers are time-major:
+ *   traj_obs [T][B][obs_dim], traj_act [T][B][4], traj_logp/value/reward/done/trunc [T][B];
+ *   last_value [B] = V(obs after the last step); last_obs [B][obs_dim] (optional) that obs.
+ * traj_act holds the RAW Gaussian sample (pre-clip for dist 0, pre-tanh for dist 1), as SB3's
+ * RolloutBuffer and brax's policy_extras["raw_action"] do.
+ * Any trajectory pointer may be NULL to skip that stream.
+ */
+int qs_rollout_policy(QsHandle h, float* state, const QsPolicyDesc* desc, const float* policy_params,
+                      int32_t T, uint32_t t0, float* last_obs,
+                      float* traj_obs, float* traj_act, float* traj_logp, float* traj_value,
+                      float* traj_reward, float* traj_done, float* traj_trunc,
+                      float* last_value, const float* first_state, void* stream);
+
+/*
+ * qs_gae: reverse-time scan over [T][B] (SB3 RolloutBuffer.compute_returns_and_advantage
+ * semantics when brax_form == 0; brax compute_gae semantics when brax_form == 1).
+ */
+int qs_gae(int32_t T, int32_t B, const float* reward, const float* value, const float* done,
+           const float* trunc, const float* last_value, float gamma, float lam, int32_t brax_form,
+           float* adv, float* ret, void* stream);
+
+/*
+ * Host-buffer convenience entry (what a non-torch binding of Env.step would call):
+ * copies action_host H2D, steps, copies obs/reward/done D2H, synchronises.
+ */
+int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
+                 float* done_host, void* stream);
+
+/* launch accounting for bench.py's gpu_launches claim */
+uint64_t qs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADSIM_ABI_H */

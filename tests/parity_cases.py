@@ -1,0 +1,198 @@
+"""Backend-agnostic parity cases: the same checks run against
+  * the g++ host build of the kernels' per-env source (CPU suite, `-m "not gpu"`), and
+  * the real sm_100a library through the C ABI (GPU suite, `-m gpu`),
+each compared with oracle/ on identical seeded inputs.
+
+Bars (BASELINE.json north_star): done / truncated flags, step counters, episode (reset)
+indices and waypoint indices bit-exact; float32 state within 1e-5 relative / 1e-6 absolute
+of the float64 oracle after one step.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle.envs import OracleEnv
+from uav_reinforcement_learning_control_b200 import config as Q
+from uav_reinforcement_learning_control_b200 import model as M
+
+from .util import assert_close, make_planes, planes_view, random_states
+
+_TREE = None
+
+
+def tree():
+    global _TREE
+    if _TREE is None:
+        _TREE = M.load_mjcf(M.default_model_path())
+    return _TREE
+
+
+CONFIGS = {
+    "hover_gym": lambda: Q.EnvConfig.hover_gym(),
+    "north_star": lambda: Q.EnvConfig.north_star(),
+    "hover_gym_autoreset": lambda: Q.EnvConfig.hover_gym(auto_reset=Q.RESET_RESAMPLE, seed=1234, env_id_offset=77),
+    "traj_gym": lambda: Q.EnvConfig.traj_gym(),
+    "mjx_brax": lambda: Q.EnvConfig.mjx_brax(),
+    "mjx_brax_wrapped": lambda: Q.EnvConfig.mjx_brax(episode_length=500, auto_reset=Q.RESET_RESTORE_FIRST),
+    "hover_brax": lambda: Q.EnvConfig.hover_brax(),
+    "hover_brax_wrapped": lambda: Q.EnvConfig.hover_brax(episode_length=100, auto_reset=Q.RESET_RESTORE_FIRST),
+    "mjx_playground": lambda: Q.EnvConfig.mjx_playground(),
+}
+
+
+def synth_inputs(cfg, n, seed):
+    """Synthetic uniformly randomised states that straddle every termination bound."""
+    gym = cfg.mode in (Q.MODE_HOVER_GYM, Q.MODE_TRAJ_GYM)
+    pos = 2.3 if cfg.mode == Q.MODE_HOVER_GYM else 3.3
+    qpos, qvel = random_states(n, seed=seed, pos=pos, vel=11.0 if gym else 21.0, omega=20.0)
+    rng = np.random.default_rng(seed + 1)
+    qpos[:, 2] = rng.uniform(-0.1, 2.2 if cfg.mode == Q.MODE_HOVER_GYM else 4.2, n).astype(np.float32)
+    act = rng.uniform(-1.2, 1.2, (n, 4)).astype(np.float32)
+    tgt = rng.uniform(-1.5, 1.8, (n, 3)).astype(np.float32)
+    sc = rng.integers(0, cfg.max_episode_steps + 8, n).astype(np.int32)
+    # a few exactly at the truncation edge
+    sc[:8] = cfg.max_episode_steps - 1
+    volt = rng.uniform(cfg.v_min, cfg.v_nominal, n).astype(np.float32)
+    ep_steps = rng.integers(0, max(cfg.episode_length, 1), n).astype(np.int32)
+    if cfg.episode_length > 0:
+        ep_steps[:16] = cfg.episode_length - 1
+    done_prev = (rng.uniform(size=n) < 0.2).astype(np.float32)
+    st = make_planes(n, qpos, qvel, target=tgt, step_count=sc, voltage=volt, episode=rng.integers(0, 5, n),
+                     ep_steps=ep_steps, done_prev=done_prev)
+    # non-finite injections: termination / NaN->0 paths
+    st[0, 20] = np.nan; st[12, 21] = np.inf; st[4, 22] = np.nan; st[17, 23] = -np.inf
+    first = None
+    if cfg.auto_reset == Q.RESET_RESTORE_FIRST:
+        fq, fv = random_states(n, seed=seed + 7, pos=0.01, vel=0.01, omega=0.01, spin=0.01, theta=0.01)
+        first = np.ascontiguousarray(np.concatenate([fq.T, fv.T]).astype(np.float32))
+    return st, act, first
+
+
+def check_single_step(backend_factory, name, n=4096, seed=0):
+    cfg = CONFIGS[name]()
+    backend = backend_factory(cfg)
+    orc = OracleEnv(tree(), cfg)
+    st, act, first = synth_inputs(cfg, n, seed)
+    prev = planes_view(st.copy())
+    s = OracleEnv.from_planes(st)
+    firsto = None if first is None else dict(qpos=first[:11].T.astype(np.float64), qvel=first[11:].T.astype(np.float64))
+    o = orc.step(s, act, firsto)
+    h = backend.step(st, act, first=first, want_term=True)
+    pv = planes_view(st)
+
+    # --- bit-exact items ---------------------------------------------------------------
+    np.testing.assert_array_equal(h["done"], o["done"], err_msg=f"{name}: done flags")
+    np.testing.assert_array_equal(h["truncated"], o["truncated"], err_msg=f"{name}: truncated flags")
+    if cfg.mode != Q.MODE_HOVER_BRAX:
+        np.testing.assert_array_equal(pv["step_count"], s["step_count"], err_msg=f"{name}: step_count")
+    gym = cfg.mode in (Q.MODE_HOVER_GYM, Q.MODE_TRAJ_GYM)
+    if gym:
+        np.testing.assert_array_equal(pv["episode"], s["episode"], err_msg=f"{name}: episode (reset) index")
+    if cfg.mode in (Q.MODE_MJX_BRAX, Q.MODE_HOVER_BRAX) and (cfg.episode_length > 0 or cfg.auto_reset):
+        np.testing.assert_array_equal(pv["ep_steps"], s["ep_steps"], err_msg=f"{name}: ep_steps")
+        if cfg.auto_reset == Q.RESET_RESTORE_FIRST:
+            np.testing.assert_array_equal(pv["done_prev"], s["done_prev"], err_msg=f"{name}: done_prev")
+    term_written = ~np.isnan(h["terminal_obs"]).all(axis=1)
+    finite_in = np.isfinite(o["terminal_obs"]).all(axis=1) | ~o["finished"]
+    np.testing.assert_array_equal(term_written[finite_in], o["finished"][finite_in],
+                                  err_msg=f"{name}: which envs wrote terminal_obs")
+
+    # --- float items ---------------------------------------------------------------------
+    ok = np.isfinite(s["qpos"]).all(axis=1) & np.isfinite(s["qvel"]).all(axis=1)
+    reset = o["finished"] & (cfg.auto_reset != Q.RESET_NONE)
+    keep = ok & ~reset
+    assert keep.sum() > n // 10
+    assert_close(pv["qpos"][keep], s["qpos"][keep], what=f"{name}: qpos", scale=prev["qpos"][keep])
+    assert_close(pv["qvel"][keep], s["qvel"][keep], what=f"{name}: qvel", scale=prev["qvel"][keep])
+    if reset.any():
+        # freshly reset / restored states: float32 op-for-op reproducible up to sincos rounding
+        assert_close(pv["qpos"][reset], s["qpos"][reset], what=f"{name}: reset qpos", rtol=1e-6, atol=1e-7)
+        assert_close(pv["qvel"][reset], s["qvel"][reset], what=f"{name}: reset qvel", rtol=1e-6, atol=1e-7)
+        if gym:
+            np.testing.assert_array_equal(pv["target"][reset], s["target"][reset], err_msg=f"{name}: reset target")
+    fin_r = np.isfinite(o["reward"])
+    assert_close(h["reward"][fin_r], o["reward"][fin_r], what=f"{name}: reward")
+    # observations: angles near +-pi wrap, compare on the circle for the gym attitude entries
+    oo, ho = o["obs"].astype(np.float64), h["obs"].astype(np.float64)
+    # rows whose INPUT state was non-finite are excluded from float comparisons: the generic pipeline
+    # (like MuJoCo's dense solve) spreads one NaN to every coordinate, the closed form keeps it
+    # contained; both flag the env done (checked bit-exactly above), which is what the reference tests
+    okobs = np.isfinite(oo).all(axis=1) & ok
+    if gym:
+        d = ho[:, 3:6] - oo[:, 3:6]
+        d = (d + 1.0) % 2.0 - 1.0                # normalised angle lives on [-1, 1)
+        ho = ho.copy(); ho[:, 3:6] = oo[:, 3:6] + d
+    if gym:
+        # normalised obs: the velocity entries are state / bound, so scale the pre-step state alike
+        sc_obs = np.zeros_like(oo)
+        sc_obs[:, 6:9] = prev["qvel"][:, 0:3] / 10.0; sc_obs[:, 9:12] = prev["qvel"][:, 3:6] / (6 * np.pi)
+    else:
+        sc_obs = np.concatenate([prev["qpos"], prev["qvel"]], axis=1)
+    sc_obs = np.where(reset[:, None], 0.0, sc_obs)
+    assert_close(ho[okobs], oo[okobs], what=f"{name}: obs", rtol=2e-5, atol=2e-6, scale=sc_obs[okobs])
+    if cfg.battery:
+        assert_close(pv["voltage"], s["voltage"], what=f"{name}: voltage")
+    for i, k in enumerate(["pos_error", "reward_hover", "reward_action", "reward"]):
+        f = np.isfinite(o[k])
+        assert_close(h["metrics"][i][f], np.asarray(o[k])[f], what=f"{name}: metric {k}", rtol=2e-5, atol=2e-6)
+    return dict(done=int(o["done"].sum()), truncated=int(o["truncated"].sum()), finished=int(o["finished"].sum()))
+
+
+def check_reset(backend_factory, name, n=2048):
+    cfg = CONFIGS[name]()
+    backend = backend_factory(cfg)
+    orc = OracleEnv(tree(), cfg)
+    rng = np.random.default_rng(5)
+    st = make_planes(n, episode=rng.integers(0, 1000, n))
+    s = OracleEnv.from_planes(st)
+    mask = (rng.uniform(size=n) < 0.7)
+    orc.reset(s, mask)
+    obs, first = backend.reset(st, mask.astype(np.uint8), want_first=True)
+    pv = planes_view(st)
+    m = mask
+    gym = cfg.mode in (Q.MODE_HOVER_GYM, Q.MODE_TRAJ_GYM)
+    # positions / velocities / targets are straight float32 Philox draws: bit-exact
+    np.testing.assert_array_equal(pv["qpos"][m][:, 0:3], s["qpos"][m][:, 0:3].astype(np.float32))
+    np.testing.assert_array_equal(pv["qvel"][m], s["qvel"][m].astype(np.float32))
+    assert_close(pv["qpos"][m][:, 3:7], s["qpos"][m][:, 3:7], what=f"{name}: reset quat", rtol=1e-6, atol=2e-7)
+    np.testing.assert_array_equal(pv["qpos"][m][:, 7:11], s["qpos"][m][:, 7:11].astype(np.float32))
+    if gym:
+        np.testing.assert_array_equal(pv["target"][m], s["target"][m])
+    np.testing.assert_array_equal(pv["step_count"][m], 0)
+    # untouched envs keep their (blank) state
+    np.testing.assert_array_equal(pv["qpos"][~m][:, 3], 1.0)
+    np.testing.assert_array_equal(pv["qpos"][~m][:, 0:3], 0.0)
+    ev = orc.evaluate(s, None)
+    assert_close(obs[m], ev["obs"][m], what=f"{name}: reset obs", rtol=2e-5, atol=2e-6)
+    np.testing.assert_array_equal(first[:11].T[m], pv["qpos"][m])
+    np.testing.assert_array_equal(first[11:].T[m], pv["qvel"][m])
+
+
+def check_observe_bit_exact_masks(backend_factory, name, n=8192, seed=3):
+    """R5: masks decided on the SAME float32 state must be bit-exact, including at the bound edges."""
+    cfg = CONFIGS[name]()
+    backend = backend_factory(cfg)
+    orc = OracleEnv(tree(), cfg)
+    st, act, _ = synth_inputs(cfg, n, seed)
+    pv = planes_view(st)
+    # plant states exactly ON the bounds and one ulp either side
+    if cfg.mode in (Q.MODE_HOVER_GYM, Q.MODE_TRAJ_GYM):
+        hi = np.float32(cfg.term_hi[0]); lo_z = np.float32(cfg.term_lo[2])
+        vals = [hi, np.nextafter(hi, np.float32(np.inf)), np.nextafter(hi, np.float32(-np.inf))]
+        for k, v in enumerate(vals):
+            st[0, 100 + k] = v; st[1, 110 + k] = -v
+            st[11, 120 + k] = np.float32(10.0) + np.float32(k - 1) * np.float32(1e-6)
+        st[2, 130] = lo_z; st[2, 131] = np.nextafter(lo_z, np.float32(-1))
+    else:
+        lim = np.float32(cfg.pos_limit_xy)
+        for k, v in enumerate([lim, np.nextafter(lim, np.float32(np.inf)), np.nextafter(lim, np.float32(-np.inf))]):
+            st[0, 100 + k] = v; st[1, 110 + k] = -v
+        st[2, 130] = np.float32(cfg.z_low); st[2, 131] = np.nextafter(np.float32(cfg.z_low), np.float32(-1))
+        st[11, 140] = np.float32(cfg.vel_limit); st[11, 141] = np.nextafter(np.float32(cfg.vel_limit), np.float32(np.inf))
+    s = OracleEnv.from_planes(st)
+    ev = orc.evaluate(s, act)
+    obs, rew, done = backend.observe(st, act)
+    np.testing.assert_array_equal(done, ev["done"], err_msg=f"{name}: done on injected state")
+    f = np.isfinite(ev["reward"])
+    assert_close(rew[f], ev["reward"][f], what=f"{name}: reward on injected state", rtol=2e-5, atol=2e-6)
+    return int(ev["done"].sum())

@@ -1,0 +1,227 @@
+// quadsim.cu -- C-ABI entry points of libquadsim.so (include/quadsim_abi.h) and kernel dispatch.
+// Built for sm_100a only; there is no CPU code path behind any of these calls.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <new>
+
+#include "qs_kernels.cuh"
+#include "qs_rollout.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+    if (ce != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(ce));
+    else snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+
+#define QS_CUDA(call)                                                      \
+    do {                                                                   \
+        cudaError_t ce_ = (call);                                          \
+        if (ce_ != cudaSuccess) return fail(QS_ECUDA, #call, ce_);         \
+    } while (0)
+
+inline int nblocks(int n, int block) { return (n + block - 1) / block; }
+
+}  // namespace
+
+struct QsEngine {
+    QsParams P;
+    int32_t n;
+    int device;
+    float* target_table;    // device, [max_episode_steps][3] or null
+    double* waypoints;      // device, [shapes][QS_MAX_WP][3] or null
+    float* scratch;         // device staging for qs_step_host: action | obs | reward | done
+    qs::Tables tables() const { return qs::Tables{target_table, waypoints}; }
+};
+
+#define QS_DISPATCH_MODE(mode, CALL)                                          \
+    switch (mode) {                                                           \
+        case QS_MODE_MJX_BRAX: { constexpr int M_ = QS_MODE_MJX_BRAX; CALL; break; }             \
+        case QS_MODE_HOVER_GYM: { constexpr int M_ = QS_MODE_HOVER_GYM; CALL; break; }           \
+        case QS_MODE_TRAJ_GYM: { constexpr int M_ = QS_MODE_TRAJ_GYM; CALL; break; }             \
+        case QS_MODE_HOVER_BRAX: { constexpr int M_ = QS_MODE_HOVER_BRAX; CALL; break; }         \
+        case QS_MODE_MJX_PLAYGROUND: { constexpr int M_ = QS_MODE_MJX_PLAYGROUND; CALL; break; } \
+        default: return fail(QS_EINVAL, "unknown mode");                      \
+    }
+
+static int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return fail(QS_ECUDA, what, ce);
+    return QS_OK;
+}
+
+extern "C" {
+
+int qs_abi_version(void) { return QS_ABI_VERSION; }
+const char* qs_last_error_string(void) { return g_err; }
+int qs_params_size(void) { return (int)sizeof(QsParams); }
+uint64_t qs_launch_count(void) { return g_launches.load(); }
+
+int qs_create(const QsParams* params, int32_t num_envs, int32_t device, const float* target_table_host,
+              const double* waypoints_host, QsHandle* out) {
+    if (!params || !out || num_envs <= 0) return fail(QS_EINVAL, "qs_create: null argument or num_envs <= 0");
+    const QsParams& P = *params;
+    if (P.mode < 0 || P.mode > QS_MODE_MJX_PLAYGROUND) return fail(QS_EINVAL, "qs_create: bad mode");
+    const bool gym = (P.mode == QS_MODE_HOVER_GYM || P.mode == QS_MODE_TRAJ_GYM);
+    if (P.obs_dim != (gym ? 12 : 21)) return fail(QS_EINVAL, "qs_create: obs_dim does not match mode");
+    const bool table = (P.mode == QS_MODE_MJX_BRAX || P.mode == QS_MODE_MJX_PLAYGROUND);
+    if (table && (!target_table_host || P.max_episode_steps <= 0))
+        return fail(QS_EINVAL, "qs_create: mjx modes need a target table");
+    if (P.waypoint_mode) {
+        if (!gym || !waypoints_host || P.wp_num_shapes <= 0 || P.wp_num_shapes > QS_MAX_SHAPES)
+            return fail(QS_EINVAL, "qs_create: bad waypoint configuration");
+        for (int s = 0; s < P.wp_num_shapes; ++s)
+            if (P.wp_count[s] <= 0 || P.wp_count[s] > QS_MAX_WP) return fail(QS_EINVAL, "qs_create: bad wp_count");
+    }
+    if (!(P.dt > 0.f) || !(P.mass > 0.f)) return fail(QS_EINVAL, "qs_create: dt and mass must be positive");
+    int ndev = 0;
+    QS_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(QS_EINVAL, "qs_create: no such device");
+    QS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(QS_EUNSUPPORTED, "qs_create: libquadsim is built for sm_100a (B200) only");
+    QsEngine* e = new (std::nothrow) QsEngine();
+    if (!e) return fail(QS_ENOMEM, "qs_create: host allocation failed");
+    e->P = P; e->n = num_envs; e->device = device; e->target_table = nullptr; e->waypoints = nullptr; e->scratch = nullptr;
+    if (table) {
+        const size_t bytes = (size_t)P.max_episode_steps * 3 * sizeof(float);
+        if (cudaMalloc(&e->target_table, bytes) != cudaSuccess) { delete e; return fail(QS_ENOMEM, "cudaMalloc target table"); }
+        cudaMemcpy(e->target_table, target_table_host, bytes, cudaMemcpyHostToDevice);
+    }
+    if (P.waypoint_mode) {
+        const size_t bytes = (size_t)P.wp_num_shapes * QS_MAX_WP * 3 * sizeof(double);
+        if (cudaMalloc(&e->waypoints, bytes) != cudaSuccess) { cudaFree(e->target_table); delete e; return fail(QS_ENOMEM, "cudaMalloc waypoints"); }
+        cudaMemcpy(e->waypoints, waypoints_host, bytes, cudaMemcpyHostToDevice);
+    }
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) { cudaFree(e->target_table); cudaFree(e->waypoints); delete e; return fail(QS_ECUDA, "qs_create", ce); }
+    *out = e;
+    return QS_OK;
+}
+
+int qs_destroy(QsHandle h) {
+    if (!h) return QS_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->target_table); cudaFree(h->waypoints); cudaFree(h->scratch);
+    delete h;
+    return QS_OK;
+}
+
+int qs_num_envs(QsHandle h) { return h ? h->n : QS_EINVAL; }
+
+int qs_get_params(QsHandle h, QsParams* out) {
+    if (!h || !out) return fail(QS_EINVAL, "qs_get_params: null");
+    *out = h->P;
+    return QS_OK;
+}
+
+int qs_reset(QsHandle h, float* state, const uint8_t* mask, float* obs, float* first_state, void* stream) {
+    if (!h || !state) return fail(QS_EINVAL, "qs_reset: null");
+    cudaStream_t s = (cudaStream_t)stream;
+    QS_DISPATCH_MODE(h->P.mode, (qs::reset_kernel<M_><<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, s>>>(
+        h->P, h->tables(), h->n, state, mask, obs, first_state)));
+    return check_launch("reset_kernel");
+}
+
+int qs_step(QsHandle h, float* state, const float* action, float* obs, float* reward, float* done,
+            float* truncated, float* metrics, float* terminal_obs, const float* first_state, void* stream) {
+    if (!h || !state || !action || !obs || !reward || !done) return fail(QS_EINVAL, "qs_step: null");
+    if (h->P.auto_reset == QS_RESET_RESTORE_FIRST && !first_state)
+        return fail(QS_EINVAL, "qs_step: auto_reset=restore_first needs first_state");
+    if (((uintptr_t)action & 15u) != 0) return fail(QS_EINVAL, "qs_step: action must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    QS_DISPATCH_MODE(h->P.mode, (qs::step_kernel<M_><<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, s>>>(
+        h->P, h->tables(), h->n, state, (const float4*)action, obs, reward, done, truncated, metrics,
+        terminal_obs, first_state)));
+    return check_launch("step_kernel");
+}
+
+int qs_observe(QsHandle h, const float* state, const float* action, float* obs, float* reward, float* done,
+               void* stream) {
+    if (!h || !state) return fail(QS_EINVAL, "qs_observe: null");
+    if (action && ((uintptr_t)action & 15u) != 0) return fail(QS_EINVAL, "qs_observe: action must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    QS_DISPATCH_MODE(h->P.mode, (qs::observe_kernel<M_><<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, s>>>(
+        h->P, h->tables(), h->n, state, (const float4*)action, obs, reward, done)));
+    return check_launch("observe_kernel");
+}
+
+int qs_physics_step(QsHandle h, float* state, const float* ctrl, void* stream) {
+    if (!h || !state || !ctrl) return fail(QS_EINVAL, "qs_physics_step: null");
+    if (((uintptr_t)ctrl & 15u) != 0) return fail(QS_EINVAL, "qs_physics_step: ctrl must be 16-byte aligned");
+    qs::physics_kernel<<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, (cudaStream_t)stream>>>(
+        h->P, h->n, state, (const float4*)ctrl);
+    return check_launch("physics_kernel");
+}
+
+int qs_rollout_random(QsHandle h, float* state, int32_t T, uint32_t t0, float* stats, const float* first_state,
+                      void* stream) {
+    if (!h || !state || T < 0) return fail(QS_EINVAL, "qs_rollout_random: bad argument");
+    if (h->P.auto_reset == QS_RESET_RESTORE_FIRST && !first_state)
+        return fail(QS_EINVAL, "qs_rollout_random: auto_reset=restore_first needs first_state");
+    cudaStream_t s = (cudaStream_t)stream;
+    QS_DISPATCH_MODE(h->P.mode, (qs::rollout_random_kernel<M_><<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, s>>>(
+        h->P, h->tables(), h->n, state, T, t0, stats, first_state)));
+    return check_launch("rollout_random_kernel");
+}
+
+int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
+                 float* done_host, void* stream) {
+    if (!h || !state || !action_host || !obs_host || !reward_host || !done_host)
+        return fail(QS_EINVAL, "qs_step_host: null");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)h->n, D = (size_t)h->P.obs_dim;
+    if (!h->scratch) QS_CUDA(cudaMalloc(&h->scratch, n * (4 + D + 2) * sizeof(float)));
+    float* d_act = h->scratch; float* d_obs = d_act + 4 * n; float* d_rew = d_obs + D * n; float* d_done = d_rew + n;
+    QS_CUDA(cudaMemcpyAsync(d_act, action_host, 4 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = qs_step(h, state, d_act, d_obs, d_rew, d_done, nullptr, nullptr, nullptr, nullptr, stream);
+    if (rc != QS_OK) return rc;
+    QS_CUDA(cudaMemcpyAsync(obs_host, d_obs, D * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaMemcpyAsync(reward_host, d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaMemcpyAsync(done_host, d_done, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    QS_CUDA(cudaStreamSynchronize(s));
+    return QS_OK;
+}
+
+// ---- policy rollout + GAE: implemented in qs_rollout.cuh -------------------------------
+int qs_policy_param_count(const QsPolicyDesc* d) {
+    if (!d) return QS_EINVAL;
+    return qs::policy_param_count(*d);
+}
+
+int qs_rollout_policy(QsHandle h, float* state, const QsPolicyDesc* desc, const float* policy_params,
+                      int32_t T, uint32_t t0, float* last_obs, float* traj_obs, float* traj_act, float* traj_logp,
+                      float* traj_value, float* traj_reward, float* traj_done, float* traj_trunc,
+                      float* last_value, const float* first_state, void* stream) {
+    if (!h || !state || !desc || !policy_params || T <= 0) return fail(QS_EINVAL, "qs_rollout_policy: bad argument");
+    if (desc->obs_dim != h->P.obs_dim || desc->hidden != 128 || desc->act_dim != 4 || desc->dist < 0 || desc->dist > 1)
+        return fail(QS_EUNSUPPORTED, "qs_rollout_policy: policy must be obs_dim->128->128->4 (dist 0|1)");
+    if (h->P.auto_reset == QS_RESET_RESTORE_FIRST && !first_state)
+        return fail(QS_EINVAL, "qs_rollout_policy: auto_reset=restore_first needs first_state");
+    qs::RolloutBuffers rb{last_obs, traj_obs, traj_act, traj_logp, traj_value, traj_reward, traj_done, traj_trunc, last_value};
+    int rc = qs::launch_rollout_policy(h->P, h->tables(), h->n, state, *desc, policy_params, T, t0, rb, first_state,
+                                       (cudaStream_t)stream);
+    if (rc == -100) return fail(QS_EUNSUPPORTED, "qs_rollout_policy: unsupported mode/dist combination");
+    if (rc != 0) return fail(QS_ECUDA, "qs_rollout_policy: launch configuration failed", (cudaError_t)rc);
+    return check_launch("rollout_policy_kernel");
+}
+
+int qs_gae(int32_t T, int32_t B, const float* reward, const float* value, const float* done, const float* trunc,
+           const float* last_value, float gamma, float lam, int32_t brax_form, float* adv, float* ret, void* stream) {
+    if (T <= 0 || B <= 0 || !reward || !value || !done || !last_value || !adv || !ret)
+        return fail(QS_EINVAL, "qs_gae: bad argument");
+    if (brax_form && !trunc) return fail(QS_EINVAL, "qs_gae: brax form needs truncation flags");
+    qs::gae_kernel<<<nblocks(B, 128), 128, 0, (cudaStream_t)stream>>>(T, B, reward, value, done, trunc, last_value,
+                                                                      gamma, lam, brax_form, adv, ret);
+    return check_launch("gae_kernel");
+}
+
+}  // extern "C"

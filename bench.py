@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched quadrotor hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels via the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU port of the reference path
+
+A "step" is one pass of the hot path over one batch of synthetic input: one fused env-step
+launch (mixer -> MuJoCo-equivalent dynamics -> obs/reward/done -> Philox auto-reset) over
+2^20 hover envs per GPU (BASELINE.json configs[1]).  Envs shard across ranks with no data-path
+collective ("scaling": "weak"); NCCL is used only for the barrier and the max-over-ranks time.
+
+Printed JSON (one line, rank 0):  value = whole-job env-steps/s with inputs resident in HBM;
+e2e = the same through the host-buffer C-ABI call (H2D actions, D2H obs/reward/done inside the
+timed region); roofline = HBM roofline of the step kernel; cpu_baseline = oracle/cpu_ref.c timed on
+the host cores; extra keys `resident` (T-step state-resident dyn-only kernel) and `rollout`
+(2x128 actor-critic policy rollout + GAE, BASELINE.json configs[2]).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (dyn-only hover step, 2^20 envs/GPU)"
+UNIT = "env-steps/s"
+NUM_ENVS = 1 << 20
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                d = json.load(f)
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.samples:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            for ts, line in self.samples[-3:]:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[0])); mx = float(parts[1])
+                except Exception:
+                    pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(cfg, n_envs=1 << 16, target_seconds=12.0, threads=0):
+    """oracle/cpu_ref.c (kind "port") on a bounded sample of the same workload, all host threads."""
+    from oracle import cpu_ref
+    from uav_reinforcement_learning_control_b200 import model as M
+    tree = M.load_mjcf(M.default_model_path())
+    hr = cpu_ref.HoverRollout(tree, cfg, n_envs)
+    cores = threads or hr.max_threads()
+    hr.run(1, seed=0, threads=cores)                       # warm-up + reset
+    steps_done, t0 = 0, time.perf_counter()
+    while True:
+        hr.run(4, seed=steps_done + 1, threads=cores)
+        steps_done += 4
+        el = time.perf_counter() - t0
+        if el >= target_seconds or steps_done >= 512:
+            break
+    return {"value": n_envs * steps_done / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_envs} hover envs x {steps_done} steps, random actions, auto-reset, float64 "
+                      f"MuJoCo-pipeline restatement (oracle/cpu_ref.c), {el:.1f} s"}, el, steps_done
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference path, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from uav_reinforcement_learning_control_b200 import config as Q
+    cfg = Q.EnvConfig.north_star(seed=0)
+    n = 1 << 16
+    from oracle import cpu_ref
+    from uav_reinforcement_learning_control_b200 import model as M
+    tree = M.load_mjcf(M.default_model_path())
+    hr = cpu_ref.HoverRollout(tree, cfg, n)
+    cores = hr.max_threads()
+    sub = 4                                                # one "step" here = a bounded sample: n envs x sub env-steps
+    for _ in range(max(args.warmup, 1)):
+        hr.run(sub, seed=1, threads=cores)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        hr.run(sub, seed=2 + k, threads=cores)
+    el = time.perf_counter() - t0
+    value = n * sub * args.steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "hover env dynamics-only step, 1M envs on 1xB200 (BASELINE.json configs[1]); "
+                               "reference arm = CPU port on a bounded sample", "num_envs_per_gpu": NUM_ENVS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} hover envs x {sub} env-steps per step x {args.steps} steps (oracle/cpu_ref.c; "
+                                   "mujoco/jax are not installable here, so the port stands in for the reference)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--num-envs", type=int, default=NUM_ENVS, help="envs per GPU")
+    ap.add_argument("--no-extras", action="store_true", help="skip resident / rollout / cpu legs")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from uav_reinforcement_learning_control_b200 import config as Q
+    from uav_reinforcement_learning_control_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = args.num_envs
+    K, W = args.steps, args.warmup
+    # global env ids: rank r owns [r*n, (r+1)*n) -> results identical for any sharding
+    cfg = Q.EnvConfig.north_star(seed=0, env_id_offset=rank * n)
+    eng = Engine(cfg, n, device=local)
+    state = eng.new_state()
+    obs = torch.empty(n, 12, device=dev); rew = torch.empty(n, device=dev); done = torch.empty(n, device=dev)
+    eng.reset(state, obs=obs)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    # a ring of pre-generated random action batches (synthetic uniformly randomised policies)
+    acts = [torch.rand(n, 4, device=dev, generator=gen) * 2 - 1 for _ in range(4)]
+    stream = torch.cuda.current_stream(dev)
+
+    # ---------------------------------------------------------------- value: HBM-resident API-mode step
+    for i in range(W):
+        eng.step(state, acts[i % 4], obs=obs, reward=rew, done=done)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    e0.record(stream)
+    for i in range(K):
+        eng.step(state, acts[i % 4], obs=obs, reward=rew, done=done)
+    e1.record(stream)
+    barrier()
+    wall1 = time.time()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = sum_over_ranks(eng.launch_count() - l0)
+    # keep the GPU busy a little longer if the timed region was too short for nvidia-smi to see it
+    clocks = None
+    if sampler:
+        if wall1 - wall0 < 0.5:
+            tl0 = time.time()
+            while time.time() - tl0 < 0.6:
+                for i in range(50):
+                    eng.step(state, acts[i % 4], obs=obs, reward=rew, done=done)
+                torch.cuda.synchronize()
+            wall1 = time.time()
+        clocks = sampler.stop(wall0, wall1)
+    value = world * n * K / (ms * 1e-3)
+    finite = bool(torch.isfinite(obs).all().item())
+
+    # bytes per env-step actually required by the algorithm for this config (DESIGN.md "Traffic"):
+    # state words in/out (21 qpos/qvel + 3 target + step_count + episode [+ voltage]) + action 16 + obs 48 + reward 4 + done 4
+    words = 21 + 3 + 1 + 1 + (1 if cfg.battery else 0)
+    bytes_per = 2 * 4 * words + 16 + 48 + 8
+    peak, peak_src = measured_peaks()
+    achieved = bytes_per * n * K / (ms * 1e-3) / 1e9          # per GPU (max-over-ranks time)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "qs::step_kernel<QS_MODE_HOVER_GYM>", "bytes_per_env_step": bytes_per,
+                "peak_source": peak_src}
+
+    # ---------------------------------------------------------------- e2e: host buffers through the C ABI
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory()
+    h_act = [(torch.rand(n, 4) * 2 - 1).pin_memory() for _ in range(2)]
+    h_obs, h_rew, h_done = pin(n, 12), pin(n), pin(n)
+    Ke = max(5, min(K, 40))
+    for i in range(3):
+        eng.step_host(state, h_act[i % 2].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+    barrier()
+    e0.record(stream)
+    for i in range(Ke):
+        eng.step_host(state, h_act[i % 2].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"value": world * n * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 * n,
+           "d2h_bytes_per_step": (48 + 8) * n, "steps": Ke, "ms_per_step": ms_e2e / Ke,
+           "api": "qs_step_host (C ABI, pinned host buffers; what HoverVecEnv.step(numpy) calls)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "hover env dynamics-only step, 1M envs on 1xB200 (BASELINE.json configs[1]): "
+                               "HoverEnv semantics, random actions, Philox auto-reset, one fused launch per step",
+                   "num_envs_per_gpu": n, "global_envs": world * n, "mode": "hover_gym/north_star",
+                   "l2": f"working set {bytes_per * n / 1e6:.0f} MB per launch > 126 MB L2 (no flush needed)",
+                   "parallelism": f"env-shard x{world}, no per-step communication"},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "outputs_finite": finite,
+    }
+
+    # ---------------------------------------------------------------- extras (rank-local, reported for context)
+    if not args.no_extras:
+        # (ii) state-resident dyn-only rollout: T steps per launch, in-kernel Philox actions
+        T = 64
+        stats = torch.zeros(4, n, device=dev)
+        eng.rollout_random(state, T, t0=0, stats=stats)
+        barrier()
+        reps = 3
+        e0.record(stream)
+        for r in range(reps):
+            eng.rollout_random(state, T, t0=(r + 1) * T, stats=stats)
+        e1.record(stream)
+        barrier()
+        ms_r = max_over_ranks(e0.elapsed_time(e1))
+        line["resident"] = {"value": world * n * T * reps / (ms_r * 1e-3), "unit": UNIT, "steps_per_launch": T,
+                            "episodes_finished": sum_over_ranks(stats[1].sum().item()),
+                            "note": "dyn-only, state in registers, obs/reward/done computed every step"}
+        # policy rollout, BASELINE.json configs[2]: 8192 envs x 1024 steps, 2x128 ReLU actor-critic + GAE
+        nb, Tp = 8192, 1024
+        cfg_p = Q.EnvConfig.north_star(seed=1, env_id_offset=rank * nb)
+        eng_p = Engine(cfg_p, nb, device=local)
+        st_p = eng_p.new_state()
+        eng_p.reset(st_p)
+        params = make_policy_params(eng_p, torch, dev, seed=0)
+        buf = eng_p.rollout_policy(st_p, params, T=Tp, t0=0, dist=0)
+        adv, ret = eng_p.gae(buf["reward"], buf["value"], buf["done"], buf["trunc"], buf["last_value"], 0.99, 0.95)
+        barrier()
+        e0.record(stream)
+        buf = eng_p.rollout_policy(st_p, params, T=Tp, t0=Tp, dist=0, buffers=buf)
+        eg = torch.cuda.Event(enable_timing=True)
+        eg.record(stream)
+        eng_p.gae(buf["reward"], buf["value"], buf["done"], buf["trunc"], buf["last_value"], 0.99, 0.95, adv=adv, ret=ret)
+        e1.record(stream)
+        barrier()
+        ms_p = max_over_ranks(e0.elapsed_time(e1))
+        ms_roll = e0.elapsed_time(eg)
+        flop = 73984.0
+        line["rollout"] = {
+            "value": world * nb * Tp / (ms_p * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb, "T": Tp,
+            "ms_rollout": ms_roll, "ms_gae": ms_p - ms_roll,
+            "traj_hbm_gbs": (80.0 * nb * Tp) / (ms_roll * 1e-3) / 1e9,
+            "policy_tflops_fp32": flop * nb * Tp / (ms_roll * 1e-3) / 1e12,
+            "note": "2x128 ReLU actor + critic (fp32 FMA path), Gaussian sampling, trajectories written once, GAE scan"}
+        del eng_p
+        # big-batch policy rollout (per-GPU shard of configs[4]): 2^18 envs x 32 steps
+        nb2, T2 = 1 << 18, 32
+        cfg_q = Q.EnvConfig.north_star(seed=2, env_id_offset=rank * nb2)
+        eng_q = Engine(cfg_q, nb2, device=local)
+        st_q = eng_q.new_state()
+        eng_q.reset(st_q)
+        bufq = eng_q.rollout_policy(st_q, params, T=T2, t0=0, dist=0)
+        barrier()
+        e0.record(stream)
+        eng_q.rollout_policy(st_q, params, T=T2, t0=T2, dist=0, buffers=bufq)
+        e1.record(stream)
+        barrier()
+        ms_q = max_over_ranks(e0.elapsed_time(e1))
+        line["rollout_large"] = {"value": world * nb2 * T2 / (ms_q * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb2,
+                                 "T": T2, "policy_tflops_fp32": flop * nb2 * T2 / (ms_q * 1e-3) / 1e12}
+        del eng_q, bufq
+        if rank == 0:
+            cb, _, _ = cpu_baseline(Q.EnvConfig.north_star(seed=0), target_seconds=args.cpu_seconds)
+            line["cpu_baseline"] = cb
+    if rank == 0 and "cpu_baseline" not in line:
+        cb, _, _ = cpu_baseline(Q.EnvConfig.north_star(seed=0), n_envs=1 << 14, target_seconds=3.0)
+        line["cpu_baseline"] = cb
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def make_policy_params(eng, torch, dev, seed=0, dist=0):
+    """Random-init 2x128 ReLU actor-critic in the packed layout of qs_policy_param_count (lecun-uniform)."""
+    D, H, A = eng.obs_dim, 128, 4
+    Ao = 2 * A if dist == 1 else A
+    g = torch.Generator(device="cpu"); g.manual_seed(seed)
+
+    def lin(i, o):
+        lim = (3.0 / i) ** 0.5
+        return (torch.rand(i, o, generator=g) * 2 - 1) * lim, torch.zeros(o)
+    parts = []
+    for out in (Ao, 1):
+        for (i, o) in ((D, H), (H, H), (H, out)):
+            w, b = lin(i, o)
+            parts += [w.reshape(-1), b]
+    if dist == 0:
+        parts.append(torch.full((A,), -0.5))          # log_std
+    parts += [torch.zeros(D), torch.ones(D)]           # obs mean, inv std
+    p = torch.cat(parts).to(dev)
+    assert p.numel() == eng.policy_param_count(dist), (p.numel(), eng.policy_param_count(dist))
+    return p.contiguous()
+
+
+if __name__ == "__main__":
+    main()

@@ -158,3 +158,66 @@ def random_states(n, seed=0, pos=1.5, vel=5.0, omega=10.0, spin=30.0, theta=50.0
     qvel[:, 0:3] = rng.uniform(-vel, vel, (n, 3)); qvel[:, 3:6] = rng.uniform(-omega, omega, (n, 3))
     qvel[:, 6:10] = rng.uniform(-spin, spin, (n, 4))
     return qpos.astype(np.float32), qvel.astype(np.float32)
+
+
+class GpuBackend:
+    """Same interface as HostHarness, but through the real library: torch tensors -> C ABI -> sm_100a kernels."""
+
+    def __init__(self, cfg, num_envs=None):
+        self.cfg = cfg
+        self.D = cfg.obs_dim
+        self._eng = None
+        self._n = None
+
+    def _engine(self, n):
+        from uav_reinforcement_learning_control_b200.engine import Engine
+        if self._eng is None or self._n != n:
+            self._eng = Engine(self.cfg, n, device=0)
+            self._n = n
+        return self._eng
+
+    def _up(self, a):
+        import torch
+        return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+    def step(self, st, action, first=None, want_term=False):
+        import torch
+        n = st.shape[1]
+        eng = self._engine(n)
+        d_st = self._up(st); d_act = self._up(np.asarray(action, dtype=np.float32)); d_first = self._up(first)
+        trunc = torch.zeros(n, device="cuda"); met = torch.zeros(4, n, device="cuda")
+        term = torch.full((n, self.D), float("nan"), device="cuda") if want_term else None
+        obs, rew, done = eng.step(d_st, d_act, truncated=trunc, metrics=met, terminal_obs=term, first_state=d_first)
+        torch.cuda.synchronize()
+        st[:] = d_st.cpu().numpy()
+        return dict(obs=obs.cpu().numpy(), reward=rew.cpu().numpy(), done=done.cpu().numpy(),
+                    truncated=trunc.cpu().numpy(), metrics=met.cpu().numpy(),
+                    terminal_obs=None if term is None else term.cpu().numpy())
+
+    def reset(self, st, mask=None, want_first=False):
+        import torch
+        n = st.shape[1]
+        eng = self._engine(n)
+        d_st = self._up(st)
+        d_mask = None if mask is None else self._up(np.asarray(mask, dtype=np.uint8))
+        first = torch.zeros(21, n, device="cuda") if want_first else None
+        obs = torch.zeros(n, self.D, device="cuda")
+        eng.reset(d_st, mask=d_mask, obs=obs, first_state=first)
+        torch.cuda.synchronize()
+        st[:] = d_st.cpu().numpy()
+        return obs.cpu().numpy(), None if first is None else first.cpu().numpy()
+
+    def observe(self, st, action=None):
+        import torch
+        eng = self._engine(st.shape[1])
+        obs, rew, done = eng.observe(self._up(st), None if action is None else self._up(np.asarray(action, np.float32)))
+        torch.cuda.synchronize()
+        return obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+
+    def physics(self, st, ctrl):
+        import torch
+        eng = self._engine(st.shape[1])
+        d_st = self._up(st)
+        eng.physics_step(d_st, self._up(np.asarray(ctrl, np.float32)))
+        torch.cuda.synchronize()
+        st[:] = d_st.cpu().numpy()

@@ -44,7 +44,8 @@ static void reset_all(const QsParams& P, const Tables& T, int n, float* state, c
         if (mask && !mask[i]) continue;
         Env e;
         load_env<MODE>(P, state, n, i, e, true);
-        reset_env<MODE>(P, T, P.env_id_offset + (uint32_t)i, e);
+        float rpy0[3];
+        reset_env<MODE>(P, T, P.env_id_offset + (uint32_t)i, e, rpy0);
         store_env<MODE>(P, state, n, i, e);
         if (first) {
             const float x[21] = {e.b.p[0], e.b.p[1], e.b.p[2], e.b.q[0], e.b.q[1], e.b.q[2], e.b.q[3],

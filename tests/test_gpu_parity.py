@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from . import parity_cases as pc
-from .util import GpuBackend, HostHarness, assert_close, make_planes, planes_view, random_states
+from .util import ATOL_QVEL, GpuBackend, HostHarness, assert_close, make_planes, planes_view, random_states
 
 pytestmark = pytest.mark.gpu
 
@@ -52,4 +52,4 @@ def test_physics_matches_host_build():
     HostHarness(cfg).physics(st_h, ctrl)
     pg, ph = planes_view(st_g), planes_view(st_h)
     assert_close(pg["qpos"], ph["qpos"], what="gpu vs host qpos", scale=qpos)
-    assert_close(pg["qvel"], ph["qvel"], what="gpu vs host qvel", scale=qvel)
+    assert_close(pg["qvel"], ph["qvel"], what="gpu vs host qvel", scale=qvel, atol=ATOL_QVEL)

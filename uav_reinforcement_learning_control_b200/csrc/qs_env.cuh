@@ -38,6 +38,7 @@ struct StepOut {
     float reward, done, truncated;
     float pos_error, reward_hover, reward_action;
     bool finished;        // episode ended this step (terminal_obs is meaningful)
+    bool needs_reset;     // DEFER_RESET only: caller must run reset_env + compute_obs for this env
 };
 
 // device-resident tables owned by the engine handle
@@ -291,9 +292,13 @@ QS_HD void evaluate(const QsParams& P, const Tables& T, Env& e, const float* a, 
 // ---------------------------------------------------------------------------------------
 // reset: Philox(seed; global env id, episode, block, stream 0)
 // ---------------------------------------------------------------------------------------
+// rpy (gym modes): the Euler angles of the new attitude.  They are the drawn angles themselves, so the
+// reset observation needs no quaternion -> Euler round trip (the reference's round trip through
+// scipy changes them by < 1e-7 rad).
 template <int MODE>
-QS_HD void reset_env(const QsParams& P, const Tables& T, uint32_t gid, Env& e) {
+QS_HD void reset_env(const QsParams& P, const Tables& T, uint32_t gid, Env& e, float rpy[3]) {
     using M = ModeTraits<MODE>;
+    rpy[0] = 0.f; rpy[1] = 0.f; rpy[2] = 0.f;
     e.step_count = 0;
     e.ep_steps = 0;
     e.done_prev = 0.f;
@@ -327,6 +332,7 @@ QS_HD void reset_env(const QsParams& P, const Tables& T, uint32_t gid, Env& e) {
         }
         e.b.p[0] = s12[0]; e.b.p[1] = s12[1]; e.b.p[2] = s12[2];
         rpy_to_quat(&s12[3], e.b.q);
+        rpy[0] = s12[3]; rpy[1] = s12[4]; rpy[2] = s12[5];
         e.b.v[0] = s12[6]; e.b.v[1] = s12[7]; e.b.v[2] = s12[8];
         e.b.w[0] = s12[9]; e.b.w[1] = s12[10]; e.b.w[2] = s12[11];
         if constexpr (MODE == QS_MODE_HOVER_GYM) {
@@ -407,7 +413,9 @@ QS_HD bool waypoint_advance(const QsParams& P, const Tables& T, uint32_t gid, En
 // (after auto-reset if one happened); term_obs (may be null) the pre-reset observation.
 // first: pointer to this env's first_state column (plane stride `nenv`), RESTORE_FIRST only.
 // ---------------------------------------------------------------------------------------
-template <int MODE>
+// DEFER_RESET: the Philox re-sampling of a finished gym env is NOT done here; the caller sees
+// o.needs_reset and performs it (the kernels compact those lanes per block, see block_autoreset).
+template <int MODE, bool DEFER_RESET = false>
 QS_HD void env_step(const QsParams& P, const Tables& T, uint32_t gid, Env& e, const float a[4],
                     float* obs, float* term_obs, const float* first, int nenv, StepOut& o) {
     using M = ModeTraits<MODE>;
@@ -425,6 +433,7 @@ QS_HD void env_step(const QsParams& P, const Tables& T, uint32_t gid, Env& e, co
     evaluate<MODE>(P, T, e, a, rpy, o);
     compute_obs<MODE>(P, e, rpy, obs);
     o.finished = false;
+    o.needs_reset = false;
 
     if constexpr (M::kGym) {
         bool lap = false;
@@ -438,9 +447,12 @@ QS_HD void env_step(const QsParams& P, const Tables& T, uint32_t gid, Env& e, co
             if (P.auto_reset == QS_RESET_RESAMPLE) {
                 // VecEnv semantics: the returned observation is the first one of the next episode
                 e.episode += 1u;
-                reset_env<MODE>(P, T, gid, e);
-                quat_to_rpy(e.b.q, rpy);
-                compute_obs<MODE>(P, e, rpy, obs);
+                if constexpr (DEFER_RESET) {
+                    o.needs_reset = true;
+                } else {
+                    reset_env<MODE>(P, T, gid, e, rpy);
+                    compute_obs<MODE>(P, e, rpy, obs);
+                }
             }
         }
     } else if constexpr (M::kBrax) {

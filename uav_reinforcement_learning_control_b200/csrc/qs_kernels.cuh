@@ -10,7 +10,13 @@
 
 namespace qs {
 
-constexpr int kBlock = 128;
+#ifndef QS_STEP_BLOCK
+#define QS_STEP_BLOCK 128
+#endif
+#ifndef QS_STEP_MIN_BLOCKS
+#define QS_STEP_MIN_BLOCKS 6   /* <= 80 registers: 24 warps/SM; measured best on B200 (profiles/README.md) */
+#endif
+constexpr int kBlock = QS_STEP_BLOCK;
 
 // Block-cooperative, fully coalesced store of per-thread rows obs_local[D] to out[n][D]:
 // rows are staged in shared memory (row stride D+1 when D is even to avoid bank conflicts)
@@ -34,29 +40,104 @@ __device__ __forceinline__ void store_rows(float* __restrict__ out, int n, int b
     __syncthreads();
 }
 
+// ------------------------------------------------------------------------------ compacted auto-reset
+// Under random (or early-training) policies ~10 % of the envs finish an episode every step, so nearly
+// every warp would run the ~570-instruction Philox reset path with 3 of 32 lanes active.  Instead the
+// finished lanes enqueue themselves in shared memory, the first `count` threads of the block perform
+// the resets densely (one env per lane), and the owners read their new state back.  Results are
+// identical to the inline path (same reset_env / compute_obs source).
+constexpr int kSlotF = 21 + 3 + 12;     // qpos/qvel, target, obs (gym modes only)
+
+struct ResetScratch {
+    int count[2];
+    int owner[1];                       // [NT] followed by episode[NT] and slots[NT][kSlotF] (carved by the caller)
+};
+
+template <int MODE, int NT>
+__device__ __forceinline__ void block_autoreset(const QsParams& P, const Tables& T, uint32_t gid_block_first,
+                                                Env& e, float* obs, bool need, int parity,
+                                                int* s_count /*[2]*/, int* s_owner /*[NT]*/, uint32_t* s_epi /*[NT]*/,
+                                                float* s_slot /*[NT][kSlotF]*/) {
+    static_assert(ModeTraits<MODE>::kGym, "Philox re-sampling exists in the gym modes only");
+    const int tid = threadIdx.x;
+    int slot = -1;
+    if (need) {
+        slot = atomicAdd(&s_count[parity], 1);
+        s_owner[slot] = tid;
+        s_epi[slot] = e.episode;
+    }
+    if (tid == 0) s_count[parity ^ 1] = 0;          // arm the other counter for the next call
+    __syncthreads();
+    const int cnt = s_count[parity];
+    if (cnt == 0) return;                           // block-uniform
+    for (int j = tid; j < cnt; j += NT) {
+        Env r;
+        r.episode = s_epi[j];
+        r.wp_idx = 0; r.wp_reached = 0; r.laps = 0;
+        float rpy[3];
+        reset_env<MODE>(P, T, gid_block_first + (uint32_t)s_owner[j], r, rpy);
+        float o_[12];
+        compute_obs<MODE>(P, r, rpy, o_);
+        float* d = s_slot + j * kSlotF;
+        d[0] = r.b.p[0]; d[1] = r.b.p[1]; d[2] = r.b.p[2];
+        d[3] = r.b.q[0]; d[4] = r.b.q[1]; d[5] = r.b.q[2]; d[6] = r.b.q[3];
+        d[7] = r.b.v[0]; d[8] = r.b.v[1]; d[9] = r.b.v[2];
+        d[10] = r.b.w[0]; d[11] = r.b.w[1]; d[12] = r.b.w[2];
+        d[13] = r.target[0]; d[14] = r.target[1]; d[15] = r.target[2];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) d[16 + k] = o_[k];
+    }
+    __syncthreads();
+    if (need) {
+        const float* d = s_slot + slot * kSlotF;
+        e.b.p[0] = d[0]; e.b.p[1] = d[1]; e.b.p[2] = d[2];
+        e.b.q[0] = d[3]; e.b.q[1] = d[4]; e.b.q[2] = d[5]; e.b.q[3] = d[6];
+        e.b.v[0] = d[7]; e.b.v[1] = d[8]; e.b.v[2] = d[9];
+        e.b.w[0] = d[10]; e.b.w[1] = d[11]; e.b.w[2] = d[12];
+        e.target[0] = d[13]; e.target[1] = d[14]; e.target[2] = d[15];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { e.b.th[k] = 0.f; e.b.s[k] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) obs[k] = d[16 + k];
+        e.step_count = 0; e.ep_steps = 0; e.done_prev = 0.f; e.voltage = P.v_nominal;
+    }
+}
+
+// whether this launch uses the compacted path (block-uniform)
+template <int MODE>
+__device__ __forceinline__ bool use_compaction(const QsParams& P) {
+    return ModeTraits<MODE>::kGym && P.auto_reset == QS_RESET_RESAMPLE && !P.waypoint_mode;
+}
+
 // ------------------------------------------------------------------------------ step
 template <int MODE>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, QS_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restrict__ state,
             const float4* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
             float* __restrict__ done, float* __restrict__ trunc, float* __restrict__ metrics,
             float* __restrict__ term_obs, const float* __restrict__ first) {
     constexpr int D = ModeTraits<MODE>::kObsDim;
-    __shared__ float sm[kBlock * (D + 1)];
+    constexpr bool kGym = ModeTraits<MODE>::kGym;
+    __shared__ float sm[kBlock * (kGym ? kSlotF : D + 1)];   // reset slots, then re-used as the obs staging tile
+    __shared__ int s_count[2];
+    __shared__ int s_owner[kGym ? kBlock : 1];
+    __shared__ uint32_t s_epi[kGym ? kBlock : 1];
     const int block_first = blockIdx.x * kBlock;
     const int i = block_first + threadIdx.x;
     const bool valid = i < n;
+    if (kGym && threadIdx.x == 0) { s_count[0] = 0; s_count[1] = 0; }
+    if (kGym) __syncthreads();
     float o_[D];
+    Env e;
+    StepOut so;
+    so.needs_reset = false;
     if (valid) {
-        Env e;
         load_env<MODE>(P, state, n, i, e);
         const float4 a4 = action[i];
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-        StepOut so;
         float tobs[D];
-        env_step<MODE>(P, T, P.env_id_offset + (uint32_t)i, e, a, o_, term_obs ? tobs : nullptr,
-                       first ? first + i : nullptr, n, so);
-        store_env<MODE>(P, state, n, i, e);
+        env_step<MODE, kGym>(P, T, P.env_id_offset + (uint32_t)i, e, a, o_, term_obs ? tobs : nullptr,
+                             first ? first + i : nullptr, n, so);
         reward[i] = so.reward;
         done[i] = so.done;
         if (trunc) trunc[i] = so.truncated;
@@ -72,6 +153,23 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restri
 #pragma unroll
         for (int k = 0; k < D; ++k) o_[k] = 0.f;
     }
+    if constexpr (kGym) {
+        if (P.auto_reset == QS_RESET_RESAMPLE) {
+            if (P.waypoint_mode) {
+                // waypoint resets draw nothing: do them inline
+                if (so.needs_reset) {
+                    float rpy[3];
+                    reset_env<MODE>(P, T, P.env_id_offset + (uint32_t)i, e, rpy);
+                    compute_obs<MODE>(P, e, rpy, o_);
+                }
+            } else {
+                block_autoreset<MODE, kBlock>(P, T, P.env_id_offset + (uint32_t)block_first, e, o_, so.needs_reset, 0,
+                                              s_count, s_owner, s_epi, sm);
+                __syncthreads();                    // slots are dead; sm becomes the obs staging tile
+            }
+        }
+    }
+    if (valid) store_env<MODE>(P, state, n, i, e);
     store_rows<D>(obs, n, block_first, o_, valid, sm);
 }
 
@@ -86,7 +184,8 @@ reset_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restr
     if (mask && !mask[i]) return;
     Env e;
     load_env<MODE>(P, state, n, i, e, true);      // keeps episode / lifetime counters
-    reset_env<MODE>(P, T, P.env_id_offset + (uint32_t)i, e);
+    float rpy[3];
+    reset_env<MODE>(P, T, P.env_id_offset + (uint32_t)i, e, rpy);
     store_env<MODE>(P, state, n, i, e);
     if (first) {
         const float x[21] = {e.b.p[0], e.b.p[1], e.b.p[2], e.b.q[0], e.b.q[1], e.b.q[2], e.b.q[3],
@@ -96,8 +195,6 @@ reset_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restr
         for (int k = 0; k < 21; ++k) first[(size_t)k * n + i] = x[k];
     }
     if (obs) {
-        float rpy[3] = {0.f, 0.f, 0.f};
-        if constexpr (ModeTraits<MODE>::kGym) quat_to_rpy(e.b.q, rpy);
         float o_[D];
         compute_obs<MODE>(P, e, rpy, o_);
 #pragma unroll
@@ -149,34 +246,60 @@ physics_kernel(const __grid_constant__ QsParams P, int n, float* __restrict__ st
 // T env steps per launch with state in registers; actions U(-1,1)^4 from Philox stream 2 keyed by
 // (global env id, global step index).  stats[4][n] += (sum reward, episodes finished, obs checksum, steps).
 template <int MODE>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, QS_STEP_MIN_BLOCKS)
 rollout_random_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restrict__ state, int steps,
                       uint32_t t0, float* __restrict__ stats, const float* __restrict__ first) {
     constexpr int D = ModeTraits<MODE>::kObsDim;
-    const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
+    constexpr bool kGym = ModeTraits<MODE>::kGym;
+    __shared__ float sm[kGym ? kBlock * kSlotF : 1];
+    __shared__ int s_count[2];
+    __shared__ int s_owner[kGym ? kBlock : 1];
+    __shared__ uint32_t s_epi[kGym ? kBlock : 1];
+    const int block_first = blockIdx.x * kBlock;
+    const int i = block_first + threadIdx.x;
+    const bool valid = i < n;
+    if (threadIdx.x == 0) { s_count[0] = 0; s_count[1] = 0; }
+    __syncthreads();
+    const bool compact = use_compaction<MODE>(P);
     Env e;
-    load_env<MODE>(P, state, n, i, e);
+    if (valid) load_env<MODE>(P, state, n, i, e);
     const uint32_t gid = P.env_id_offset + (uint32_t)i;
     float sum_r = 0.f, fin = 0.f, chk = 0.f;
     for (int t = 0; t < steps; ++t) {
-        const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_ACTION}, P.seed_lo, P.seed_hi);
-        const float a[4] = {uniform_(r.x, -1.f, 1.f), uniform_(r.y, -1.f, 1.f), uniform_(r.z, -1.f, 1.f),
-                            uniform_(r.w, -1.f, 1.f)};
         float o_[D];
         StepOut so;
-        env_step<MODE>(P, T, gid, e, a, o_, nullptr, first ? first + i : nullptr, n, so);
-        sum_r += so.reward;
-        fin += so.finished ? 1.f : 0.f;
-        float c = 0.f;
+        so.needs_reset = false;
+        if (valid) {
+            const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_ACTION}, P.seed_lo, P.seed_hi);
+            const float a[4] = {uniform_(r.x, -1.f, 1.f), uniform_(r.y, -1.f, 1.f), uniform_(r.z, -1.f, 1.f),
+                                uniform_(r.w, -1.f, 1.f)};
+            env_step<MODE, kGym>(P, T, gid, e, a, o_, nullptr, first ? first + i : nullptr, n, so);
+            sum_r += so.reward;
+            fin += so.finished ? 1.f : 0.f;
+        }
+        if constexpr (kGym) {
+            if (compact) {
+                block_autoreset<MODE, kBlock>(P, T, P.env_id_offset + (uint32_t)block_first, e, o_, so.needs_reset, t & 1,
+                                              s_count, s_owner, s_epi, sm);
+            } else if (so.needs_reset) {
+                float rpy[3];
+                reset_env<MODE>(P, T, gid, e, rpy);
+                compute_obs<MODE>(P, e, rpy, o_);
+            }
+        }
+        if (valid) {
+            float c = 0.f;
 #pragma unroll
-        for (int k = 0; k < D; ++k) c += o_[k];
-        chk += c;
+            for (int k = 0; k < D; ++k) c += o_[k];
+            chk += c;
+        }
     }
-    store_env<MODE>(P, state, n, i, e);
-    if (stats) {
-        stats[i] += sum_r; stats[(size_t)n + i] += fin; stats[2 * (size_t)n + i] += chk;
-        stats[3 * (size_t)n + i] += (float)steps;
+    if (valid) {
+        store_env<MODE>(P, state, n, i, e);
+        if (stats) {
+            stats[i] += sum_r; stats[(size_t)n + i] += fin; stats[2 * (size_t)n + i] += chk;
+            stats[3 * (size_t)n + i] += (float)steps;
+        }
     }
 }
 

@@ -323,9 +323,13 @@ inline int launch_rollout_policy(const QsParams& P, const Tables& T, int n, floa
     if (P.mode == QS_MODE_HOVER_GYM && d.dist == 0) { QS_RL(QS_MODE_HOVER_GYM, 0); }
     if (P.mode == QS_MODE_HOVER_GYM && d.dist == 1) { QS_RL(QS_MODE_HOVER_GYM, 1); }
     if (P.mode == QS_MODE_TRAJ_GYM && d.dist == 0) { QS_RL(QS_MODE_TRAJ_GYM, 0); }
-    if (P.mode == QS_MODE_MJX_BRAX && d.dist == 1) { QS_RL(QS_MODE_MJX_BRAX, 1); }
-    if (P.mode == QS_MODE_MJX_BRAX && d.dist == 0) { QS_RL(QS_MODE_MJX_BRAX, 0); }
 #undef QS_RL
+    // 21-D observations: the fp32 weights alone take 159 KB of shared memory, so only the 32-env tile
+    // (2 x [128][36] activation buffers) fits in the 227 KB a CTA may use
+    if (P.mode == QS_MODE_MJX_BRAX && d.dist == 1)
+        return launch_rollout_t<QS_MODE_MJX_BRAX, 1, 32>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    if (P.mode == QS_MODE_MJX_BRAX && d.dist == 0)
+        return launch_rollout_t<QS_MODE_MJX_BRAX, 0, 32>(P, T, n, state, params, steps, t0, opt, rb, first, s);
     return -100;
 }
 

@@ -52,7 +52,7 @@ def load_library(path: str | None = None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    path = path or LIB_PATH
+    path = path or os.environ.get("QS_LIB_PATH") or LIB_PATH     # QS_LIB_PATH: tuning variants for A/B runs
     if not os.path.exists(path):
         raise QuadSimError(f"{path} is missing: run `python -m uav_reinforcement_learning_control_b200.build` "
                            "(or __graft_entry__.build()).  There is no CPU fallback.")

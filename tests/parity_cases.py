@@ -197,3 +197,75 @@ def check_observe_bit_exact_masks(backend_factory, name, n=8192, seed=3):
     f = np.isfinite(ev["reward"])
     assert_close(rew[f], ev["reward"][f], what=f"{name}: reward on injected state", rtol=2e-5, atol=2e-6)
     return int(ev["done"].sum())
+
+
+def check_waypoints(backend_factory, n=600, steps=6, auto_reset=True):
+    """evaluate.py:535-557 waypoint advance: indices, reach counters, laps and targets bit-exact vs the oracle,
+    over several steps with states planted inside / outside / exactly on the reach radius."""
+    from uav_reinforcement_learning_control_b200 import trajectories as TJ
+    tables = TJ.default_tables(0.5)
+    cfg = Q.EnvConfig.waypoint_eval(tables, auto_reset=Q.RESET_RESAMPLE if auto_reset else Q.RESET_NONE,
+                                    env_id_offset=4, max_episode_steps=50)
+    backend = backend_factory(cfg)
+    orc = OracleEnv(tree(), cfg)
+    st = make_planes(n)
+    s = OracleEnv.from_planes(st)
+    orc.reset(s)
+    backend.reset(st)
+    pv = planes_view(st)
+    np.testing.assert_array_equal(pv["wp_idx"], s["wp_idx"]); np.testing.assert_array_equal(pv["target"], s["target"])
+    np.testing.assert_array_equal(pv["qpos"][:, 0:3], s["qpos"][:, 0:3].astype(np.float32))
+    rng = np.random.default_rng(8)
+    total_reached = 0
+    for t in range(steps):
+        # teleport every env next to its current target (some inside the 0.25 m radius, some outside), at rest
+        ids = np.arange(n) + cfg.env_id_offset
+        off = rng.normal(size=(n, 3)); off /= np.linalg.norm(off, axis=1, keepdims=True)
+        off *= rng.choice([0.05, 0.2, 0.2495, 0.2505, 0.4], size=(n, 1))
+        wp = np.stack([tables[i % 3][pv["wp_idx"][k]] for k, i in enumerate(ids)])
+        # last waypoint before the lap closes for a few envs, so laps complete
+        pos = (wp + off).astype(np.float32)
+        st[0:3] = pos.T; st[3] = 1; st[4:7] = 0; st[11:21] = 0
+        s["qpos"][:, 0:3] = pos; s["qpos"][:, 3:7] = [1, 0, 0, 0]; s["qpos"][:, 7:] = 0; s["qvel"][:] = 0
+        act = np.tile(np.array([[-0.958, 0, 0, 0]], np.float32), (n, 1))      # ~hover thrust: the env barely moves
+        o = orc.step(s, act)
+        h = backend.step(st, act, want_term=True)
+        pv = planes_view(st)
+        np.testing.assert_array_equal(h["done"], o["done"], err_msg=f"t={t} done")
+        np.testing.assert_array_equal(h["truncated"], o["truncated"], err_msg=f"t={t} trunc")
+        np.testing.assert_array_equal(pv["wp_idx"], s["wp_idx"], err_msg=f"t={t} wp_idx")
+        np.testing.assert_array_equal(pv["wp_reached"], s["wp_reached"], err_msg=f"t={t} wp_reached")
+        np.testing.assert_array_equal(pv["laps"], s["laps"], err_msg=f"t={t} laps")
+        np.testing.assert_array_equal(pv["target"], s["target"], err_msg=f"t={t} target")
+        np.testing.assert_array_equal(pv["episode"], s["episode"], err_msg=f"t={t} episode")
+        np.testing.assert_array_equal(pv["step_count"], s["step_count"], err_msg=f"t={t} step_count")
+        assert_close(h["obs"], o["obs"], rtol=2e-5, atol=2e-6, what=f"t={t} obs")
+        total_reached = int(s["wp_reached"].sum())
+    assert total_reached > n           # most envs advanced more than once
+    return total_reached
+
+
+def check_lap_completion(backend_factory):
+    """An env walked around the whole table closes the lap: laps += 1, episode ends (evaluate.py:552-555)."""
+    from uav_reinforcement_learning_control_b200 import trajectories as TJ
+    tables = [TJ.square(0.5)]
+    cfg = Q.EnvConfig.waypoint_eval(tables, auto_reset=Q.RESET_RESAMPLE)
+    backend = backend_factory(cfg)
+    orc = OracleEnv(tree(), cfg)
+    n = 64
+    st = make_planes(n); s = OracleEnv.from_planes(st)
+    orc.reset(s); backend.reset(st)
+    act = np.tile(np.array([[-0.958, 0, 0, 0]], np.float32), (n, 1))
+    laps_seen = 0
+    for t in range(len(tables[0]) + 2):
+        pv = planes_view(st)
+        pos = np.stack([tables[0][k] for k in pv["wp_idx"]]).astype(np.float32)
+        st[0:3] = pos.T; st[3] = 1; st[4:7] = 0; st[11:21] = 0
+        s["qpos"][:, 0:3] = pos; s["qpos"][:, 3:7] = [1, 0, 0, 0]; s["qpos"][:, 7:] = 0; s["qvel"][:] = 0
+        o = orc.step(s, act); h = backend.step(st, act, want_term=True)
+        pv = planes_view(st)
+        np.testing.assert_array_equal(pv["laps"], s["laps"]); np.testing.assert_array_equal(pv["wp_idx"], s["wp_idx"])
+        np.testing.assert_array_equal(pv["episode"], s["episode"])
+        laps_seen = int(s["laps"].sum())
+    assert laps_seen == n              # every env completed exactly one lap and was reset to waypoint 0 / target 1
+    np.testing.assert_array_equal(planes_view(st)["episode"], 1)

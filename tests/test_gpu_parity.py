@@ -53,3 +53,12 @@ def test_physics_matches_host_build():
     pg, ph = planes_view(st_g), planes_view(st_h)
     assert_close(pg["qpos"], ph["qpos"], what="gpu vs host qpos", scale=qpos)
     assert_close(pg["qvel"], ph["qvel"], what="gpu vs host qvel", scale=qvel, atol=ATOL_QVEL)
+
+
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_waypoint_advance_bit_exact(auto_reset):
+    pc.check_waypoints(GpuBackend, n=3000, steps=6, auto_reset=auto_reset)
+
+
+def test_waypoint_lap_completion():
+    pc.check_lap_completion(GpuBackend)

@@ -26,3 +26,12 @@ def test_reset_vs_oracle(name):
 @pytest.mark.parametrize("name", ["hover_gym", "traj_gym", "mjx_brax", "hover_brax"])
 def test_masks_bit_exact_on_injected_state(name):
     assert pc.check_observe_bit_exact_masks(HostHarness, name, n=4096) > 0
+
+
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_waypoint_advance_bit_exact(auto_reset):
+    pc.check_waypoints(HostHarness, n=300, steps=5, auto_reset=auto_reset)
+
+
+def test_waypoint_lap_completion():
+    pc.check_lap_completion(HostHarness)

@@ -16,6 +16,10 @@ namespace qs {
 #ifndef QS_STEP_MIN_BLOCKS
 #define QS_STEP_MIN_BLOCKS 6   /* <= 80 registers: 24 warps/SM; measured best on B200 (profiles/README.md) */
 #endif
+#ifndef QS_OBS_DIRECT
+#define QS_OBS_DIRECT 1   /* 1: per-thread 128-bit obs stores (measured 3 % faster: two barriers fewer);
+                             0: coalesced through a shared-memory tile */
+#endif
 constexpr int kBlock = QS_STEP_BLOCK;
 
 // Block-cooperative, fully coalesced store of per-thread rows obs_local[D] to out[n][D]:
@@ -48,48 +52,57 @@ __device__ __forceinline__ void store_rows(float* __restrict__ out, int n, int b
 // identical to the inline path (same reset_env / compute_obs source).
 constexpr int kSlotF = 21 + 3 + 12;     // qpos/qvel, target, obs (gym modes only)
 
+// Shared scratch of the compacted reset, sized for NT threads.
+template <int NT>
 struct ResetScratch {
-    int count[2];
-    int owner[1];                       // [NT] followed by episode[NT] and slots[NT][kSlotF] (carved by the caller)
+    int wcnt[2][NT / 32];               // finished lanes per warp, double-buffered across steps
+    unsigned short owner[NT];           // [warp][rank]: thread id of the finished lane
+    uint32_t epi[NT];                   // its (already incremented) episode index
+    float slot[NT * kSlotF];            // new state + obs, one row per reset
 };
 
+// Atomic-free: every warp ranks its finished lanes with a ballot and writes them into its own 32-entry
+// region; after ONE barrier all threads know the per-warp counts, thread j picks the j-th entry, and
+// after a second barrier the owners read their row back.
 template <int MODE, int NT>
 __device__ __forceinline__ void block_autoreset(const QsParams& P, const Tables& T, uint32_t gid_block_first,
-                                                Env& e, float* obs, bool need, int parity,
-                                                int* s_count /*[2]*/, int* s_owner /*[NT]*/, uint32_t* s_epi /*[NT]*/,
-                                                float* s_slot /*[NT][kSlotF]*/) {
+                                                Env& e, float* obs, bool need, int parity, ResetScratch<NT>& S) {
     static_assert(ModeTraits<MODE>::kGym, "Philox re-sampling exists in the gym modes only");
-    const int tid = threadIdx.x;
-    int slot = -1;
-    if (need) {
-        slot = atomicAdd(&s_count[parity], 1);
-        s_owner[slot] = tid;
-        s_epi[slot] = e.episode;
-    }
-    if (tid == 0) s_count[parity ^ 1] = 0;          // arm the other counter for the next call
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned ballot = __ballot_sync(0xffffffffu, need);
+    const int rank = __popc(ballot & ((1u << lane) - 1u));
+    if (need) { S.owner[w * 32 + rank] = (unsigned short)tid; S.epi[w * 32 + rank] = e.episode; }
+    if (lane == 0) S.wcnt[parity][w] = __popc(ballot);
     __syncthreads();
-    const int cnt = s_count[parity];
-    if (cnt == 0) return;                           // block-uniform
-    for (int j = tid; j < cnt; j += NT) {
+    int cnt[NW], total = 0, base = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { cnt[k] = S.wcnt[parity][k]; base += (k < w) ? cnt[k] : 0; total += cnt[k]; }
+    if (total == 0) return;                         // block-uniform
+    for (int j = tid; j < total; j += NT) {
+        int k = j, ww = 0;
+#pragma unroll
+        for (int q = 0; q < NW - 1; ++q) { if (k >= cnt[q] && ww == q) { k -= cnt[q]; ww = q + 1; } }
+        const int src = ww * 32 + k;
         Env r;
-        r.episode = s_epi[j];
+        r.episode = S.epi[src];
         r.wp_idx = 0; r.wp_reached = 0; r.laps = 0;
         float rpy[3];
-        reset_env<MODE>(P, T, gid_block_first + (uint32_t)s_owner[j], r, rpy);
+        reset_env<MODE>(P, T, gid_block_first + (uint32_t)S.owner[src], r, rpy);
         float o_[12];
         compute_obs<MODE>(P, r, rpy, o_);
-        float* d = s_slot + j * kSlotF;
+        float* d = S.slot + j * kSlotF;
         d[0] = r.b.p[0]; d[1] = r.b.p[1]; d[2] = r.b.p[2];
         d[3] = r.b.q[0]; d[4] = r.b.q[1]; d[5] = r.b.q[2]; d[6] = r.b.q[3];
         d[7] = r.b.v[0]; d[8] = r.b.v[1]; d[9] = r.b.v[2];
         d[10] = r.b.w[0]; d[11] = r.b.w[1]; d[12] = r.b.w[2];
         d[13] = r.target[0]; d[14] = r.target[1]; d[15] = r.target[2];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) d[16 + k] = o_[k];
+        for (int k2 = 0; k2 < 12; ++k2) d[16 + k2] = o_[k2];
     }
     __syncthreads();
     if (need) {
-        const float* d = s_slot + slot * kSlotF;
+        const float* d = S.slot + (base + rank) * kSlotF;
         e.b.p[0] = d[0]; e.b.p[1] = d[1]; e.b.p[2] = d[2];
         e.b.q[0] = d[3]; e.b.q[1] = d[4]; e.b.q[2] = d[5]; e.b.q[3] = d[6];
         e.b.v[0] = d[7]; e.b.v[1] = d[8]; e.b.v[2] = d[9];
@@ -109,6 +122,14 @@ __device__ __forceinline__ bool use_compaction(const QsParams& P) {
     return ModeTraits<MODE>::kGym && P.auto_reset == QS_RESET_RESAMPLE && !P.waypoint_mode;
 }
 
+// 12-float observation row -> three 128-bit stores
+__device__ __forceinline__ void store_obs12(float* __restrict__ obs, int i, const float* o) {
+    float4* d = reinterpret_cast<float4*>(obs + (size_t)i * 12);
+    d[0] = make_float4(o[0], o[1], o[2], o[3]);
+    d[1] = make_float4(o[4], o[5], o[6], o[7]);
+    d[2] = make_float4(o[8], o[9], o[10], o[11]);
+}
+
 // ------------------------------------------------------------------------------ step
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, QS_STEP_MIN_BLOCKS)
@@ -118,15 +139,11 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restri
             float* __restrict__ term_obs, const float* __restrict__ first) {
     constexpr int D = ModeTraits<MODE>::kObsDim;
     constexpr bool kGym = ModeTraits<MODE>::kGym;
-    __shared__ float sm[kBlock * (kGym ? kSlotF : D + 1)];   // reset slots, then re-used as the obs staging tile
-    __shared__ int s_count[2];
-    __shared__ int s_owner[kGym ? kBlock : 1];
-    __shared__ uint32_t s_epi[kGym ? kBlock : 1];
+    // gym modes: reset scratch; brax modes: staging tile for the 21-float observation rows
+    __shared__ __align__(16) unsigned char smem_raw[kGym ? sizeof(ResetScratch<kBlock>) : sizeof(float) * kBlock * (D + 1)];
     const int block_first = blockIdx.x * kBlock;
     const int i = block_first + threadIdx.x;
     const bool valid = i < n;
-    if (kGym && threadIdx.x == 0) { s_count[0] = 0; s_count[1] = 0; }
-    if (kGym) __syncthreads();
     float o_[D];
     Env e;
     StepOut so;
@@ -164,13 +181,21 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restri
                 }
             } else {
                 block_autoreset<MODE, kBlock>(P, T, P.env_id_offset + (uint32_t)block_first, e, o_, so.needs_reset, 0,
-                                              s_count, s_owner, s_epi, sm);
-                __syncthreads();                    // slots are dead; sm becomes the obs staging tile
+                                              *reinterpret_cast<ResetScratch<kBlock>*>(smem_raw));
             }
         }
+        // one store sequence for all lanes (splitting it by needs_reset makes nearly every warp run it twice)
+        if (valid) store_env<MODE>(P, state, n, i, e);
+#if QS_OBS_DIRECT
+        if (valid) store_obs12(obs, i, o_);
+#else
+        __syncthreads();                            // reset slots are dead: reuse the scratch as the obs tile
+        store_rows<D>(obs, n, block_first, o_, valid, reinterpret_cast<float*>(smem_raw));
+#endif
+    } else {
+        if (valid) store_env<MODE>(P, state, n, i, e);
+        store_rows<D>(obs, n, block_first, o_, valid, reinterpret_cast<float*>(smem_raw));
     }
-    if (valid) store_env<MODE>(P, state, n, i, e);
-    store_rows<D>(obs, n, block_first, o_, valid, sm);
 }
 
 // ------------------------------------------------------------------------------ reset
@@ -251,15 +276,10 @@ rollout_random_kernel(const __grid_constant__ QsParams P, Tables T, int n, float
                       uint32_t t0, float* __restrict__ stats, const float* __restrict__ first) {
     constexpr int D = ModeTraits<MODE>::kObsDim;
     constexpr bool kGym = ModeTraits<MODE>::kGym;
-    __shared__ float sm[kGym ? kBlock * kSlotF : 1];
-    __shared__ int s_count[2];
-    __shared__ int s_owner[kGym ? kBlock : 1];
-    __shared__ uint32_t s_epi[kGym ? kBlock : 1];
+    __shared__ __align__(16) unsigned char smem_raw[kGym ? sizeof(ResetScratch<kBlock>) : 16];
     const int block_first = blockIdx.x * kBlock;
     const int i = block_first + threadIdx.x;
     const bool valid = i < n;
-    if (threadIdx.x == 0) { s_count[0] = 0; s_count[1] = 0; }
-    __syncthreads();
     const bool compact = use_compaction<MODE>(P);
     Env e;
     if (valid) load_env<MODE>(P, state, n, i, e);
@@ -280,7 +300,7 @@ rollout_random_kernel(const __grid_constant__ QsParams P, Tables T, int n, float
         if constexpr (kGym) {
             if (compact) {
                 block_autoreset<MODE, kBlock>(P, T, P.env_id_offset + (uint32_t)block_first, e, o_, so.needs_reset, t & 1,
-                                              s_count, s_owner, s_epi, sm);
+                                              *reinterpret_cast<ResetScratch<kBlock>*>(smem_raw));
             } else if (so.needs_reset) {
                 float rpy[3];
                 reset_env<MODE>(P, T, gid, e, rpy);

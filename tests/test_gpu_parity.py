@@ -62,3 +62,19 @@ def test_waypoint_advance_bit_exact(auto_reset):
 
 def test_waypoint_lap_completion():
     pc.check_lap_completion(GpuBackend)
+
+
+def test_horizon_error_curve_512_steps():
+    """Full-length episodes under a PD hover controller: flags stay bit-exact and the float32 trajectory stays
+    within 1e-3 m / 1e-3 (quaternion) of the float64 oracle after 512 steps."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import horizon_error
+    res = horizon_error.run(n_envs=64, steps=512, seed=4)
+    assert res["steps"] == 512 and res["alive_at_end"] >= 60, res["alive_at_end"]
+    assert res["flags_bit_exact"]
+    c = res["curve"]
+    assert c["pos_max"][0] < 2e-6 and c["pos_max"][-1] < 1e-3, (c["pos_max"][0], c["pos_max"][-1])
+    assert c["quat_max"][-1] < 1e-3 and c["obs_max"][-1] < 1e-3
+    assert res["mean_distance_to_target_at_end_m"] < 0.2      # the controller did reach the targets

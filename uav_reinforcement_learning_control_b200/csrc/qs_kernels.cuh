@@ -133,17 +133,18 @@ __device__ __forceinline__ void store_obs12(float* __restrict__ obs, int i, cons
 // ------------------------------------------------------------------------------ step
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, QS_STEP_MIN_BLOCKS)
-step_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restrict__ state,
+step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int count, float* __restrict__ state,
             const float4* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
             float* __restrict__ done, float* __restrict__ trunc, float* __restrict__ metrics,
             float* __restrict__ term_obs, const float* __restrict__ first) {
+    // n = plane stride (all envs of the handle); this launch steps envs [lo, lo + count)
     constexpr int D = ModeTraits<MODE>::kObsDim;
     constexpr bool kGym = ModeTraits<MODE>::kGym;
     // gym modes: reset scratch; brax modes: staging tile for the 21-float observation rows
     __shared__ __align__(16) unsigned char smem_raw[kGym ? sizeof(ResetScratch<kBlock>) : sizeof(float) * kBlock * (D + 1)];
-    const int block_first = blockIdx.x * kBlock;
+    const int block_first = lo + blockIdx.x * kBlock;
     const int i = block_first + threadIdx.x;
-    const bool valid = i < n;
+    const bool valid = i < lo + count;
     float o_[D];
     Env e;
     StepOut so;
@@ -190,11 +191,11 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restri
         if (valid) store_obs12(obs, i, o_);
 #else
         __syncthreads();                            // reset slots are dead: reuse the scratch as the obs tile
-        store_rows<D>(obs, n, block_first, o_, valid, reinterpret_cast<float*>(smem_raw));
+        store_rows<D>(obs, lo + count, block_first, o_, valid, reinterpret_cast<float*>(smem_raw));
 #endif
     } else {
         if (valid) store_env<MODE>(P, state, n, i, e);
-        store_rows<D>(obs, n, block_first, o_, valid, reinterpret_cast<float*>(smem_raw));
+        store_rows<D>(obs, lo + count, block_first, o_, valid, reinterpret_cast<float*>(smem_raw));
     }
 }
 

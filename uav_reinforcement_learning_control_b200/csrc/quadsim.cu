@@ -37,6 +37,8 @@ struct QsEngine {
     float* target_table;    // device, [max_episode_steps][3] or null
     double* waypoints;      // device, [shapes][QS_MAX_WP][3] or null
     float* scratch;         // device staging for qs_step_host: action | obs | reward | done
+    cudaStream_t hs[2];     // qs_step_host: two copy/compute streams (H2D of chunk k+1 under D2H of chunk k)
+    cudaEvent_t hev[3];
     qs::Tables tables() const { return qs::Tables{target_table, waypoints}; }
 };
 
@@ -91,6 +93,7 @@ int qs_create(const QsParams* params, int32_t num_envs, int32_t device, const fl
     QsEngine* e = new (std::nothrow) QsEngine();
     if (!e) return fail(QS_ENOMEM, "qs_create: host allocation failed");
     e->P = P; e->n = num_envs; e->device = device; e->target_table = nullptr; e->waypoints = nullptr; e->scratch = nullptr;
+    e->hs[0] = e->hs[1] = nullptr; e->hev[0] = e->hev[1] = e->hev[2] = nullptr;
     if (table) {
         const size_t bytes = (size_t)P.max_episode_steps * 3 * sizeof(float);
         if (cudaMalloc(&e->target_table, bytes) != cudaSuccess) { delete e; return fail(QS_ENOMEM, "cudaMalloc target table"); }
@@ -111,6 +114,8 @@ int qs_destroy(QsHandle h) {
     if (!h) return QS_OK;
     cudaSetDevice(h->device);
     cudaFree(h->target_table); cudaFree(h->waypoints); cudaFree(h->scratch);
+    for (int k = 0; k < 2; ++k) if (h->hs[k]) cudaStreamDestroy(h->hs[k]);
+    for (int k = 0; k < 3; ++k) if (h->hev[k]) cudaEventDestroy(h->hev[k]);
     delete h;
     return QS_OK;
 }
@@ -131,17 +136,24 @@ int qs_reset(QsHandle h, float* state, const uint8_t* mask, float* obs, float* f
     return check_launch("reset_kernel");
 }
 
+static int launch_step(QsHandle h, int lo, int count, float* state, const float* action, float* obs, float* reward,
+                       float* done, float* truncated, float* metrics, float* terminal_obs, const float* first_state,
+                       cudaStream_t s) {
+    QS_DISPATCH_MODE(h->P.mode, (qs::step_kernel<M_><<<nblocks(count, qs::kBlock), qs::kBlock, 0, s>>>(
+        h->P, h->tables(), h->n, lo, count, state, (const float4*)action, obs, reward, done, truncated, metrics,
+        terminal_obs, first_state)));
+    return check_launch("step_kernel");
+}
+
 int qs_step(QsHandle h, float* state, const float* action, float* obs, float* reward, float* done,
             float* truncated, float* metrics, float* terminal_obs, const float* first_state, void* stream) {
     if (!h || !state || !action || !obs || !reward || !done) return fail(QS_EINVAL, "qs_step: null");
     if (h->P.auto_reset == QS_RESET_RESTORE_FIRST && !first_state)
         return fail(QS_EINVAL, "qs_step: auto_reset=restore_first needs first_state");
     if (((uintptr_t)action & 15u) != 0) return fail(QS_EINVAL, "qs_step: action must be 16-byte aligned");
-    cudaStream_t s = (cudaStream_t)stream;
-    QS_DISPATCH_MODE(h->P.mode, (qs::step_kernel<M_><<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, s>>>(
-        h->P, h->tables(), h->n, state, (const float4*)action, obs, reward, done, truncated, metrics,
-        terminal_obs, first_state)));
-    return check_launch("step_kernel");
+    if (h->P.obs_dim == 12 && ((uintptr_t)obs & 15u) != 0) return fail(QS_EINVAL, "qs_step: obs must be 16-byte aligned");
+    return launch_step(h, 0, h->n, state, action, obs, reward, done, truncated, metrics, terminal_obs, first_state,
+                       (cudaStream_t)stream);
 }
 
 int qs_observe(QsHandle h, const float* state, const float* action, float* obs, float* reward, float* done,
@@ -177,16 +189,37 @@ int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_
                  float* done_host, void* stream) {
     if (!h || !state || !action_host || !obs_host || !reward_host || !done_host)
         return fail(QS_EINVAL, "qs_step_host: null");
+    if (h->P.auto_reset == QS_RESET_RESTORE_FIRST) return fail(QS_EUNSUPPORTED, "qs_step_host: use qs_step for brax auto-reset");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)h->n, D = (size_t)h->P.obs_dim;
-    if (!h->scratch) QS_CUDA(cudaMalloc(&h->scratch, n * (4 + D + 2) * sizeof(float)));
+    if (!h->scratch) {
+        QS_CUDA(cudaMalloc(&h->scratch, n * (4 + D + 2) * sizeof(float)));
+        for (int k = 0; k < 2; ++k) QS_CUDA(cudaStreamCreateWithFlags(&h->hs[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 3; ++k) QS_CUDA(cudaEventCreateWithFlags(&h->hev[k], cudaEventDisableTiming));
+    }
     float* d_act = h->scratch; float* d_obs = d_act + 4 * n; float* d_rew = d_obs + D * n; float* d_done = d_rew + n;
-    QS_CUDA(cudaMemcpyAsync(d_act, action_host, 4 * n * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = qs_step(h, state, d_act, d_obs, d_rew, d_done, nullptr, nullptr, nullptr, nullptr, stream);
-    if (rc != QS_OK) return rc;
-    QS_CUDA(cudaMemcpyAsync(obs_host, d_obs, D * n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    QS_CUDA(cudaMemcpyAsync(reward_host, d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    QS_CUDA(cudaMemcpyAsync(done_host, d_done, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    // Chunked, double-streamed: PCIe is full duplex, so the H2D of chunk k+1 and the kernel of chunk k+1 run under the
+    // D2H of chunk k.  Chunks are multiples of the block size; small batches go through as one chunk.
+    const int chunks = n >= (size_t)1 << 17 ? 8 : 1;
+    const size_t per = ((n + chunks - 1) / chunks + qs::kBlock - 1) / qs::kBlock * qs::kBlock;
+    QS_CUDA(cudaEventRecord(h->hev[0], s));                       // state is ready when the caller's stream gets here
+    for (int k = 0; k < 2; ++k) QS_CUDA(cudaStreamWaitEvent(h->hs[k], h->hev[0], 0));
+    for (int c = 0; c < chunks; ++c) {
+        const size_t lo = (size_t)c * per;
+        if (lo >= n) break;
+        const size_t cnt = (lo + per <= n) ? per : n - lo;
+        cudaStream_t cs = h->hs[c & 1];
+        QS_CUDA(cudaMemcpyAsync(d_act + 4 * lo, action_host + 4 * lo, 4 * cnt * sizeof(float), cudaMemcpyHostToDevice, cs));
+        int rc = launch_step(h, (int)lo, (int)cnt, state, d_act, d_obs, d_rew, d_done, nullptr, nullptr, nullptr, nullptr, cs);
+        if (rc != QS_OK) return rc;
+        QS_CUDA(cudaMemcpyAsync(obs_host + D * lo, d_obs + D * lo, D * cnt * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        QS_CUDA(cudaMemcpyAsync(reward_host + lo, d_rew + lo, cnt * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        QS_CUDA(cudaMemcpyAsync(done_host + lo, d_done + lo, cnt * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    }
+    for (int k = 0; k < 2; ++k) {
+        QS_CUDA(cudaEventRecord(h->hev[1 + k], h->hs[k]));
+        QS_CUDA(cudaStreamWaitEvent(s, h->hev[1 + k], 0));        // later work on the caller's stream sees the new state
+    }
     QS_CUDA(cudaStreamSynchronize(s));
     return QS_OK;
 }

@@ -344,6 +344,21 @@ def main():
             "traj_hbm_gbs": (80.0 * nb * Tp) / (ms_roll * 1e-3) / 1e9,
             "policy_tflops_fp32": flop * nb * Tp / (ms_roll * 1e-3) / 1e12,
             "note": "2x128 ReLU actor + critic (fp32 FMA path), Gaussian sampling, trajectories written once, GAE scan"}
+        # the same workload with the policy forward on tcgen05/TMEM (bf16 operands, fp32 accumulate)
+        eng_p.rollout_policy(st_p, params, T=Tp, t0=2 * Tp, dist=0, buffers=buf, tensor_cores=True)
+        barrier()
+        e0.record(stream)
+        eng_p.rollout_policy(st_p, params, T=Tp, t0=3 * Tp, dist=0, buffers=buf, tensor_cores=True)
+        eg.record(stream)
+        eng_p.gae(buf["reward"], buf["value"], buf["done"], buf["trunc"], buf["last_value"], 0.99, 0.95, adv=adv, ret=ret)
+        e1.record(stream)
+        barrier()
+        ms_p = max_over_ranks(e0.elapsed_time(e1)); ms_roll = e0.elapsed_time(eg)
+        line["rollout_tc"] = {
+            "value": world * nb * Tp / (ms_p * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb, "T": Tp,
+            "ms_rollout": ms_roll, "ms_gae": ms_p - ms_roll, "traj_hbm_gbs": (80.0 * nb * Tp) / (ms_roll * 1e-3) / 1e9,
+            "policy_tflops_bf16": flop * nb * Tp / (ms_roll * 1e-3) / 1e12,
+            "note": "tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), 128-env M tiles, 64 of 148 SMs busy at 8192 envs"}
         del eng_p
         # big-batch policy rollout (per-GPU shard of configs[4]): 2^18 envs x 32 steps
         nb2, T2 = 1 << 18, 32
@@ -351,15 +366,18 @@ def main():
         eng_q = Engine(cfg_q, nb2, device=local)
         st_q = eng_q.new_state()
         eng_q.reset(st_q)
-        bufq = eng_q.rollout_policy(st_q, params, T=T2, t0=0, dist=0)
-        barrier()
-        e0.record(stream)
-        eng_q.rollout_policy(st_q, params, T=T2, t0=T2, dist=0, buffers=bufq)
-        e1.record(stream)
-        barrier()
-        ms_q = max_over_ranks(e0.elapsed_time(e1))
-        line["rollout_large"] = {"value": world * nb2 * T2 / (ms_q * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb2,
-                                 "T": T2, "policy_tflops_fp32": flop * nb2 * T2 / (ms_q * 1e-3) / 1e12}
+        bufq = None
+        for key, tcf in (("rollout_large", False), ("rollout_large_tc", True)):
+            bufq = eng_q.rollout_policy(st_q, params, T=T2, t0=0, dist=0, buffers=bufq, tensor_cores=tcf)
+            barrier()
+            e0.record(stream)
+            eng_q.rollout_policy(st_q, params, T=T2, t0=T2, dist=0, buffers=bufq, tensor_cores=tcf)
+            e1.record(stream)
+            barrier()
+            ms_q = max_over_ranks(e0.elapsed_time(e1))
+            line[key] = {"value": world * nb2 * T2 / (ms_q * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb2, "T": T2,
+                         ("policy_tflops_bf16" if tcf else "policy_tflops_fp32"): flop * nb2 * T2 / (ms_q * 1e-3) / 1e12,
+                         "traj_hbm_gbs": (80.0 * nb2 * T2) / (ms_q * 1e-3) / 1e9}
         del eng_q, bufq
         if rank == 0:
             cb, _, _ = cpu_baseline(Q.EnvConfig.north_star(seed=0), target_seconds=args.cpu_seconds)

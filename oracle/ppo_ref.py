@@ -50,14 +50,27 @@ def param_count(obs_dim, dist):
     return 2 * (obs_dim * H + H + H * H + H) + H * Ao + Ao + H + 1 + (A if dist == 0 else 0) + 2 * obs_dim
 
 
-def forward(pp, obs):
-    x = (np.asarray(obs, dtype=np.float64) - pp["mean"]) * pp["inv_std"]
-    h = np.maximum(x @ pp["aW1"] + pp["ab1"], 0.0)
-    h = np.maximum(h @ pp["aW2"] + pp["ab2"], 0.0)
-    head = h @ pp["aW3"] + pp["ab3"]
-    c = np.maximum(x @ pp["cW1"] + pp["cb1"], 0.0)
-    c = np.maximum(c @ pp["cW2"] + pp["cb2"], 0.0)
-    value = c @ pp["cW3"] + pp["cb3"][0]
+def bf16_round(a):
+    """Round-to-nearest-even to bfloat16 precision (returned as float64)."""
+    u = np.asarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+def forward(pp, obs, bf16=False):
+    """bf16=True models the tcgen05 path: every MMA operand (activations and weights of all three layers)
+    rounded to bfloat16, products and sums in (at least) float32, biases added in float32."""
+    q = bf16_round if bf16 else (lambda a: np.asarray(a, dtype=np.float64))
+    x = (np.asarray(obs, dtype=np.float32) - pp["mean"].astype(np.float32)) * pp["inv_std"].astype(np.float32) if bf16 \
+        else (np.asarray(obs, dtype=np.float64) - pp["mean"]) * pp["inv_std"]
+    x = q(x)
+    b1a, b1c = (q(pp["ab1"]), q(pp["cb1"])) if bf16 else (pp["ab1"], pp["cb1"])     # tcgen05 path: layer-1 bias rides in the MMA
+    h = np.maximum(x @ q(pp["aW1"]) + b1a, 0.0)
+    h = np.maximum(q(h) @ q(pp["aW2"]) + pp["ab2"], 0.0)
+    head = q(h) @ q(pp["aW3"]) + pp["ab3"]
+    c = np.maximum(x @ q(pp["cW1"]) + b1c, 0.0)
+    c = np.maximum(q(c) @ q(pp["cW2"]) + pp["cb2"], 0.0)
+    value = q(c) @ q(pp["cW3"]) + pp["cb3"][0]
     return head, value
 
 

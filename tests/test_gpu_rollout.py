@@ -183,3 +183,41 @@ def test_rollout_random_matches_stepwise():
     np.testing.assert_array_equal(a[:27].view(np.uint32), b[:27].view(np.uint32))
     np.testing.assert_array_equal(stats[1].cpu().numpy(), fin)
     assert_close(stats[0].cpu().numpy(), rsum, rtol=1e-5, atol=1e-5, what="reward sums")
+
+
+@pytest.mark.parametrize("dist,B,T", [(0, 128, 6), (0, 300, 5), (1, 1000, 4)])
+def test_rollout_tensor_core_path(dist, B, T):
+    """tcgen05/TMEM policy forward: given the observations the kernel recorded, its actions / values / log-probs
+    must match the oracle's bf16-operand, fp32-accumulate forward pass; bookkeeping must stay consistent."""
+    import torch
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    cfg = Q.EnvConfig.north_star(seed=21, env_id_offset=64, max_episode_steps=4)
+    eng = Engine(cfg, B, device=0)
+    st = eng.new_state(); eng.reset(st)
+    params = _random_policy(12, dist, seed=17, scale=0.6)
+    buf = eng.rollout_policy(st, torch.from_numpy(params).cuda(), T=T, t0=3, dist=dist, tensor_cores=True, bootstrap_gamma=0.9)
+    torch.cuda.synchronize()
+    b = {k: v.cpu().numpy() for k, v in buf.items()}
+    pp = ppo_ref.unpack(params, 12, dist)
+    ids = np.arange(B, dtype=np.uint32) + np.uint32(64)
+    for t in range(T):
+        head, value = ppo_ref.forward(pp, b["obs"][t], bf16=True)
+        raw, act, logp = ppo_ref.sample(pp, head, ppo_ref.policy_noise(cfg.seed, ids, 3 + t), dist)
+        assert_close(b["value"][t], value, rtol=2e-3, atol=2e-3, what=f"t={t} value (tcgen05)")
+        assert_close(b["act"][t], raw, rtol=2e-3, atol=2e-3, what=f"t={t} action (tcgen05)")
+        assert_close(b["logp"][t], logp, rtol=5e-3, atol=5e-3, what=f"t={t} logp (tcgen05)")
+        # and it is close to the exact fp32 network too (bf16 operand rounding only)
+        head32, value32 = ppo_ref.forward(pp, b["obs"][t])
+        assert np.abs(value - value32).max() < 0.1
+    assert np.isfinite(b["obs"]).all() and np.isfinite(b["reward"]).all()
+    _, v_last = ppo_ref.forward(pp, b["last_obs"], bf16=True)
+    assert_close(b["last_value"], v_last, rtol=2e-3, atol=2e-3, what="last value (tcgen05)")
+    pv = planes_view(st.cpu().numpy())
+    fin = np.maximum(b["done"], b["trunc"]).sum(axis=0)
+    np.testing.assert_array_equal(pv["episode"], fin.astype(np.uint32))       # one reset per finished episode
+    assert (b["trunc"].sum() > 0)                                             # 4-step episodes did truncate
+    # the same rollout on the fp32 FMA path sees the same first observation and similar values
+    st2 = eng.new_state(); eng.reset(st2)
+    buf2 = eng.rollout_policy(st2, torch.from_numpy(params).cuda(), T=1, t0=3, dist=dist)
+    np.testing.assert_array_equal(buf2["obs"][0].cpu().numpy(), b["obs"][0])
+    assert np.abs(buf2["value"][0].cpu().numpy() - b["value"][0]).max() < 0.1

@@ -19,7 +19,7 @@ for lib in libs:
         continue
     d = json.loads(line[-1])
     msg = f"{name:10s} value {d['value']:.3e}  ms/step {d['ms_per_step']:.4f}  hbm frac {d['roofline']['frac']:.3f}  e2e {d['e2e']['value']:.3e}"
-    for k in ("resident", "rollout", "rollout_large"):
+    for k in ("resident", "rollout", "rollout_tc", "rollout_large", "rollout_large_tc"):
         if k in d:
             msg += f"  {k} {d[k]['value']:.3e}"
     print(msg, flush=True)

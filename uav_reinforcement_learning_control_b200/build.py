@@ -16,7 +16,8 @@ ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(CSRC, "libquadsim.so")
 
 SOURCES = ["quadsim.cu"]
-HEADERS = ["qs_math.cuh", "qs_philox.cuh", "qs_dynamics.cuh", "qs_env.cuh", "qs_kernels.cuh", "qs_rollout.cuh"]
+HEADERS = ["qs_math.cuh", "qs_philox.cuh", "qs_dynamics.cuh", "qs_env.cuh", "qs_kernels.cuh", "qs_rollout.cuh",
+           "qs_rollout_tc.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

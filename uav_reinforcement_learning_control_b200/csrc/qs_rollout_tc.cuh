@@ -1,0 +1,475 @@
+// qs_rollout_tc.cuh -- tcgen05 / TMEM variant of the state-resident policy rollout (sm_100a only).
+//
+// Same contract as rollout_policy_kernel (qs_rollout.cuh; replaces acting.generate_unroll in
+// ppo_train.train, train_brax_ppo.py:589-620, and SB3 collect_rollouts, train.py:133-137), but the three
+// dense layers of the 2x128 actor and critic run on the 5th-generation tensor cores:
+//
+//   * one CTA = 2 independent tiles of 128 threads = 128 envs (one UMMA M-tile) sharing the weights in smem;
+//     within a tile thread i owns env i (state in registers) AND TMEM lane i, so after an MMA every thread reads exactly its own env's activations with tcgen05.ld 32x32b;
+//   * operands are bf16 in shared memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte
+//     core matrices, SBO = 128 B between row groups, LBO = rows/8 * 128 B between 16-byte K chunks), written
+//     by the owners themselves: a warp's 16-byte stores for one K chunk are 512 contiguous bytes;
+//   * accumulators are fp32 in TMEM (256 columns): L1 computes actor|critic together (N = 256, K = 16),
+//     L2 is 8 + 8 instructions of M128 N128 K16, L3 is 8 + 8 of M128 N16 K16 (heads padded to 16 columns);
+//   * a single elected thread issues tcgen05.mma and tcgen05.commit -> mbarrier; everybody waits on the
+//     barrier, then runs the epilogue (bias + ReLU + bf16 pack -> next layer's A operand).
+// fp32 weights arrive in the same packed vector as the FMA kernel and are converted to bf16 UMMA layout in
+// shared memory once per CTA per launch.  Numerics: bf16 inputs, fp32 accumulation -- the oracle models
+// exactly that rounding (oracle/ppo_ref.py forward(..., bf16=True)).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include "qs_kernels.cuh"
+#include "qs_rollout.cuh"
+
+namespace qs {
+namespace tc {
+
+constexpr int kM = 128;                 // envs per tile = UMMA M
+// TILES (template): independent 128-env tiles per CTA sharing the weights; 2 for large batches (2 warps per SMSP),
+// 1 when the batch is too small to fill the SMs with 256-env CTAs
+constexpr uint32_t kTileCols = 256;     // TMEM columns per tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);                 // start address  [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;        // leading byte offset [16,30)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;        // stride byte offset  [32,46)
+    d |= (uint64_t)1 << 46;                                   // descriptor version 1 (Blackwell)
+    return d;                                                 // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p; \n\t"
+        "}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u));
+}
+
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// tile-local barriers (128 threads each): the tiles of a CTA never wait for each other inside the step loop,
+// so one tile's MMA phases overlap the other tile's epilogues / env steps
+__device__ __forceinline__ void tile_sync(int tile) { asm volatile("bar.sync %0, 128;" :: "r"(tile + 1) : "memory"); }
+__device__ __forceinline__ bool tile_or(int tile, bool pred) {
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %2, 0;\n\tbar.red.or.pred p, %1, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(r) : "r"(tile + 1), "r"((uint32_t)pred) : "memory");
+    return r != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// bounded wait: a tensor-core phase takes microseconds; if the barrier never flips something is wrong with
+// the descriptors, and a trap is better than a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+
+// byte offset of (row, 8-element K chunk kc) in a K-major no-swizzle operand with `rows` rows
+__device__ __forceinline__ uint32_t op_offset(int rows, int row, int kc) {
+    return (uint32_t)((kc * (rows >> 3) + (row >> 3)) * 128 + (row & 7) * 16);
+}
+
+// shared-memory map (bytes)
+struct Smem {
+    static constexpr int W1 = 0;                          // B: [256 x 16] bf16
+    static constexpr int W2A = W1 + 256 * 16 * 2;         // B: [128 x 128]
+    static constexpr int W2C = W2A + 128 * 128 * 2;
+    static constexpr int W3A = W2C + 128 * 128 * 2;       // B: [16 x 128]
+    static constexpr int W3C = W3A + 16 * 128 * 2;
+    static constexpr int WEND = W3C + 16 * 128 * 2;       // end of the (shared) B operands
+    // per tile: A1 [128 x 16], A2A / A2C [128 x 128] (A2* are also the A operands of L3)
+    static constexpr int A1 = 0, A2A = 128 * 16 * 2, A2C = A2A + 128 * 128 * 2, TILE_BYTES = A2C + 128 * 128 * 2;
+    static constexpr int TILE0 = WEND;
+    __host__ __device__ static constexpr int f32_off(int tiles) { return TILE0 + tiles * TILE_BYTES; }   // fp32 constants, see below
+    static constexpr int kB1 = 0, kB2A = 256, kB2C = 384, kB3 = 512 /*[32]*/, kLogStd = 544, kMean = 548, kInvStd = 560,
+                         kNumF = 576;
+    __host__ __device__ static constexpr int bar_off(int tiles) { return f32_off(tiles) + kNumF * 4; }   // mbarriers (8 B per tile) + tmem base (4 B)
+    __host__ __device__ static constexpr int total(int tiles) { return bar_off(tiles) + 8 * tiles + 16; }
+};
+
+// this path is built for the 12-D gym observation (K padded to 16)
+template <int MODE, int DIST, int TILES>
+__global__ void __launch_bounds__(kM * TILES, 1)
+rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restrict__ state,
+                         const float* __restrict__ params, int steps, uint32_t t0, int deterministic,
+                         float bootstrap_gamma, RolloutBuffers rb, const float* __restrict__ first) {
+    static_assert(ModeTraits<MODE>::kObsDim == 12, "tensor-core rollout is built for the 12-D observation");
+    constexpr int D = 12;
+    constexpr int Ao = DIST == 1 ? 2 * kA : kA;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr uint32_t kTmemCols = kTileCols * TILES;
+    float* sF = reinterpret_cast<float*>(smem + Smem::f32_off(TILES));
+    constexpr int NT = kM * TILES;
+    const PolicyLayout L = policy_layout(D, DIST);
+    const int gtid = threadIdx.x;                          // thread in the CTA (setup loops)
+    const int tile = gtid / kM, tid = gtid % kM, warp = tid >> 5;   // tile-local thread / warp: TMEM lane = tid
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES)) + tile;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::bar_off(TILES) + 8 * TILES);
+    unsigned char* tsm = smem + Smem::TILE0 + tile * Smem::TILE_BYTES;   // this tile's A operands
+    const int b0 = (blockIdx.x * TILES + tile) * kM;
+
+    // ---- one-time setup: weights fp32 -> bf16 UMMA layout, constants, barrier, TMEM -------------------
+    for (int idx = gtid; idx < (Smem::WEND) / 4; idx += NT) reinterpret_cast<uint32_t*>(smem)[idx] = 0u;   // zero all B operands
+    __syncthreads();
+    {
+        __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1);
+        // W1cat (n, k): n < 128 actor, n >= 128 critic; params store W[k][n]
+        for (int idx = gtid; idx < D * 256; idx += NT) {
+            const int k = idx / 256, nn = idx % 256;
+            const float w = nn < 128 ? params[L.aW1 + k * kH + nn] : params[L.cW1 + k * kH + (nn - 128)];
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(w);
+        }
+        (void)w1;
+        // the layer-1 bias rides in the padded K slot 12 (the A operand carries a constant 1 there); it is therefore
+        // rounded to bf16 like the weights
+        for (int nn = gtid; nn < 256; nn += NT) {
+            const float bv = nn < 128 ? params[L.ab1 + nn] : params[L.cb1 + (nn - 128)];
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, D >> 3) + (D & 7) * 2) = __float2bfloat16_rn(bv);
+        }
+        for (int idx = gtid; idx < kH * kH; idx += NT) {
+            const int k = idx / kH, nn = idx % kH;
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W2A + op_offset(128, nn, k >> 3) + (k & 7) * 2) =
+                __float2bfloat16_rn(params[L.aW2 + idx]);
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W2C + op_offset(128, nn, k >> 3) + (k & 7) * 2) =
+                __float2bfloat16_rn(params[L.cW2 + idx]);
+        }
+        for (int idx = gtid; idx < kH * Ao; idx += NT) {
+            const int k = idx / Ao, nn = idx % Ao;
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W3A + op_offset(16, nn, k >> 3) + (k & 7) * 2) =
+                __float2bfloat16_rn(params[L.aW3 + idx]);
+        }
+        for (int k = gtid; k < kH; k += NT)
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W3C + op_offset(16, 0, k >> 3) + (k & 7) * 2) =
+                __float2bfloat16_rn(params[L.cW3 + k]);
+        for (int idx = gtid; idx < Smem::kNumF; idx += NT) sF[idx] = 0.f;
+    }
+    __syncthreads();
+    for (int k = gtid; k < kH; k += NT) {
+        sF[Smem::kB1 + k] = params[L.ab1 + k]; sF[Smem::kB1 + 128 + k] = params[L.cb1 + k];
+        sF[Smem::kB2A + k] = params[L.ab2 + k]; sF[Smem::kB2C + k] = params[L.cb2 + k];
+    }
+    if (gtid < Ao) sF[Smem::kB3 + gtid] = params[L.ab3 + gtid];
+    if (gtid == 0) sF[Smem::kB3 + 16] = params[L.cb3];
+    if (DIST == 0 && gtid < kA) sF[Smem::kLogStd + gtid] = params[L.log_std + gtid];
+    if (gtid < D) { sF[Smem::kMean + gtid] = params[L.mean + gtid]; sF[Smem::kInvStd + gtid] = params[L.inv_std + gtid]; }
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (gtid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    fence_async_smem();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_all = *tmem_slot;
+    const uint32_t tmem = tmem_all + (uint32_t)tile * kTileCols;        // this tile's 256 accumulator columns
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes
+
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t tbase = smem_u32(tsm);
+    const uint32_t idesc_l1 = make_idesc(128, 256), idesc_l2 = make_idesc(128, 128), idesc_l3 = make_idesc(128, 16);
+    // descriptors: LBO = (rows/8)*128 bytes between the two 16-byte K chunks of one instruction, SBO = 128
+    const uint64_t dA1 = make_desc(tbase + Smem::A1, 16 * 128, 128), dW1 = make_desc(sbase + Smem::W1, 32 * 128, 128);
+    uint32_t phase = 0;
+
+    const bool owner = (b0 + tid) < n;
+    const uint32_t gid = P.env_id_offset + (uint32_t)(b0 + tid);
+    Env e;
+    float obs_[D];
+    if (owner) {
+        load_env<MODE>(P, state, n, b0 + tid, e);
+        float rpy[3];
+        quat_to_rpy(e.b.q, rpy);
+        compute_obs<MODE>(P, e, rpy, obs_);
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) obs_[k] = 0.f;
+    }
+
+    // forward pass for the observation in `o`; returns head[Ao] and value
+    auto forward = [&](const float* o, float* head, float& value) {
+        // A1: normalised obs, bf16, K padded 12 -> 16
+        {
+            float x[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = k < D ? (o[k] - sF[Smem::kMean + k]) * sF[Smem::kInvStd + k] : (k == D ? 1.0f : 0.f);
+            uint4 c0 = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+            uint4 c1 = make_uint4(pack_bf16(x[8], x[9]), pack_bf16(x[10], x[11]), pack_bf16(x[12], x[13]), pack_bf16(x[14], x[15]));
+            *reinterpret_cast<uint4*>(tsm + Smem::A1 + op_offset(128, tid, 0)) = c0;
+            *reinterpret_cast<uint4*>(tsm + Smem::A1 + op_offset(128, tid, 1)) = c1;
+        }
+        fence_async_smem();
+        fence_before();
+        tile_sync(tile);
+        if (tid == 0) {
+            fence_after();
+            mma_bf16(tmem, dA1, dW1, idesc_l1, 0u);                         // D1[128 x 256] = A1 . W1cat
+            mma_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after();
+        // epilogue 1: h1 = relu(D1 + b1) -> bf16 A2A | A2C
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float v[32];
+            tmem_ld32(my_tmem + (uint32_t)(c * 32), v);
+            const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) h[j] = fmaxf(v[q * 8 + j], 0.f);          // bias already inside the MMA
+                *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
+                    make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+            }
+        }
+        fence_async_smem();
+        fence_before();
+        tile_sync(tile);
+        if (tid == 0) {
+            fence_after();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                                   // K = 128 in 8 steps of 16 (2 chunks of 2048 B each)
+                mma_bf16(tmem, make_desc(tbase + Smem::A2A + j * 4096, 16 * 128, 128),
+                         make_desc(sbase + Smem::W2A + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                mma_bf16(tmem + 128u, make_desc(tbase + Smem::A2C + j * 4096, 16 * 128, 128),
+                         make_desc(sbase + Smem::W2C + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+            }
+            mma_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after();
+        // epilogue 2: h2 = relu(D2 + b2) -> bf16, written over A2A | A2C (the L2 MMAs have completed)
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float v[32];
+            tmem_ld32(my_tmem + (uint32_t)(c * 32), v);
+            const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
+            const int bb = (c < 4) ? Smem::kB2A : Smem::kB2C;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) h[j] = fmaxf(v[q * 8 + j] + sF[bb + (c & 3) * 32 + q * 8 + j], 0.f);
+                *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
+                    make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+            }
+        }
+        fence_async_smem();
+        fence_before();
+        tile_sync(tile);
+        if (tid == 0) {
+            fence_after();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)                                     // heads: N = 16 (B rows/8 = 2 -> LBO 256 B, K step 512 B)
+                mma_bf16(tmem, make_desc(tbase + Smem::A2A + j * 4096, 16 * 128, 128),
+                         make_desc(sbase + Smem::W3A + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                mma_bf16(tmem + 16u, make_desc(tbase + Smem::A2C + j * 4096, 16 * 128, 128),
+                         make_desc(sbase + Smem::W3C + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+            mma_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after();
+        {
+            float v[32];
+            tmem_ld32(my_tmem, v);
+#pragma unroll
+            for (int j = 0; j < Ao; ++j) head[j] = v[j] + sF[Smem::kB3 + j];
+            value = v[16] + sF[Smem::kB3 + 16];
+        }
+        fence_before();       // the next forward's MMAs overwrite TMEM: order our loads before the coming barrier
+    };
+
+    for (int t = 0; t < steps; ++t) {
+        const size_t o = (size_t)t * n + b0 + tid;
+        if (owner && rb.obs) {
+            float4* dd = reinterpret_cast<float4*>(rb.obs + o * D);
+            dd[0] = make_float4(obs_[0], obs_[1], obs_[2], obs_[3]);
+            dd[1] = make_float4(obs_[4], obs_[5], obs_[6], obs_[7]);
+            dd[2] = make_float4(obs_[8], obs_[9], obs_[10], obs_[11]);
+        }
+        float head[Ao], value;
+        forward(obs_, head, value);
+
+        StepOut so;
+        so.reward = 0.f; so.done = 0.f; so.truncated = 0.f; so.finished = false; so.needs_reset = false;
+        float tobs[D];
+        bool need_boot = false;
+        if (owner) {
+            const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_POLICY}, P.seed_lo, P.seed_hi);
+            float eps[4];
+            {
+                const float u0 = ((float)(r.x >> 8) + 1.0f) * 5.9604644775390625e-8f;
+                const float u1 = (float)(r.y >> 8) * 5.9604644775390625e-8f;
+                const float u2 = ((float)(r.z >> 8) + 1.0f) * 5.9604644775390625e-8f;
+                const float u3 = (float)(r.w >> 8) * 5.9604644775390625e-8f;
+                const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+                float s0, c0, s1, c1;
+                sincosf(6.283185307179586f * u1, &s0, &c0);
+                sincosf(6.283185307179586f * u3, &s1, &c1);
+                eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
+            }
+            float raw[4], act[4], logp = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float z = deterministic ? 0.f : eps[j];
+                if constexpr (DIST == 0) {
+                    const float ls = sF[Smem::kLogStd + j];
+                    raw[j] = fmaf(expf(ls), z, head[j]);
+                    logp += -0.5f * z * z - ls - 0.9189385332046727f;
+                    act[j] = clamp_(raw[j], -1.0f, 1.0f);
+                } else {
+                    const float scale = softplus_(head[kA + j]) + 0.001f;
+                    raw[j] = fmaf(scale, z, head[j]);
+                    const float ldj = 2.0f * (0.6931471805599453f - raw[j] - softplus_(-2.0f * raw[j]));
+                    logp += -0.5f * z * z - logf(scale) - 0.9189385332046727f - ldj;
+                    act[j] = tanhf(raw[j]);
+                }
+            }
+            if (rb.act) reinterpret_cast<float4*>(rb.act)[o] = make_float4(raw[0], raw[1], raw[2], raw[3]);
+            if (rb.logp) rb.logp[o] = logp;
+            if (rb.value) rb.value[o] = value;
+            env_step<MODE>(P, T, gid, e, act, obs_, tobs, first ? first + b0 + tid : nullptr, n, so);
+            need_boot = bootstrap_gamma > 0.f && so.finished && so.truncated != 0.f && so.done == 0.f;
+        }
+        // SB3 timeout bootstrap: reward += gamma * V(terminal_obs) for truncated-not-terminated episodes
+        if (tile_or(tile, need_boot)) {
+            float h2[Ao], vt;
+            forward(need_boot ? tobs : obs_, h2, vt);
+            if (need_boot) so.reward = fmaf(bootstrap_gamma, vt, so.reward);
+        }
+        if (owner) {
+            if (rb.reward) rb.reward[o] = so.reward;
+            if (rb.done) rb.done[o] = so.done;
+            if (rb.trunc) rb.trunc[o] = so.truncated;
+        }
+    }
+
+    {
+        float head[Ao], value;
+        forward(obs_, head, value);
+        if (owner) {
+            if (rb.last_obs) {
+                float4* dd = reinterpret_cast<float4*>(rb.last_obs + (size_t)(b0 + tid) * D);
+                dd[0] = make_float4(obs_[0], obs_[1], obs_[2], obs_[3]);
+                dd[1] = make_float4(obs_[4], obs_[5], obs_[6], obs_[7]);
+                dd[2] = make_float4(obs_[8], obs_[9], obs_[10], obs_[11]);
+            }
+            if (rb.last_value) rb.last_value[b0 + tid] = value;
+            store_env<MODE>(P, state, n, b0 + tid, e);
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (gtid < 32) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_all), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <int MODE, int DIST, int TILES>
+inline int launch_rollout_tc_tt(const QsParams& P, const Tables& T, int n, float* state, const float* params, int steps,
+                                uint32_t t0, const RolloutOpts& opt, const RolloutBuffers& rb, const float* first,
+                                cudaStream_t s) {
+    auto kern = rollout_policy_tc_kernel<MODE, DIST, TILES>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total(TILES));
+    if (ce != cudaSuccess) return (int)ce;
+    kern<<<(n + kM * TILES - 1) / (kM * TILES), kM * TILES, Smem::total(TILES), s>>>(
+        P, T, n, state, params, steps, t0, opt.deterministic, opt.bootstrap_gamma, rb, first);
+    return 0;
+}
+
+template <int MODE, int DIST>
+inline int launch_rollout_tc_t(const QsParams& P, const Tables& T, int n, float* state, const float* params, int steps,
+                               uint32_t t0, const RolloutOpts& opt, const RolloutBuffers& rb, const float* first,
+                               cudaStream_t s) {
+    // two tiles per CTA only when that still gives every SM a CTA
+    if (n >= 148 * 2 * kM) return launch_rollout_tc_tt<MODE, DIST, 2>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    return launch_rollout_tc_tt<MODE, DIST, 1>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+}
+
+inline int launch_rollout_policy_tc(const QsParams& P, const Tables& T, int n, float* state, const QsPolicyDesc& d,
+                                    const float* params, int steps, uint32_t t0, const RolloutBuffers& rb,
+                                    const float* first, cudaStream_t s) {
+    RolloutOpts opt{d.deterministic, d.bootstrap_gamma};
+    if (P.mode == QS_MODE_HOVER_GYM && d.dist == 0)
+        return launch_rollout_tc_t<QS_MODE_HOVER_GYM, 0>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    if (P.mode == QS_MODE_HOVER_GYM && d.dist == 1)
+        return launch_rollout_tc_t<QS_MODE_HOVER_GYM, 1>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    if (P.mode == QS_MODE_TRAJ_GYM && d.dist == 0)
+        return launch_rollout_tc_t<QS_MODE_TRAJ_GYM, 0>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    return -100;
+}
+
+}  // namespace tc
+}  // namespace qs

@@ -8,6 +8,7 @@
 
 #include "qs_kernels.cuh"
 #include "qs_rollout.cuh"
+#include "qs_rollout_tc.cuh"
 
 namespace {
 
@@ -240,8 +241,15 @@ int qs_rollout_policy(QsHandle h, float* state, const QsPolicyDesc* desc, const 
     if (h->P.auto_reset == QS_RESET_RESTORE_FIRST && !first_state)
         return fail(QS_EINVAL, "qs_rollout_policy: auto_reset=restore_first needs first_state");
     qs::RolloutBuffers rb{last_obs, traj_obs, traj_act, traj_logp, traj_value, traj_reward, traj_done, traj_trunc, last_value};
-    int rc = qs::launch_rollout_policy(h->P, h->tables(), h->n, state, *desc, policy_params, T, t0, rb, first_state,
+    int rc;
+    if (desc->tensor_cores) {
+        if (h->P.obs_dim != 12) return fail(QS_EUNSUPPORTED, "qs_rollout_policy: the tcgen05 path is built for the 12-D observation");
+        rc = qs::tc::launch_rollout_policy_tc(h->P, h->tables(), h->n, state, *desc, policy_params, T, t0, rb, first_state,
+                                              (cudaStream_t)stream);
+    } else {
+        rc = qs::launch_rollout_policy(h->P, h->tables(), h->n, state, *desc, policy_params, T, t0, rb, first_state,
                                        (cudaStream_t)stream);
+    }
     if (rc == -100) return fail(QS_EUNSUPPORTED, "qs_rollout_policy: unsupported mode/dist combination");
     if (rc != 0) return fail(QS_ECUDA, "qs_rollout_policy: launch configuration failed", (cudaError_t)rc);
     return check_launch("rollout_policy_kernel");

@@ -188,22 +188,23 @@ class Engine:
         self._check(self.lib.qs_rollout_random(self.handle, _ptr(state), int(T), int(t0) & 0xFFFFFFFF, _ptr(stats),
                                                _ptr(first_state), self._stream()))
 
-    def policy_desc(self, dist=0, deterministic=False, bootstrap_gamma=0.0):
+    def policy_desc(self, dist=0, deterministic=False, bootstrap_gamma=0.0, tensor_cores=False):
         d = Q.QsPolicyDesc()
         d.obs_dim, d.hidden, d.act_dim, d.dist = self.obs_dim, 128, 4, int(dist)
         d.deterministic, d.bootstrap_gamma = int(deterministic), float(bootstrap_gamma)
+        d.tensor_cores = int(tensor_cores)
         return d
 
     def policy_param_count(self, dist=0):
         d = self.policy_desc(dist)
         return int(self.lib.qs_policy_param_count(C.byref(d)))
 
-    def rollout_policy(self, state, params, T, t0=0, dist=0, deterministic=False, bootstrap_gamma=0.0,
+    def rollout_policy(self, state, params, T, t0=0, dist=0, deterministic=False, bootstrap_gamma=0.0, tensor_cores=False,
                        buffers=None, first_state=None):
         """Runs T fused policy+env steps.  `buffers`: dict of optional preallocated trajectory tensors."""
         torch = self.torch
         n, D = self.num_envs, self.obs_dim
-        d = self.policy_desc(dist, deterministic, bootstrap_gamma)
+        d = self.policy_desc(dist, deterministic, bootstrap_gamma, tensor_cores)
         self._chk(state, (Q.NPLANES, n), "state")
         self._chk(params, (self.policy_param_count(dist),), "policy params")
         b = dict(buffers or {})

@@ -64,17 +64,22 @@ struct ResetScratch {
 // Atomic-free: every warp ranks its finished lanes with a ballot and writes them into its own 32-entry
 // region; after ONE barrier all threads know the per-warp counts, thread j picks the j-th entry, and
 // after a second barrier the owners read their row back.
-template <int MODE, int NT>
+struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+
+// `tid` is the thread's index inside the group of NT threads that `sync` synchronises (a whole CTA by default,
+// one 128-thread tile in the tensor-core rollout kernel).
+template <int MODE, int NT, class Sync = BlockSync>
 __device__ __forceinline__ void block_autoreset(const QsParams& P, const Tables& T, uint32_t gid_block_first,
-                                                Env& e, float* obs, bool need, int parity, ResetScratch<NT>& S) {
+                                                Env& e, float* obs, bool need, int parity, ResetScratch<NT>& S,
+                                                int tid = threadIdx.x, Sync sync = Sync()) {
     static_assert(ModeTraits<MODE>::kGym, "Philox re-sampling exists in the gym modes only");
     constexpr int NW = NT / 32;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int lane = tid & 31, w = tid >> 5;
     const unsigned ballot = __ballot_sync(0xffffffffu, need);
     const int rank = __popc(ballot & ((1u << lane) - 1u));
     if (need) { S.owner[w * 32 + rank] = (unsigned short)tid; S.epi[w * 32 + rank] = e.episode; }
     if (lane == 0) S.wcnt[parity][w] = __popc(ballot);
-    __syncthreads();
+    sync();
     int cnt[NW], total = 0, base = 0;
 #pragma unroll
     for (int k = 0; k < NW; ++k) { cnt[k] = S.wcnt[parity][k]; base += (k < w) ? cnt[k] : 0; total += cnt[k]; }
@@ -100,7 +105,7 @@ __device__ __forceinline__ void block_autoreset(const QsParams& P, const Tables&
 #pragma unroll
         for (int k2 = 0; k2 < 12; ++k2) d[16 + k2] = o_[k2];
     }
-    __syncthreads();
+    sync();
     if (need) {
         const float* d = S.slot + (base + rank) * kSlotF;
         e.b.p[0] = d[0]; e.b.p[1] = d[1]; e.b.p[2] = d[2];

@@ -124,6 +124,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// relu + round-to-nearest bf16 + pack of two fp32 in ONE instruction (F2FP.RELU.BF16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// two fp32 adds in one instruction (FADD2, Blackwell packed fp32)
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+    unsigned long long p, q;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(p) : "l"(q));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&p);
@@ -280,12 +295,11 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             tmem_ld32(my_tmem + (uint32_t)(c * 32), v);
             const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float h[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) h[j] = fmaxf(v[q * 8 + j], 0.f);          // bias already inside the MMA
+            for (int q = 0; q < 4; ++q) {                  // bias is already inside the MMA: relu + bf16 pack only
+                const float* h = v + q * 8;
                 *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
-                    make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+                    make_uint4(pack_relu_bf16(h[0], h[1]), pack_relu_bf16(h[2], h[3]), pack_relu_bf16(h[4], h[5]),
+                               pack_relu_bf16(h[6], h[7]));
             }
         }
         fence_async_smem();
@@ -316,11 +330,14 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             const int bb = (c < 4) ? Smem::kB2A : Smem::kB2C;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float h[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) h[j] = fmaxf(v[q * 8 + j] + sF[bb + (c & 3) * 32 + q * 8 + j], 0.f);
+                float* h = v + q * 8;
+                const float4 ba = *reinterpret_cast<const float4*>(sF + bb + (c & 3) * 32 + q * 8);
+                const float4 bc = *reinterpret_cast<const float4*>(sF + bb + (c & 3) * 32 + q * 8 + 4);
+                add2(h[0], h[1], ba.x, ba.y); add2(h[2], h[3], ba.z, ba.w);
+                add2(h[4], h[5], bc.x, bc.y); add2(h[6], h[7], bc.z, bc.w);
                 *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
-                    make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+                    make_uint4(pack_relu_bf16(h[0], h[1]), pack_relu_bf16(h[2], h[3]), pack_relu_bf16(h[4], h[5]),
+                               pack_relu_bf16(h[6], h[7]));
             }
         }
         fence_async_smem();
@@ -399,8 +416,24 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             if (rb.act) reinterpret_cast<float4*>(rb.act)[o] = make_float4(raw[0], raw[1], raw[2], raw[3]);
             if (rb.logp) rb.logp[o] = logp;
             if (rb.value) rb.value[o] = value;
-            env_step<MODE>(P, T, gid, e, act, obs_, tobs, first ? first + b0 + tid : nullptr, n, so);
+            env_step<MODE, true>(P, T, gid, e, act, obs_, tobs, first ? first + b0 + tid : nullptr, n, so);
             need_boot = bootstrap_gamma > 0.f && so.finished && so.truncated != 0.f && so.done == 0.f;
+        }
+        // Philox re-sampling of finished envs, compacted per tile.  The scratch lives in this tile's A2A buffer,
+        // which is idle between the head MMAs of this step and the first epilogue of the next one.
+        if (P.auto_reset == QS_RESET_RESAMPLE) {
+            if (P.waypoint_mode) {
+                if (so.needs_reset) {
+                    float rpy[3];
+                    reset_env<MODE>(P, T, gid, e, rpy);
+                    compute_obs<MODE>(P, e, rpy, obs_);
+                }
+            } else {
+                struct TileSync { int t; __device__ __forceinline__ void operator()() const { tile_sync(t); } };
+                block_autoreset<MODE, kM, TileSync>(P, T, P.env_id_offset + (uint32_t)b0, e, obs_, so.needs_reset, t & 1,
+                                                    *reinterpret_cast<ResetScratch<kM>*>(tsm + Smem::A2A), tid, TileSync{tile});
+                tile_sync(tile);      // every owner has read its row before the buffer becomes an MMA operand again
+            }
         }
         // SB3 timeout bootstrap: reward += gamma * V(terminal_obs) for truncated-not-terminated episodes
         if (tile_or(tile, need_boot)) {

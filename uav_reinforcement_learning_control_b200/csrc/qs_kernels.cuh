@@ -204,6 +204,138 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
     }
 }
 
+// ------------------------------------------------------------------------------ step, prefetching variant
+// Gym modes.  Persistent CTAs walk over 128-env tiles; while tile k is being computed the planes and actions of
+// tile k+1 stream into a second shared-memory stage with cp.async (LDGSTS), so no warp ever waits on HBM latency
+// (ncu on the plain kernel: 30 % of warp time in long_scoreboard).  The staged tile keeps the planar layout with
+// stride kBlock, so the very same load_env reads it.  Stores, the compacted reset and every result are identical
+// to step_kernel.
+#ifndef QS_PF_MIN_BLOCKS
+#define QS_PF_MIN_BLOCKS 4
+#endif
+#ifndef QS_PF_STAGES
+#define QS_PF_STAGES 2                              // 2: double-buffered; 1: single stage refilled after the register load
+#endif
+constexpr int kPfPlanes = 31;                       // planes 0..30 (31 = brax-only)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct PfStage {
+    float plane[kPfPlanes][kBlock];
+    float4 action[kBlock];
+};
+
+// which planes a gym-mode step reads (block-uniform)
+__device__ __forceinline__ bool pf_plane_needed(const QsParams& P, int p) {
+    if (p <= 24 || p == 26) return true;
+    if (p == 25) return P.battery != 0;
+    if (p >= 28 && p <= 30) return P.waypoint_mode != 0;
+    return false;
+}
+
+// issue the asynchronous copies of tile [first, first + rows) into `st`
+__device__ __forceinline__ void pf_issue(const QsParams& P, PfStage& st, const float* __restrict__ state, int n,
+                                         const float4* __restrict__ action, int first, int rows) {
+    const int t = threadIdx.x;
+    if (rows == kBlock && (n & 3) == 0 && (first & 3) == 0) {
+        // 16-byte copies: kBlock/4 chunks per plane
+        constexpr int CH = kBlock / 4;
+        for (int idx = t; idx < kPfPlanes * CH; idx += kBlock) {
+            const int p = idx / CH, c = idx - p * CH;
+            if (pf_plane_needed(P, p)) cp_async16(&st.plane[p][4 * c], state + (size_t)p * n + first + 4 * c);
+        }
+    } else {
+        for (int idx = t; idx < kPfPlanes * kBlock; idx += kBlock) {
+            const int p = idx / kBlock, c = idx - p * kBlock;
+            if (c < rows && pf_plane_needed(P, p)) cp_async4(&st.plane[p][c], state + (size_t)p * n + first + c);
+        }
+    }
+    if (t < rows) cp_async16(&st.action[t], action + first + t);
+    cp_async_commit();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, QS_PF_MIN_BLOCKS)
+step_kernel_pf(const __grid_constant__ QsParams P, Tables T, int n, int lo, int count, float* __restrict__ state,
+               const float4* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
+               float* __restrict__ done, float* __restrict__ trunc, float* __restrict__ metrics,
+               float* __restrict__ term_obs) {
+    static_assert(ModeTraits<MODE>::kGym, "prefetching step kernel: gym modes");
+    constexpr int D = 12;
+    extern __shared__ __align__(16) unsigned char pf_smem[];
+    PfStage* stage = reinterpret_cast<PfStage*>(pf_smem);                         // [QS_PF_STAGES]
+    ResetScratch<kBlock>& scratch = *reinterpret_cast<ResetScratch<kBlock>*>(pf_smem + QS_PF_STAGES * sizeof(PfStage));
+    const int ntiles = (count + kBlock - 1) / kBlock;
+    int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    pf_issue(P, stage[0], state, n, action, lo + tile * kBlock, min(kBlock, count - tile * kBlock));
+    int buf = 0, parity = 0;
+    for (; tile < ntiles; tile += gridDim.x, buf ^= 1, parity ^= 1) {
+        const int block_first = lo + tile * kBlock;
+        const int rows = min(kBlock, count - tile * kBlock);
+        const int i = block_first + threadIdx.x;
+        const bool valid = threadIdx.x < rows;
+        cp_async_wait_all();
+        __syncthreads();                                   // tile `tile` has landed in stage[buf]; stage[buf^1] is free
+        const int nxt = tile + gridDim.x;
+        constexpr int kCur = QS_PF_STAGES == 2 ? 1 : 0;
+        PfStage& cur = stage[buf & kCur];
+#if QS_PF_STAGES == 2
+        if (nxt < ntiles) pf_issue(P, stage[buf ^ 1], state, n, action, lo + nxt * kBlock, min(kBlock, count - nxt * kBlock));
+#endif
+        float o_[D];
+        Env e;
+        StepOut so;
+        so.needs_reset = false;
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            load_env<MODE>(P, &cur.plane[0][0], kBlock, threadIdx.x, e);
+            a4 = cur.action[threadIdx.x];
+        }
+#if QS_PF_STAGES == 1
+        __syncthreads();                                   // everyone holds its env in registers: refill the stage
+        if (nxt < ntiles) pf_issue(P, cur, state, n, action, lo + nxt * kBlock, min(kBlock, count - nxt * kBlock));
+#endif
+        if (valid) {
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            float tobs[D];
+            env_step<MODE, true>(P, T, P.env_id_offset + (uint32_t)i, e, a, o_, term_obs ? tobs : nullptr, nullptr, n, so);
+            reward[i] = so.reward;
+            done[i] = so.done;
+            if (trunc) trunc[i] = so.truncated;
+            if (metrics) {
+                metrics[i] = so.pos_error; metrics[(size_t)n + i] = so.reward_hover;
+                metrics[2 * (size_t)n + i] = so.reward_action; metrics[3 * (size_t)n + i] = so.reward;
+            }
+            if (term_obs && so.finished) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) term_obs[(size_t)i * D + k] = tobs[k];
+            }
+        }
+        if (P.auto_reset == QS_RESET_RESAMPLE) {
+            if (P.waypoint_mode) {
+                if (so.needs_reset) {
+                    float rpy[3];
+                    reset_env<MODE>(P, T, P.env_id_offset + (uint32_t)i, e, rpy);
+                    compute_obs<MODE>(P, e, rpy, o_);
+                }
+            } else {
+                block_autoreset<MODE, kBlock>(P, T, P.env_id_offset + (uint32_t)block_first, e, o_, so.needs_reset, parity, scratch);
+            }
+        }
+        if (valid) { store_env<MODE>(P, state, n, i, e); store_obs12(obs, i, o_); }
+    }
+}
+
+inline size_t step_pf_smem_bytes() { return QS_PF_STAGES * sizeof(PfStage) + sizeof(ResetScratch<kBlock>); }
+
 // ------------------------------------------------------------------------------ reset
 template <int MODE>
 __global__ void __launch_bounds__(kBlock)

@@ -6,6 +6,11 @@
 #include <atomic>
 #include <new>
 
+// The cp.async-prefetching persistent step kernel (qs_kernels.cuh: step_kernel_pf) is kept as a build option: on B200 it
+// measured 75.8 us per 2^20-env step against 73.0 us for the plain kernel (profiles/README.md), so it is off by default.
+#ifndef QS_USE_PREFETCH_STEP
+#define QS_USE_PREFETCH_STEP 0
+#endif
 #include "qs_kernels.cuh"
 #include "qs_rollout.cuh"
 #include "qs_rollout_tc.cuh"
@@ -38,6 +43,7 @@ struct QsEngine {
     float* target_table;    // device, [max_episode_steps][3] or null
     double* waypoints;      // device, [shapes][QS_MAX_WP][3] or null
     float* scratch;         // device staging for qs_step_host: action | obs | reward | done
+    int pf_grid;            // persistent grid of the prefetching step kernel (SMs x resident CTAs)
     cudaStream_t hs[2];     // qs_step_host: two copy/compute streams (H2D of chunk k+1 under D2H of chunk k)
     cudaEvent_t hev[3];
     qs::Tables tables() const { return qs::Tables{target_table, waypoints}; }
@@ -105,6 +111,18 @@ int qs_create(const QsParams* params, int32_t num_envs, int32_t device, const fl
         if (cudaMalloc(&e->waypoints, bytes) != cudaSuccess) { cudaFree(e->target_table); delete e; return fail(QS_ENOMEM, "cudaMalloc waypoints"); }
         cudaMemcpy(e->waypoints, waypoints_host, bytes, cudaMemcpyHostToDevice);
     }
+    e->pf_grid = prop.multiProcessorCount;
+#if QS_USE_PREFETCH_STEP
+    {
+        const int smem = (int)qs::step_pf_smem_bytes();
+        int per_sm = 1;
+        cudaFuncSetAttribute(qs::step_kernel_pf<QS_MODE_HOVER_GYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(qs::step_kernel_pf<QS_MODE_TRAJ_GYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qs::step_kernel_pf<QS_MODE_HOVER_GYM>, qs::kBlock, smem);
+        if (per_sm < 1) per_sm = 1;
+        e->pf_grid = prop.multiProcessorCount * per_sm;
+    }
+#endif
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { cudaFree(e->target_table); cudaFree(e->waypoints); delete e; return fail(QS_ECUDA, "qs_create", ce); }
     *out = e;
@@ -140,6 +158,21 @@ int qs_reset(QsHandle h, float* state, const uint8_t* mask, float* obs, float* f
 static int launch_step(QsHandle h, int lo, int count, float* state, const float* action, float* obs, float* reward,
                        float* done, float* truncated, float* metrics, float* terminal_obs, const float* first_state,
                        cudaStream_t s) {
+#if QS_USE_PREFETCH_STEP
+    if (h->P.mode == QS_MODE_HOVER_GYM || h->P.mode == QS_MODE_TRAJ_GYM) {
+        // persistent, cp.async-prefetching variant: one wave of CTAs walks over all tiles
+        const size_t smem = qs::step_pf_smem_bytes();
+        const int tiles = nblocks(count, qs::kBlock);
+        const int grid = tiles < h->pf_grid ? tiles : h->pf_grid;
+        if (h->P.mode == QS_MODE_HOVER_GYM)
+            qs::step_kernel_pf<QS_MODE_HOVER_GYM><<<grid, qs::kBlock, smem, s>>>(h->P, h->tables(), h->n, lo, count, state,
+                (const float4*)action, obs, reward, done, truncated, metrics, terminal_obs);
+        else
+            qs::step_kernel_pf<QS_MODE_TRAJ_GYM><<<grid, qs::kBlock, smem, s>>>(h->P, h->tables(), h->n, lo, count, state,
+                (const float4*)action, obs, reward, done, truncated, metrics, terminal_obs);
+        return check_launch("step_kernel_pf");
+    }
+#endif
     QS_DISPATCH_MODE(h->P.mode, (qs::step_kernel<M_><<<nblocks(count, qs::kBlock), qs::kBlock, 0, s>>>(
         h->P, h->tables(), h->n, lo, count, state, (const float4*)action, obs, reward, done, truncated, metrics,
         terminal_obs, first_state)));

@@ -24,6 +24,9 @@
  *   29     waypoints reached (int32)                             evaluate.py:550
  *   30     laps completed (int32)                                evaluate.py:553
  *   31     done flag of the previous step (float32 0/1; Brax AutoResetWrapper)
+ *   32..34 rate-wrapper integral state (N m)                    envs/rate_wrapper.py:64
+ *   35..38 previous policy action (RelPosActWrapper obs)        envs/hover_env.py:165, rate_wrapper.py:100-104
+ *   39     reserved
  * Actions are [num_envs][4] float32 (row-major, 16 B per env); observations are
  * [num_envs][obs_dim] float32 row-major; reward/done/truncated are [num_envs] float32.
  */
@@ -37,7 +40,7 @@ extern "C" {
 #endif
 
 #define QS_ABI_VERSION 1
-#define QS_NPLANES 32
+#define QS_NPLANES 40
 #define QS_NQ 11
 #define QS_NV 10
 #define QS_MAX_WP 64
@@ -118,7 +121,14 @@ typedef struct QsParams {
     int32_t wp_num_shapes;
     int32_t wp_count[QS_MAX_SHAPES];
     float wp_reach_radius;
-    int32_t reserved[7];
+    /* --- rate-control action wrapper (envs/rate_wrapper.py:16-111) ------------ */
+    int32_t rate_wrapper;             /* 1: action = [thrust, roll/pitch/yaw RATE] -> torques by a PI loop */
+    float rate_max;                   /* rad/s for |a| = 1 (360 deg/s)            */
+    float rate_kd[3];                 /* P gains (inertia-scaled)                 */
+    float rate_inertia[3];            /* IXX, IYY, IZZ of utils/drone_config.py   */
+    float rate_ki, rate_imax;         /* integral gain (torque space), anti-windup clamp */
+    float max_torque;                 /* normalisation of the torque command (0.5 N m) */
+    int32_t reserved[5];
 } QsParams;
 
 typedef struct QsEngine* QsHandle;

@@ -57,7 +57,8 @@ class OracleEnv:
         return dict(qpos=qpos, qvel=np.zeros((n, 10)), target=np.zeros((n, 3), F32),
                     step_count=np.zeros(n, np.int32), voltage=np.zeros(n), episode=np.zeros(n, np.uint32),
                     ep_steps=np.zeros(n, np.int32), wp_idx=np.zeros(n, np.int32),
-                    wp_reached=np.zeros(n, np.int32), laps=np.zeros(n, np.int32), done_prev=np.zeros(n, F32))
+                    wp_reached=np.zeros(n, np.int32), laps=np.zeros(n, np.int32), done_prev=np.zeros(n, F32),
+                    rate_int=np.zeros((n, 3)), prev_action=np.zeros((n, 4), F32))
 
     @staticmethod
     def from_planes(st):
@@ -70,6 +71,8 @@ class OracleEnv:
         s["episode"] = st[26].view(np.uint32).copy(); s["ep_steps"] = st[27].view(np.int32).copy()
         s["wp_idx"] = st[28].view(np.int32).copy(); s["wp_reached"] = st[29].view(np.int32).copy()
         s["laps"] = st[30].view(np.int32).copy(); s["done_prev"] = st[31].copy()
+        if st.shape[0] > 38:
+            s["rate_int"] = st[32:35].T.astype(np.float64); s["prev_action"] = st[35:39].T.astype(F32).copy()
         return s
 
     # ------------------------------------------------------------------ pieces of step()
@@ -88,6 +91,18 @@ class OracleEnv:
             dV = (cfg.v_drop_base + cfg.v_drop_load * load) * self.pipe.dt
             voltage = np.clip(voltage - dV, cfg.v_min, cfg.v_nominal)
         return F, voltage
+
+    def rate_to_torque(self, s, action):
+        """RateControlWrapper.action (envs/rate_wrapper.py:69-98), float64 like the reference."""
+        cfg = self.cfg
+        a = np.asarray(action, dtype=F32)
+        des = a[:, 1:4].astype(np.float64) * np.deg2rad(cfg.rate_max_deg)
+        actual = s["qvel"][:, 3:6].astype(F32).astype(np.float64)      # QuadState keeps float32 (utils/state.py:25)
+        err = des - actual
+        tau_p = np.asarray(cfg.rate_inertia) * np.asarray(cfg.rate_kd) * err
+        s["rate_int"] = np.clip(s["rate_int"] + cfg.rate_ki * self.pipe.dt * err, -cfg.rate_imax, cfg.rate_imax)
+        tau_norm = np.clip((tau_p + s["rate_int"]) / Q.MAX_TORQUE, -1.0, 1.0)
+        return np.concatenate([a[:, 0:1].astype(np.float64), tau_norm], axis=1).astype(F32)
 
     @staticmethod
     def state12(qpos, qvel):
@@ -191,6 +206,7 @@ class OracleEnv:
         if k == 0:
             return
         s["step_count"][m] = 0; s["ep_steps"][m] = 0; s["done_prev"][m] = 0; s["voltage"][m] = cfg.v_nominal
+        s["rate_int"][m] = 0.0; s["prev_action"][m] = 0.0          # rate_wrapper.py:108-111, hover_env.py:211
         qpos = np.zeros((k, 11)); qvel = np.zeros((k, 10)); qpos[:, 3] = 1.0
         if _gym(cfg.mode):
             if cfg.waypoint_mode:
@@ -257,7 +273,11 @@ class OracleEnv:
         n = s["qpos"].shape[0]
         if _brax(cfg.mode) and cfg.auto_reset == Q.RESET_RESTORE_FIRST:
             s["ep_steps"][s["done_prev"] != 0] = 0
-        ctrl, s["voltage"] = self.action_to_ctrl(action, s["voltage"])
+        env_action = action
+        if _gym(cfg.mode) and cfg.rate_wrapper:
+            env_action = self.rate_to_torque(s, action)
+            s["prev_action"] = np.asarray(action, dtype=F32).copy()       # rate_wrapper.py:100-104
+        ctrl, s["voltage"] = self.action_to_ctrl(env_action, s["voltage"])
         with np.errstate(all="ignore"):
             s["qpos"], s["qvel"] = self.pipe.step(s["qpos"], s["qvel"], ctrl)
         s["step_count"] = s["step_count"] + 1

@@ -37,6 +37,8 @@ CONFIGS = {
     "hover_brax": lambda: Q.EnvConfig.hover_brax(),
     "hover_brax_wrapped": lambda: Q.EnvConfig.hover_brax(episode_length=100, auto_reset=Q.RESET_RESTORE_FIRST),
     "mjx_playground": lambda: Q.EnvConfig.mjx_playground(),
+    # SB3 default training wrapper (train.py:31): CTBR action -> torque PI loop fused as an action pre-stage
+    "hover_gym_rate": lambda: Q.EnvConfig.hover_gym(rate_wrapper=True, auto_reset=Q.RESET_RESAMPLE, seed=77),
 }
 
 
@@ -58,7 +60,7 @@ def synth_inputs(cfg, n, seed):
         ep_steps[:16] = cfg.episode_length - 1
     done_prev = (rng.uniform(size=n) < 0.2).astype(np.float32)
     st = make_planes(n, qpos, qvel, target=tgt, step_count=sc, voltage=volt, episode=rng.integers(0, 5, n),
-                     ep_steps=ep_steps, done_prev=done_prev)
+                     ep_steps=ep_steps, done_prev=done_prev, rate_int=rng.uniform(-0.012, 0.012, (n, 3)))
     # non-finite injections: termination / NaN->0 paths
     st[0, 20] = np.nan; st[12, 21] = np.inf; st[4, 22] = np.nan; st[17, 23] = -np.inf
     first = None
@@ -133,6 +135,9 @@ def check_single_step(backend_factory, name, n=4096, seed=0):
                  scale=sc_obs[okobs])
     if cfg.battery:
         assert_close(pv["voltage"], s["voltage"], what=f"{name}: voltage")
+    if cfg.rate_wrapper:
+        assert_close(pv["rate_int"], s["rate_int"], what=f"{name}: rate integral", rtol=1e-5, atol=1e-7)
+        np.testing.assert_array_equal(pv["prev_action"], s["prev_action"], err_msg=f"{name}: prev_action")
     for i, k in enumerate(["pos_error", "reward_hover", "reward_action", "reward"]):
         f = np.isfinite(o[k])
         assert_close(h["metrics"][i][f], np.asarray(o[k])[f], what=f"{name}: metric {k}", rtol=2e-5, atol=2e-6)

@@ -100,3 +100,27 @@ def test_ppo_trainer_improves_hover_reward():
     log = tr.train(12)
     r0 = np.mean([l["mean_reward"] for l in log[:2]]); r1 = np.mean([l["mean_reward"] for l in log[-2:]])
     assert np.isfinite(r1) and r1 > r0 * 1.15, (r0, r1)
+
+
+def test_rate_control_wrapper_fused():
+    """RateControlWrapper (envs/rate_wrapper.py): commanding zero body rates must damp an initial spin, and the
+    integral state must follow ki*dt*err with the 0.01 N m clamp."""
+    import torch
+    from uav_reinforcement_learning_control_b200.gym_vec import HoverVecEnv
+    env = HoverVecEnv(num_envs=32, wrapper="RateControlWrapper", auto_reset=False, seed=5)
+    env.set_state([0, 0, 1.0, 1, 0, 0, 0], [0, 0, 0, 3.0, -2.0, 1.0])
+    a = torch.zeros(32, 4, device=env.device); a[:, 0] = -0.958
+    w0 = env._planes[14:17].clone()
+    for _ in range(20):
+        env.step(a)
+    w1 = env._planes[14:17]
+    assert float(w1.abs().max()) < 0.3 * float(w0.abs().max())
+    assert float(env._rate_int_torque.abs().max()) <= 0.01 + 1e-7
+    assert env.max_rate_rad == pytest.approx(2 * np.pi)
+    # RelPosActWrapper: 7-D observation = normalised relative position + previous action
+    env2 = HoverVecEnv(num_envs=16, wrapper="RelPosActWrapper", seed=1)
+    obs, _ = env2.reset()
+    assert tuple(obs.shape) == (16, 7) and float(obs[:, 3:].abs().max()) == 0.0
+    act = torch.rand(16, 4, device=env2.device) * 0.2 - 0.1; act[:, 0] = -0.958
+    obs, *_ = env2.step(act)
+    assert torch.equal(obs[:, 3:], act) and env2.observation_space.shape == (7,)

@@ -66,7 +66,7 @@ def _worker(rank, world, port, out):
         raw = philox.draw_blocks(9, ids, np.uint32(t), 1, philox.STREAM_ACTION)
         act = np.stack([philox.uniform(raw[:, i], -1.0, 1.0) for i in range(4)], axis=1)
         hh.step(st, act)
-    gathered = [torch.zeros(32, n // world) for _ in range(world)]
+    gathered = [torch.zeros(Q.NPLANES, n // world) for _ in range(world)]
     dist.all_gather(gathered, torch.from_numpy(st.copy()))
     if rank == 0:
         out.put((ok, stats, torch.cat(gathered, dim=1).numpy()))

@@ -26,7 +26,7 @@ ATOL_OBS21 = np.concatenate([np.full(11, ATOL), ATOL_QVEL])
 
 
 def make_planes(n, qpos=None, qvel=None, target=None, step_count=None, voltage=None, episode=None,
-                ep_steps=None, wp_idx=None, wp_reached=None, laps=None, done_prev=None):
+                ep_steps=None, wp_idx=None, wp_reached=None, laps=None, done_prev=None, rate_int=None):
     """float32 [NPLANES, n] state array (include/quadsim_abi.h layout)."""
     st = np.zeros((NPLANES, n), dtype=np.float32)
     if qpos is not None:
@@ -51,6 +51,8 @@ def make_planes(n, qpos=None, qvel=None, target=None, step_count=None, voltage=N
     put_int(30, laps, np.int32)
     if done_prev is not None:
         st[31] = np.asarray(done_prev, dtype=np.float32)
+    if rate_int is not None:
+        st[32:35] = np.asarray(rate_int, dtype=np.float32).T
     return st
 
 
@@ -61,6 +63,7 @@ def planes_view(st):
         "step_count": st[24].view(np.int32), "voltage": st[25], "episode": st[26].view(np.uint32),
         "ep_steps": st[27].view(np.int32), "wp_idx": st[28].view(np.int32),
         "wp_reached": st[29].view(np.int32), "laps": st[30].view(np.int32), "done_prev": st[31],
+        "rate_int": st[32:35].T, "prev_action": st[35:39].T,
     }
 
 

@@ -18,7 +18,7 @@ from .model import QuadConstants
 MODE_MJX_BRAX, MODE_HOVER_GYM, MODE_TRAJ_GYM, MODE_HOVER_BRAX, MODE_MJX_PLAYGROUND = range(5)
 MODE_NAMES = {"mjx_brax": 0, "hover_gym": 1, "traj_gym": 2, "hover_brax": 3, "mjx_playground": 4}
 RESET_NONE, RESET_RESTORE_FIRST, RESET_RESAMPLE = 0, 1, 2
-NPLANES = 32
+NPLANES = 40
 MAX_WP = 64
 MAX_SHAPES = 4
 
@@ -56,7 +56,10 @@ class QsParams(C.Structure):
         ("reset_noise", C.c_float), ("reset_z", C.c_float),
         ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("env_id_offset", C.c_uint32),
         ("waypoint_mode", C.c_int32), ("wp_num_shapes", C.c_int32), ("wp_count", C.c_int32 * MAX_SHAPES),
-        ("wp_reach_radius", C.c_float), ("reserved", C.c_int32 * 7),
+        ("wp_reach_radius", C.c_float),
+        ("rate_wrapper", C.c_int32), ("rate_max", C.c_float), ("rate_kd", C.c_float * 3),
+        ("rate_inertia", C.c_float * 3), ("rate_ki", C.c_float), ("rate_imax", C.c_float), ("max_torque", C.c_float),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -126,6 +129,13 @@ class EnvConfig:
     waypoint_mode: bool = False
     waypoints: tuple = ()                         # tuple of (n_i, 3) float64 arrays, one per shape
     wp_reach_radius: float = 0.25
+    # RateControlWrapper (envs/rate_wrapper.py:16-23,58; pid_gains.json "rate_wrapper"; train.py:31 default wrapper)
+    rate_wrapper: bool = False
+    rate_max_deg: float = 360.0
+    rate_kd: tuple = (26.0, 26.0, 18.0)
+    rate_ki: float = 0.025
+    rate_imax: float = 0.01
+    rate_inertia: tuple = (4.16e-4, 4.23e-4, 5.37e-4)   # IXX, IYY, IZZ (utils/drone_config.py:15-17)
 
     # ---- the reference's five env variants -------------------------------------------
     @staticmethod
@@ -243,6 +253,10 @@ def pack_params(c: QuadConstants, cfg: EnvConfig) -> QsParams:
     for s, w in enumerate(cfg.waypoints):
         P.wp_count[s] = len(w)
     P.wp_reach_radius = cfg.wp_reach_radius
+    P.rate_wrapper = int(cfg.rate_wrapper)
+    P.rate_max = math.radians(cfg.rate_max_deg)
+    put("rate_kd", cfg.rate_kd); put("rate_inertia", cfg.rate_inertia)
+    P.rate_ki, P.rate_imax, P.max_torque = cfg.rate_ki, cfg.rate_imax, MAX_TORQUE
     return P
 
 

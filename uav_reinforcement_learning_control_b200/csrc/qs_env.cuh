@@ -32,6 +32,8 @@ struct Env {
     int32_t ep_steps;
     int32_t wp_idx, wp_reached, laps;
     float done_prev;
+    float rate_int[3];     // RateControlWrapper integral state
+    float prev_action[4];  // last policy action (what RelPosActWrapper appends to the observation)
 };
 
 struct StepOut {
@@ -73,11 +75,19 @@ QS_HD void load_env(const QsParams& P, const float* __restrict__ st, int n, int 
     e.step_count = 0; e.voltage = P.v_nominal; e.ep_steps = 0;
     e.episode = for_reset ? f2u_(s[26 * (size_t)n]) : 0u;   // Philox counter word; brax modes only need it in reset
     e.wp_idx = 0; e.wp_reached = 0; e.laps = 0; e.done_prev = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) e.rate_int[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e.prev_action[k] = 0.f;
     if constexpr (M::kGym) {
         e.target[0] = s[21 * (size_t)n]; e.target[1] = s[22 * (size_t)n]; e.target[2] = s[23 * (size_t)n];
         e.step_count = f2i_(s[24 * (size_t)n]);
         if (P.battery) e.voltage = s[25 * (size_t)n];
         e.episode = f2u_(s[26 * (size_t)n]);
+        if (P.rate_wrapper) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) e.rate_int[k] = s[(32 + k) * (size_t)n];
+        }
         if (P.waypoint_mode) {
             e.wp_idx = f2i_(s[28 * (size_t)n]);
             e.wp_reached = f2i_(s[29 * (size_t)n]);
@@ -111,6 +121,12 @@ QS_HD void store_env(const QsParams& P, float* __restrict__ st, int n, int i, co
         s[24 * (size_t)n] = i2f_(e.step_count);
         if (P.battery) s[25 * (size_t)n] = e.voltage;
         s[26 * (size_t)n] = u2f_(e.episode);
+        if (P.rate_wrapper) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s[(32 + k) * (size_t)n] = e.rate_int[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[(35 + k) * (size_t)n] = e.prev_action[k];
+        }
         if (P.waypoint_mode) {
             s[28 * (size_t)n] = i2f_(e.wp_idx);
             s[29 * (size_t)n] = i2f_(e.wp_reached);
@@ -156,6 +172,21 @@ QS_HD void action_to_ctrl(const QsParams& P, const float a[4], float& voltage, f
         const float load = (0.25f * sum) / fmaxf(P.max_motor_thrust, 1e-6f);
         const float dV = fma_(P.v_drop_load, load, P.v_drop_base) * P.dt;
         voltage = clamp_(voltage - dV, P.v_min, P.v_nominal);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// RateControlWrapper.action (envs/rate_wrapper.py:69-98): [thrust, roll/pitch/yaw rate] in [-1,1] ->
+// [thrust, tau_x, tau_y, tau_z] in [-1,1] through a per-axis PI loop on the body rates.
+// ---------------------------------------------------------------------------------------
+QS_HD void rate_to_torque(const QsParams& P, const float a[4], const float w[3], float rate_int[3], float out[4]) {
+    out[0] = a[0];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float err = fma_(a[1 + k], P.rate_max, -w[k]);
+        const float tau_p = P.rate_inertia[k] * P.rate_kd[k] * err;
+        rate_int[k] = clamp_(fma_(P.rate_ki * P.dt, err, rate_int[k]), -P.rate_imax, P.rate_imax);
+        out[1 + k] = clamp_((tau_p + rate_int[k]) / P.max_torque, -1.0f, 1.0f);
     }
 }
 
@@ -304,7 +335,9 @@ QS_HD void reset_env(const QsParams& P, const Tables& T, uint32_t gid, Env& e, f
     e.done_prev = 0.f;
     e.voltage = P.v_nominal;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { e.b.th[k] = 0.f; e.b.s[k] = 0.f; }
+    for (int k = 0; k < 3; ++k) e.rate_int[k] = 0.f;       // RateControlWrapper.reset (rate_wrapper.py:108-111)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { e.b.th[k] = 0.f; e.b.s[k] = 0.f; e.prev_action[k] = 0.f; }
     if constexpr (M::kGym) {
         if (P.waypoint_mode) {
             // evaluate.py:487-497: start on waypoint 0, identity attitude, at rest; target = waypoint 1
@@ -424,7 +457,20 @@ QS_HD void env_step(const QsParams& P, const Tables& T, uint32_t gid, Env& e, co
         if (P.auto_reset == QS_RESET_RESTORE_FIRST && e.done_prev != 0.f) e.ep_steps = 0;
     }
     float ctrl[4];
-    action_to_ctrl(P, a, e.voltage, ctrl);
+    if constexpr (M::kGym) {
+        if (P.rate_wrapper) {
+            // the policy commands body rates; the base env sees torques, _prev_action keeps the rate action
+            float at[4];
+            rate_to_torque(P, a, e.b.w, e.rate_int, at);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e.prev_action[k] = a[k];
+            action_to_ctrl(P, at, e.voltage, ctrl);
+        } else {
+            action_to_ctrl(P, a, e.voltage, ctrl);
+        }
+    } else {
+        action_to_ctrl(P, a, e.voltage, ctrl);
+    }
     physics_step(P, e.b, ctrl);
     e.step_count += 1;
 

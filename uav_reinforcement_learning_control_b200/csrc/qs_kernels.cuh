@@ -118,6 +118,10 @@ __device__ __forceinline__ void block_autoreset(const QsParams& P, const Tables&
 #pragma unroll
         for (int k = 0; k < 12; ++k) obs[k] = d[16 + k];
         e.step_count = 0; e.ep_steps = 0; e.done_prev = 0.f; e.voltage = P.v_nominal;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) e.rate_int[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e.prev_action[k] = 0.f;
     }
 }
 

@@ -60,12 +60,18 @@ class _TargetState:
 class HoverVecEnv:
     def __init__(self, num_envs: int = 16, device=0, *, max_episode_steps: int = 512, battery: bool = True,
                  auto_reset: bool = True, seed: int = 0, env_id_offset: int = 0, cfg: Q.EnvConfig | None = None,
-                 xml_path: str | None = None, sb3_infos: bool | None = None):
+                 xml_path: str | None = None, sb3_infos: bool | None = None, wrapper: str | None = None):
         import torch
         self.torch = torch
+        # wrapper: the reference's WRAPPER_REGISTRY names (envs/wrappers.py:28-29).  "RateControlWrapper" (the SB3
+        # trainer's default, train.py:31) is fused into the step kernel as an action pre-stage; "RelPosActWrapper"
+        # (7-D obs = normalised rel-pos + previous action, envs/wrappers.py:13-25) is a view built here.
+        if wrapper not in (None, "none", "RateControlWrapper", "RelPosActWrapper"):
+            raise KeyError(wrapper)
+        self.wrapper = None if wrapper in (None, "none") else wrapper
         if cfg is None:
             cfg = Q.EnvConfig.hover_gym(battery=battery, max_episode_steps=max_episode_steps, seed=seed,
-                                        env_id_offset=env_id_offset,
+                                        env_id_offset=env_id_offset, rate_wrapper=(wrapper == "RateControlWrapper"),
                                         auto_reset=Q.RESET_RESAMPLE if auto_reset else Q.RESET_NONE)
         self.cfg = cfg
         self.engine = Engine(cfg, num_envs, device=device, xml_path=xml_path)
@@ -74,7 +80,7 @@ class HoverVecEnv:
         D = cfg.obs_dim
         # spaces / bounds (hover_env.py:31-65)
         self.single_action_space = Box(-1.0, 1.0, (4,), np.float32)
-        self.single_observation_space = Box(-1.0, 1.0, (D,), np.float32)
+        self.single_observation_space = Box(-1.0, 1.0, (7 if self.wrapper == "RelPosActWrapper" else D,), np.float32)
         self.action_space = self.single_action_space
         self.observation_space = self.single_observation_space
         self._obs_bounds = Box(cfg.obs_lo, cfg.obs_hi)
@@ -123,6 +129,19 @@ class HoverVecEnv:
         s[:, 0:3] = self._planes[0:3].t()
         return s
 
+    def _wrap_obs(self, obs):
+        if self.wrapper == "RelPosActWrapper":
+            return self.torch.cat([obs[:, 0:3], self._prev_action], dim=1)
+        return obs
+
+    @property
+    def max_rate_rad(self):
+        return float(np.deg2rad(self.cfg.rate_max_deg))
+
+    @property
+    def _rate_int_torque(self):
+        return self._planes[32:35].t()
+
     def _infos(self, finished=None):
         info = {"target": self._planes[21:24].t(), "voltage": self._planes[25],
                 "voltage_scale": (self._planes[25] / self.cfg.v_nominal).clamp(0.0, 1.0)}
@@ -137,8 +156,8 @@ class HoverVecEnv:
     def reset(self, seed=None, options=None):
         self._episode_seed(seed)
         self.engine.reset(self._planes, obs=self._obs)
-        self._prev_action.zero_()
-        return self._obs, self._infos()
+        self._prev_action = self.torch.zeros_like(self._prev_action)
+        return self._wrap_obs(self._obs), self._infos()
 
     def step(self, actions):
         """-> (obs, reward, terminated, truncated, infos); torch in -> torch out, NumPy in -> NumPy out."""
@@ -150,7 +169,9 @@ class HoverVecEnv:
         self.engine.step(self._planes, a, obs=self._obs, reward=self._rew, done=self._term, truncated=self._trunc,
                          terminal_obs=self._terminal_obs)
         finished = (self._term != 0) | (self._trunc != 0)
-        return self._obs, self._rew, self._term != 0, self._trunc != 0, self._infos(finished)
+        if self.wrapper == "RelPosActWrapper" and bool(finished.any()):
+            self._prev_action = self.torch.where(finished[:, None], self.torch.zeros_like(a), a)   # reset() zeroes it
+        return self._wrap_obs(self._obs), self._rew, self._term != 0, self._trunc != 0, self._infos(finished)
 
     def _step_numpy(self, actions):
         torch = self.torch

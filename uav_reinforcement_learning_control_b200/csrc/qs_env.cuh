@@ -196,9 +196,9 @@ QS_HD void rate_to_torque(const QsParams& P, const float a[4], const float w[3],
 // ---------------------------------------------------------------------------------------
 QS_HD void quat_to_rpy(const float q[4], float rpy[3]) {
     const float w = q[0], x = q[1], y = q[2], z = q[3];
-    rpy[0] = atan2f(2.f * fma_(y, z, w * x), fma_(-2.f, fma_(x, x, y * y), 1.f));
+    rpy[0] = atan2_(2.f * fma_(y, z, w * x), fma_(-2.f, fma_(x, x, y * y), 1.f));
     rpy[1] = asinf(clamp_(2.f * fma_(w, y, -x * z), -1.f, 1.f));
-    rpy[2] = atan2f(2.f * fma_(x, y, w * z), fma_(-2.f, fma_(y, y, z * z), 1.f));
+    rpy[2] = atan2_(2.f * fma_(x, y, w * z), fma_(-2.f, fma_(y, y, z * z), 1.f));
 }
 
 // scipy Rotation.from_euler('xyz', [r, p, y]).as_quat() -> wxyz (utils/state.py:59-60)
@@ -282,7 +282,7 @@ QS_HD void evaluate(const QsParams& P, const Tables& T, Env& e, const float* a, 
         bool inside = true;
 #pragma unroll
         for (int i = 0; i < 12; ++i)
-            inside = inside && finite_(s12[i]) && (s12[i] >= P.term_lo[i]) && (s12[i] <= P.term_hi[i]);
+            inside = inside && (s12[i] >= P.term_lo[i]) && (s12[i] <= P.term_hi[i]);   // false for NaN / +-Inf too
         o.done = inside ? 0.f : 1.f;
         o.truncated = (e.step_count >= P.max_episode_steps) ? 1.f : 0.f;
     } else if constexpr (MODE == QS_MODE_MJX_BRAX) {

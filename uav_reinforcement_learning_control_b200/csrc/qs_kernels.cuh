@@ -14,7 +14,14 @@ namespace qs {
 #define QS_STEP_BLOCK 128
 #endif
 #ifndef QS_STEP_MIN_BLOCKS
-#define QS_STEP_MIN_BLOCKS 6   /* <= 80 registers: 24 warps/SM; measured best on B200 (profiles/README.md) */
+#define QS_STEP_MIN_BLOCKS 7   /* <= 72 registers: 28 warps/SM; measured best on B200 (profiles/README.md) */
+#endif
+#ifndef QS_RESET_STRATEGY
+#define QS_RESET_STRATEGY 3   /* step kernel: 0 = inline per-lane reset, 1 = block-level compaction, 2 = warp-cooperative Philox
+                                 (shuffles + __fns), 3 = warp-cooperative Philox through a per-warp shared scratch */
+#endif
+#ifndef QS_USE_PDL
+#define QS_USE_PDL 1          /* step kernel: programmatic dependent launch (griddepcontrol) */
 #endif
 #ifndef QS_OBS_DIRECT
 #define QS_OBS_DIRECT 1   /* 1: per-thread 128-bit obs stores (measured 3 % faster: two barriers fewer);
@@ -125,6 +132,127 @@ __device__ __forceinline__ void block_autoreset(const QsParams& P, const Tables&
     }
 }
 
+// Warp-cooperative alternative without any block barrier: the Philox blocks of up to 8 finished lanes are computed
+// by 32 lanes at once (lane L -> reset L/4, block L%4) and handed to the owners with shuffles; only the cheap
+// post-processing (range map, Euler -> quaternion, observation) runs at low lane efficiency.
+template <int MODE>
+__device__ __forceinline__ void warp_autoreset(const QsParams& P, const Tables& T, uint32_t gid_warp_first, Env& e,
+                                               float* obs, bool need) {
+    static_assert(ModeTraits<MODE>::kGym, "Philox re-sampling exists in the gym modes only");
+    const int lane = threadIdx.x & 31;
+    unsigned pending = __ballot_sync(0xffffffffu, need);
+    while (pending) {
+        const int npass = min(__popc(pending), 8);
+        const int r = lane >> 2, blk = lane & 3;
+        // lane that owns the r-th pending reset (r < npass)
+        const int src = r < npass ? (int)__fns(pending, 0, r + 1) : 0;
+        const uint32_t epi_src = __shfl_sync(0xffffffffu, e.episode, src);
+        U4 rnd = U4{0u, 0u, 0u, 0u};
+        if (r < npass) rnd = philox4x32_10(U4{gid_warp_first + (uint32_t)src, epi_src, (uint32_t)blk, STREAM_RESET}, P.seed_lo, P.seed_hi);
+        const int myrank = __popc(pending & ((1u << lane) - 1u));
+        const bool mine = need && ((pending >> lane) & 1u) && myrank < 8;
+        const int from = (mine ? myrank : 0) * 4;
+        uint32_t w[16];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            w[4 * b + 0] = __shfl_sync(0xffffffffu, rnd.x, from + b);
+            w[4 * b + 1] = __shfl_sync(0xffffffffu, rnd.y, from + b);
+            w[4 * b + 2] = __shfl_sync(0xffffffffu, rnd.z, from + b);
+            w[4 * b + 3] = __shfl_sync(0xffffffffu, rnd.w, from + b);
+        }
+        if (mine) {
+            float s12[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) s12[k] = uniform_(w[k], P.init_lo[k], P.init_hi[k]);
+            e.b.p[0] = s12[0]; e.b.p[1] = s12[1]; e.b.p[2] = s12[2];
+            rpy_to_quat(&s12[3], e.b.q);
+            e.b.v[0] = s12[6]; e.b.v[1] = s12[7]; e.b.v[2] = s12[8];
+            e.b.w[0] = s12[9]; e.b.w[1] = s12[10]; e.b.w[2] = s12[11];
+            if constexpr (MODE == QS_MODE_HOVER_GYM) {
+                e.target[0] = uniform_(w[12], P.target_lo[0], P.target_hi[0]);
+                e.target[1] = uniform_(w[13], P.target_lo[1], P.target_hi[1]);
+                e.target[2] = uniform_(w[14], P.target_lo[2], P.target_hi[2]);
+            } else {
+                e.target[0] = e.b.p[0]; e.target[1] = e.b.p[1]; e.target[2] = e.b.p[2];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { e.b.th[k] = 0.f; e.b.s[k] = 0.f; e.prev_action[k] = 0.f; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) e.rate_int[k] = 0.f;
+            e.step_count = 0; e.ep_steps = 0; e.done_prev = 0.f; e.voltage = P.v_nominal;
+            compute_obs<MODE>(P, e, &s12[3], obs);
+        }
+        // drop the (up to 8) lowest pending bits
+        unsigned done_bits = 0u;
+        unsigned tmp = pending;
+        for (int k = 0; k < npass; ++k) { const unsigned low = tmp & (0u - tmp); done_bits |= low; tmp ^= low; }
+        pending &= ~done_bits;
+    }
+}
+
+// Strategy 3: warp-cooperative reset through a small per-warp shared scratch, no block barrier and no __fns.
+// A finished lane with rank r (among the warp's finished lanes) posts (lane, episode) in slot r; lanes 4r..4r+3 each
+// compute ONE Philox block of that reset and already map their four words to the target ranges (the bounds are
+// indexed by the block id, a constant-bank load), post the four floats, and the owner picks up its 16 values with
+// four 128-bit shared loads.  Only Euler -> quaternion and the observation run at low lane efficiency.  Up to 8
+// resets per pass; more (rare: the mean is ~3.5 per warp under random policies) loop.  Same arithmetic as reset_env.
+struct WarpResetScratch {
+    uint32_t src[8];
+    uint32_t epi[8];
+    float4 val[32];
+};
+
+template <int MODE>
+__device__ __forceinline__ void warp_autoreset_smem(const QsParams& P, uint32_t gid_warp_first, Env& e, float* obs,
+                                                    bool need, WarpResetScratch& S) {
+    static_assert(ModeTraits<MODE>::kGym, "Philox re-sampling exists in the gym modes only");
+    const int lane = threadIdx.x & 31;
+    unsigned pending = __ballot_sync(0xffffffffu, need);
+    while (pending) {                                   // warp-uniform
+        const int rank = __popc(pending & ((1u << lane) - 1u));
+        const bool mine = ((pending >> lane) & 1u) && rank < 8;
+        if (mine) { S.src[rank] = (uint32_t)lane; S.epi[rank] = e.episode; }
+        __syncwarp();
+        const int npass = min(__popc(pending), 8);
+        const int r = lane >> 2, blk = lane & 3;
+        constexpr int kBlocks = (MODE == QS_MODE_HOVER_GYM) ? 4 : 3;
+        if (r < npass && blk < kBlocks) {
+            const U4 rnd = philox4x32_10(U4{gid_warp_first + S.src[r], S.epi[r], (uint32_t)blk, STREAM_RESET}, P.seed_lo, P.seed_hi);
+            // words 0..11 -> state12 ranges, 12..14 -> target ranges: both live in one table of 16 (lo, hi) pairs
+            const float* lo = blk < 3 ? &P.init_lo[4 * blk] : &P.target_lo[0];
+            const float* hi = blk < 3 ? &P.init_hi[4 * blk] : &P.target_hi[0];
+            float4 v;
+            v.x = uniform_(rnd.x, lo[0], hi[0]);
+            v.y = uniform_(rnd.y, lo[1], hi[1]);
+            v.z = uniform_(rnd.z, lo[2], hi[2]);
+            v.w = blk < 3 ? uniform_(rnd.w, lo[3], hi[3]) : 0.f;
+            S.val[lane] = v;
+        }
+        __syncwarp();
+        if (mine) {
+            const float4 a = S.val[4 * rank], b = S.val[4 * rank + 1], c = S.val[4 * rank + 2];
+            e.b.p[0] = a.x; e.b.p[1] = a.y; e.b.p[2] = a.z;
+            float rpy[3] = {a.w, b.x, b.y};
+            rpy_to_quat(rpy, e.b.q);
+            e.b.v[0] = b.z; e.b.v[1] = b.w; e.b.v[2] = c.x;
+            e.b.w[0] = c.y; e.b.w[1] = c.z; e.b.w[2] = c.w;
+            if constexpr (MODE == QS_MODE_HOVER_GYM) {
+                const float4 d = S.val[4 * rank + 3];
+                e.target[0] = d.x; e.target[1] = d.y; e.target[2] = d.z;
+            } else {
+                e.target[0] = e.b.p[0]; e.target[1] = e.b.p[1]; e.target[2] = e.b.p[2];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { e.b.th[k] = 0.f; e.b.s[k] = 0.f; e.prev_action[k] = 0.f; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) e.rate_int[k] = 0.f;
+            e.step_count = 0; e.ep_steps = 0; e.done_prev = 0.f; e.voltage = P.v_nominal;
+            compute_obs<MODE>(P, e, rpy, obs);
+        }
+        pending &= ~__ballot_sync(0xffffffffu, mine);   // also orders this pass's shared reads before the next pass's writes
+    }
+}
+
 // whether this launch uses the compacted path (block-uniform)
 template <int MODE>
 __device__ __forceinline__ bool use_compaction(const QsParams& P) {
@@ -150,10 +278,21 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
     constexpr int D = ModeTraits<MODE>::kObsDim;
     constexpr bool kGym = ModeTraits<MODE>::kGym;
     // gym modes: reset scratch; brax modes: staging tile for the 21-float observation rows
-    __shared__ __align__(16) unsigned char smem_raw[kGym ? sizeof(ResetScratch<kBlock>) : sizeof(float) * kBlock * (D + 1)];
+#if QS_RESET_STRATEGY == 1 || !QS_OBS_DIRECT
+    constexpr size_t kGymScratch = sizeof(ResetScratch<kBlock>);
+#else
+    constexpr size_t kGymScratch = sizeof(WarpResetScratch) * (kBlock / 32);
+#endif
+    __shared__ __align__(16) unsigned char smem_raw[kGym ? kGymScratch : sizeof(float) * kBlock * (D + 1)];
     const int block_first = lo + blockIdx.x * kBlock;
     const int i = block_first + threadIdx.x;
     const bool valid = i < lo + count;
+#if QS_USE_PDL
+    // programmatic dependent launch (quadsim.cu: launch_step): let the next kernel on the stream start its ramp-up
+    // now, and do not touch global memory before everything launched ahead of us has completed and flushed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     float o_[D];
     Env e;
     StepOut so;
@@ -190,8 +329,21 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
                     compute_obs<MODE>(P, e, rpy, o_);
                 }
             } else {
+#if QS_RESET_STRATEGY == 1
                 block_autoreset<MODE, kBlock>(P, T, P.env_id_offset + (uint32_t)block_first, e, o_, so.needs_reset, 0,
                                               *reinterpret_cast<ResetScratch<kBlock>*>(smem_raw));
+#elif QS_RESET_STRATEGY == 2
+                warp_autoreset<MODE>(P, T, P.env_id_offset + (uint32_t)(i - (int)(threadIdx.x & 31)), e, o_, so.needs_reset);
+#elif QS_RESET_STRATEGY == 3
+                warp_autoreset_smem<MODE>(P, P.env_id_offset + (uint32_t)(i - (int)(threadIdx.x & 31)), e, o_, so.needs_reset,
+                                          reinterpret_cast<WarpResetScratch*>(smem_raw)[threadIdx.x >> 5]);
+#else
+                if (so.needs_reset) {
+                    float rpy[3];
+                    reset_env<MODE>(P, T, P.env_id_offset + (uint32_t)i, e, rpy);
+                    compute_obs<MODE>(P, e, rpy, o_);
+                }
+#endif
             }
         }
         // one store sequence for all lanes (splitting it by needs_reset makes nearly every warp run it twice)

@@ -26,6 +26,13 @@
 namespace qs {
 namespace tc {
 
+// -DQS_TC_PROFILE: per-phase clock64 accounting of the step loop, printed by thread 0 of CTA 0 (tuning builds only)
+#ifdef QS_TC_PROFILE
+#define QS_TCP(k) do { const long long c_ = clock64(); prof_[k] += c_ - pc_; pc_ = c_; } while (0)
+#else
+#define QS_TCP(k) do { } while (0)
+#endif
+
 constexpr int kM = 128;                 // envs per tile = UMMA M
 // TILES (template): independent 128-env tiles per CTA sharing the weights; 2 for large batches (2 warps per SMSP),
 // 1 when the batch is too small to fill the SMs with 256-env CTAs
@@ -266,6 +273,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         for (int k = 0; k < D; ++k) obs_[k] = 0.f;
     }
 
+#ifdef QS_TC_PROFILE
+    long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long pc_ = clock64();
+#endif
     // forward pass for the observation in `o`; returns head[Ao] and value
     auto forward = [&](const float* o, float* head, float& value) {
         // A1: normalised obs, bf16, K padded 12 -> 16
@@ -286,8 +297,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             mma_bf16(tmem, dA1, dW1, idesc_l1, 0u);                         // D1[128 x 256] = A1 . W1cat
             mma_commit(bar);
         }
+        QS_TCP(0);
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
+        QS_TCP(1);
         // epilogue 1: h1 = relu(D1 + b1) -> bf16 A2A | A2C
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
@@ -302,6 +315,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                                pack_relu_bf16(h[6], h[7]));
             }
         }
+        QS_TCP(2);
         fence_async_smem();
         fence_before();
         tile_sync(tile);
@@ -321,6 +335,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
+        QS_TCP(3);
         // epilogue 2: h2 = relu(D2 + b2) -> bf16, written over A2A | A2C (the L2 MMAs have completed)
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
@@ -340,6 +355,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                                pack_relu_bf16(h[6], h[7]));
             }
         }
+        QS_TCP(4);
         fence_async_smem();
         fence_before();
         tile_sync(tile);
@@ -357,6 +373,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
+        QS_TCP(5);
         {
             float v[32];
             tmem_ld32(my_tmem, v);
@@ -365,6 +382,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             value = v[16] + sF[Smem::kB3 + 16];
         }
         fence_before();       // the next forward's MMAs overwrite TMEM: order our loads before the coming barrier
+        QS_TCP(6);
     };
 
     for (int t = 0; t < steps; ++t) {
@@ -375,6 +393,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             dd[1] = make_float4(obs_[4], obs_[5], obs_[6], obs_[7]);
             dd[2] = make_float4(obs_[8], obs_[9], obs_[10], obs_[11]);
         }
+        QS_TCP(11);
         float head[Ao], value;
         forward(obs_, head, value);
 
@@ -417,9 +436,11 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             if (rb.act) reinterpret_cast<float4*>(rb.act)[o] = make_float4(raw[0], raw[1], raw[2], raw[3]);
             if (rb.logp) rb.logp[o] = logp;
             if (rb.value) rb.value[o] = value;
+            QS_TCP(7);
             env_step<MODE, true>(P, T, gid, e, act, obs_, tobs, first ? first + b0 + tid : nullptr, n, so);
             need_boot = bootstrap_gamma > 0.f && so.finished && so.truncated != 0.f && so.done == 0.f;
         }
+        QS_TCP(8);
         // Philox re-sampling of finished envs, compacted per tile.  The scratch lives in this tile's A2A buffer,
         // which is idle between the head MMAs of this step and the first epilogue of the next one.
         if (P.auto_reset == QS_RESET_RESAMPLE) {
@@ -436,6 +457,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 tile_sync(tile);      // every owner has read its row before the buffer becomes an MMA operand again
             }
         }
+        QS_TCP(9);
         // SB3 timeout bootstrap: reward += gamma * V(terminal_obs) for truncated-not-terminated episodes
         if (tile_or(tile, need_boot)) {
             float h2[Ao], vt;
@@ -447,7 +469,14 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             if (rb.done) rb.done[o] = so.done;
             if (rb.trunc) rb.trunc[o] = so.truncated;
         }
+        QS_TCP(10);
     }
+#ifdef QS_TC_PROFILE
+    if (blockIdx.x == 0 && (gtid == 0 || gtid == NT - 1))
+        printf("tcprof tid %d steps %d: A1+sync %lld | L1wait %lld | epi1 %lld | L2 sync+wait %lld | epi2 %lld | L3 sync+wait %lld | head %lld | sample %lld | env %lld | reset %lld | boot+store %lld | obs store %lld (cycles/step)\n",
+               gtid, steps, prof_[0] / steps, prof_[1] / steps, prof_[2] / steps, prof_[3] / steps, prof_[4] / steps, prof_[5] / steps,
+               prof_[6] / steps, prof_[7] / steps, prof_[8] / steps, prof_[9] / steps, prof_[10] / steps, prof_[11] / steps);
+#endif
 
     {
         float head[Ao], value;

@@ -173,9 +173,25 @@ static int launch_step(QsHandle h, int lo, int count, float* state, const float*
         return check_launch("step_kernel_pf");
     }
 #endif
+#if QS_USE_PDL
+    // Programmatic dependent launch: the step kernel signals launch_dependents at its top and waits for its
+    // predecessors (griddepcontrol.wait) before its first global access, so the launch latency, CTA ramp-up and
+    // parameter set-up of step k+1 overlap the drain of whatever ran before it on the stream.
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)nblocks(count, qs::kBlock)); lc.blockDim = dim3(qs::kBlock); lc.dynamicSmemBytes = 0; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    const float4* a4 = (const float4*)action;
+    QS_DISPATCH_MODE(h->P.mode, (cudaLaunchKernelEx(&lc, qs::step_kernel<M_>, h->P, h->tables(), (int)h->n, lo, count, state, a4,
+        obs, reward, done, truncated, metrics, terminal_obs, first_state)));
+#else
     QS_DISPATCH_MODE(h->P.mode, (qs::step_kernel<M_><<<nblocks(count, qs::kBlock), qs::kBlock, 0, s>>>(
         h->P, h->tables(), h->n, lo, count, state, (const float4*)action, obs, reward, done, truncated, metrics,
         terminal_obs, first_state)));
+#endif
     return check_launch("step_kernel");
 }
 

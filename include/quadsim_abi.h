@@ -128,6 +128,10 @@ typedef struct QsParams {
     float rate_inertia[3];            /* IXX, IYY, IZZ of utils/drone_config.py   */
     float rate_ki, rate_imax;         /* integral gain (torque space), anti-windup clamp */
     float max_torque;                 /* normalisation of the torque command (0.5 N m) */
+    /* --- TrajectoryFollowEnv spline reference (envs/trajectory_follow_env.py:55-58,176-218) --- */
+    float spline_duration;            /* traj_duration_seconds (30); <= 0: sample times are arange(N) * dt */
+    float traj_center_lo[3], traj_center_hi[3];   /* centre ~ U(lo, hi)                         */
+    float traj_amp[3];                /* waypoint offsets ~ U(-amp, amp): 0.6, 0.6, 0.4          */
     int32_t reserved[5];
 } QsParams;
 
@@ -241,6 +245,18 @@ int qs_rollout_policy(QsHandle h, float* state, const QsPolicyDesc* desc, const 
 int qs_gae(int32_t T, int32_t B, const float* reward, const float* value, const float* done,
            const float* trunc, const float* last_value, float gamma, float lam, int32_t brax_form,
            float* adv, float* ret, void* stream);
+
+/*
+ * qs_traj_info: TrajectoryFollowEnv's info["target" | "target_vel" | "target_acc"] (envs/trajectory_follow_env.py:
+ * 162-168 in step, :245-250 in reset), out9 [B][9] float32 = pos(3) | vel(3) | acc(3) of each env's natural-cubic-
+ * spline reference (:176-218).  Nothing is stored per env: the spline of an episode is re-derived from the Philox
+ * draws of (seed, global env id, episode).  `episode` / `sample_index` (device, [B]; either may be NULL) override
+ * the state's episode plane (26) and the default index clamp(step_count - 1, 0, N - 1): a caller that wants the
+ * info of the step that just ran -- including envs that were auto-reset by it -- passes copies of planes 26 and 24
+ * taken before the step.  QS_MODE_TRAJ_GYM only.
+ */
+int qs_traj_info(QsHandle h, const float* state, const uint32_t* episode, const int32_t* sample_index, float* out9,
+                 void* stream);
 
 /*
  * Host-buffer convenience entry (what a non-torch binding of Env.step would call):

@@ -57,19 +57,26 @@ def bf16_round(a):
     return r.astype(np.uint32).view(np.float32).astype(np.float64)
 
 
+def bias_hilo(b):
+    """Bias as the tcgen05 path feeds it to the MMA: a bf16 high part plus a bf16 low part (two K slots)."""
+    hi = bf16_round(b)
+    return hi + bf16_round(np.asarray(b, dtype=np.float64) - hi)
+
+
 def forward(pp, obs, bf16=False):
     """bf16=True models the tcgen05 path: every MMA operand (activations and weights of all three layers)
-    rounded to bfloat16, products and sums in (at least) float32, biases added in float32."""
+    rounded to bfloat16, products and sums in (at least) float32; the layer-1 and layer-2 biases ride inside
+    the MMAs as bf16 hi + lo pairs (bias_hilo), the head biases are added in float32."""
     q = bf16_round if bf16 else (lambda a: np.asarray(a, dtype=np.float64))
+    qb = bias_hilo if bf16 else (lambda a: np.asarray(a, dtype=np.float64))
     x = (np.asarray(obs, dtype=np.float32) - pp["mean"].astype(np.float32)) * pp["inv_std"].astype(np.float32) if bf16 \
         else (np.asarray(obs, dtype=np.float64) - pp["mean"]) * pp["inv_std"]
     x = q(x)
-    b1a, b1c = (q(pp["ab1"]), q(pp["cb1"])) if bf16 else (pp["ab1"], pp["cb1"])     # tcgen05 path: layer-1 bias rides in the MMA
-    h = np.maximum(x @ q(pp["aW1"]) + b1a, 0.0)
-    h = np.maximum(q(h) @ q(pp["aW2"]) + pp["ab2"], 0.0)
+    h = np.maximum(x @ q(pp["aW1"]) + qb(pp["ab1"]), 0.0)
+    h = np.maximum(q(h) @ q(pp["aW2"]) + qb(pp["ab2"]), 0.0)
     head = q(h) @ q(pp["aW3"]) + pp["ab3"]
-    c = np.maximum(x @ q(pp["cW1"]) + b1c, 0.0)
-    c = np.maximum(q(c) @ q(pp["cW2"]) + pp["cb2"], 0.0)
+    c = np.maximum(x @ q(pp["cW1"]) + qb(pp["cb1"]), 0.0)
+    c = np.maximum(q(c) @ q(pp["cW2"]) + qb(pp["cb2"]), 0.0)
     value = q(c) @ q(pp["cW3"]) + pp["cb3"][0]
     return head, value
 

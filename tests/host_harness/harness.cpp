@@ -10,6 +10,7 @@
 #include <math.h>
 
 #include "../../uav_reinforcement_learning_control_b200/csrc/qs_env.cuh"
+#include "../../uav_reinforcement_learning_control_b200/csrc/qs_traj.cuh"
 
 using namespace qs;
 
@@ -125,6 +126,11 @@ int hh_physics(const QsParams* P, int n, float* state, const float* ctrl) {
         physics_step(*P, e.b, ctrl + 4 * (size_t)i);
         store_env<QS_MODE_HOVER_BRAX>(*P, state, n, i, e);
     }
+    return 0;
+}
+
+int hh_traj_info(const QsParams* P, int n, const uint32_t* episode, const int32_t* sample_index, float* out9) {
+    for (int i = 0; i < n; ++i) traj_info_eval(*P, P->env_id_offset + (uint32_t)i, episode[i], sample_index[i], out9 + 9 * (size_t)i);
     return 0;
 }
 

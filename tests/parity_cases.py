@@ -274,3 +274,32 @@ def check_lap_completion(backend_factory):
         laps_seen = int(s["laps"].sum())
     assert laps_seen == n              # every env completed exactly one lap and was reset to waypoint 0 / target 1
     np.testing.assert_array_equal(planes_view(st)["episode"], 1)
+
+
+def check_traj_info(backend_factory, n=256):
+    """TrajectoryFollowEnv info target / target_vel / target_acc: engine vs scipy (oracle/traj_spline.py)."""
+    from oracle import traj_spline
+    for kw in (dict(), dict(seed=99, env_id_offset=1000, spline_duration=None, max_episode_steps=300)):
+        cfg = Q.EnvConfig.traj_gym(**kw)
+        backend = backend_factory(cfg)
+        rng = np.random.default_rng(3)
+        episode = rng.integers(0, 50, n).astype(np.uint32)
+        N = cfg.max_episode_steps
+        idx = rng.integers(0, N, n).astype(np.int32)
+        idx[:8] = [0, 0, N - 1, N - 1, 1, N - 2, N // 2, N // 3]
+        got = backend.traj_info(episode, idx)
+        ids = np.arange(n, dtype=np.uint32) + np.uint32(cfg.env_id_offset)
+        want = traj_spline.info(cfg, ids, episode, idx)
+        # float64 spline on both sides, cast to float32: agreement to float32 rounding
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+        # the trajectory starts at the drone's start position (trajectory_follow_env.py:208-209, 241-243) ...
+        start, _, n_wp, _ = traj_spline.draws(cfg, ids, episode)
+        at0 = backend.traj_info(episode, np.zeros(n, np.int32))
+        np.testing.assert_allclose(at0[:, 0:3], start, rtol=0, atol=1e-6)
+        # ... with zero curvature at both ends (natural boundary condition)
+        atN = backend.traj_info(episode, np.full(n, N - 1, np.int32))
+        assert np.abs(at0[:, 6:9]).max() < 1e-5 and np.abs(atN[:, 6:9]).max() < 1e-4
+        assert set(np.unique(n_wp)) <= {3, 4, 5} and len(np.unique(n_wp)) == 3
+        # out-of-range indices clamp like min(step_count - 1, N - 1) / the reset info at index 0
+        np.testing.assert_array_equal(backend.traj_info(episode, np.full(n, -1, np.int32)), at0)
+        np.testing.assert_array_equal(backend.traj_info(episode, np.full(n, N + 7, np.int32)), atN)

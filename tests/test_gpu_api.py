@@ -124,3 +124,34 @@ def test_rate_control_wrapper_fused():
     act = torch.rand(16, 4, device=env2.device) * 0.2 - 0.1; act[:, 0] = -0.958
     obs, *_ = env2.step(act)
     assert torch.equal(obs[:, 3:], act) and env2.observation_space.shape == (7,)
+
+
+def test_trajectory_follow_vec_env_spline_info():
+    """TrajectoryFollowEnv through the vector facade: info target / target_vel / target_acc follow the spline of the
+    episode the step belongs to (envs/trajectory_follow_env.py:162-168), the obs / reward target stays at the start
+    position (Q7), and an auto-reset switches to the next episode's spline."""
+    import numpy as np
+    import torch
+    from oracle import traj_spline
+    from uav_reinforcement_learning_control_b200 import config as Q
+    from uav_reinforcement_learning_control_b200.gym_vec import HoverVecEnv
+    n = 64
+    cfg = Q.EnvConfig.traj_gym(auto_reset=Q.RESET_RESAMPLE, seed=5, max_episode_steps=40)
+    env = HoverVecEnv(n, cfg=cfg)
+    obs, info = env.reset()
+    ids = np.arange(n, dtype=np.uint32)
+    want0 = traj_spline.info(cfg, ids, np.zeros(n, np.uint32), np.zeros(n, np.int64))
+    np.testing.assert_allclose(info["target"].cpu().numpy(), want0[:, 0:3], atol=2e-6)
+    np.testing.assert_allclose(info["target_vel"].cpu().numpy(), want0[:, 3:6], atol=2e-6)
+    start = env._planes[0:3].t().clone()
+    assert torch.allclose(info["target"], start, atol=1e-6)              # the spline starts at the drone
+    hover = torch.tensor([[-0.9, 0.0, 0.0, 0.0]], device=env.device).repeat(n, 1)
+    episode = np.zeros(n, np.uint32); sc = np.zeros(n, np.int64)
+    for t in range(60):
+        obs, rew, term, trunc, info = env.step(hover)
+        want = traj_spline.info(cfg, ids, episode, sc)                   # idx = step_count - 1 with step_count = sc + 1
+        np.testing.assert_allclose(info["target"].cpu().numpy(), want[:, 0:3], atol=2e-6)
+        np.testing.assert_allclose(info["target_acc"].cpu().numpy(), want[:, 6:9], atol=2e-5)
+        fin = (term | trunc).cpu().numpy()
+        episode = episode + fin.astype(np.uint32); sc = np.where(fin, 0, sc + 1)
+    assert episode.min() >= 1                                            # every env went through an auto-reset

@@ -82,3 +82,41 @@ def test_horizon_error_curve_512_steps():
     assert c["pos_med"][-1] < 5e-3
     assert c["quat_max"][-1] < 1e-3 and c["obs_max"][-1] < 5e-3
     assert res["mean_distance_to_target_at_end_m"] < 0.2      # the controller did reach the targets
+
+
+def test_lean_step_kernel_matches_general_kernel():
+    """qs_step picks the feature-folded step_kernel<HOVER_GYM, FeatLean> when the handle is the plain north-star
+    configuration and neither metrics nor terminal_obs is requested.  Same inputs through both instantiations:
+    masks / counters / episode indices bit-exact, floats to float32 rounding (the general one is checked against
+    the oracle above)."""
+    import torch
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    cfg = pc.CONFIGS["north_star"]()
+    for n in (4096, 1000):                       # full tiles, and a ragged tail
+        st, act, _ = pc.synth_inputs(cfg, n, seed=5)
+        eng = Engine(cfg, n, device=0)
+        a_st = torch.from_numpy(st.copy()).cuda(); b_st = torch.from_numpy(st.copy()).cuda()
+        d_act = torch.from_numpy(act).cuda()
+        trunc_a = torch.zeros(n, device="cuda"); trunc_b = torch.zeros(n, device="cuda")
+        met = torch.zeros(4, n, device="cuda"); term = torch.zeros(n, 12, device="cuda")
+        oa, ra, da = eng.step(a_st, d_act, truncated=trunc_a, metrics=met, terminal_obs=term)     # general kernel
+        ob, rb, db = eng.step(b_st, d_act, truncated=trunc_b)                                      # lean kernel
+        torch.cuda.synchronize()
+        assert torch.equal(da, db) and torch.equal(trunc_a, trunc_b)
+        pa, pb = planes_view(a_st.cpu().numpy()), planes_view(b_st.cpu().numpy())
+        for k in ("step_count", "episode"):
+            np.testing.assert_array_equal(pa[k], pb[k], err_msg=k)
+        assert da.sum().item() > n // 20          # the synthetic states do straddle the bounds -> resets happened
+        ok = np.isfinite(pa["qpos"]).all(axis=1) & np.isfinite(pa["qvel"]).all(axis=1)
+        assert_close(pb["qpos"][ok], pa["qpos"][ok], rtol=1e-6, atol=1e-7, what="lean vs general qpos")
+        assert_close(pb["qvel"][ok], pa["qvel"][ok], rtol=1e-6, atol=1e-6, what="lean vs general qvel")
+        np.testing.assert_array_equal(pa["target"], pb["target"])
+        fo = torch.isfinite(oa).all(dim=1).cpu().numpy()
+        assert_close(ob.cpu().numpy()[fo], oa.cpu().numpy()[fo], rtol=1e-6, atol=1e-6, what="lean vs general obs")
+        fr = torch.isfinite(ra).cpu().numpy()
+        assert_close(rb.cpu().numpy()[fr], ra.cpu().numpy()[fr], rtol=1e-6, atol=1e-7, what="lean vs general reward")
+
+
+def test_traj_spline_info_vs_scipy():
+    """qs_traj_info against oracle/traj_spline.py, which calls scipy's CubicSpline like the reference."""
+    pc.check_traj_info(GpuBackend, n=512)

@@ -35,3 +35,9 @@ def test_waypoint_advance_bit_exact(auto_reset):
 
 def test_waypoint_lap_completion():
     pc.check_lap_completion(HostHarness)
+
+
+def test_traj_spline_info_vs_scipy():
+    """TrajectoryFollowEnv spline reference (envs/trajectory_follow_env.py:176-218): the kernels' closed form
+    (csrc/qs_traj.cuh, host build) against scipy.interpolate.CubicSpline(bc_type='natural') on the same draws."""
+    pc.check_traj_info(HostHarness, n=256)

@@ -100,7 +100,7 @@ class HostHarness:
             src = os.path.join(HARNESS_DIR, "harness.cpp")
             csrc = os.path.join(ROOT, "uav_reinforcement_learning_control_b200", "csrc")
             deps = [src, os.path.join(ROOT, "include", "quadsim_abi.h")] + [
-                os.path.join(csrc, f) for f in ("qs_env.cuh", "qs_dynamics.cuh", "qs_philox.cuh", "qs_math.cuh")]
+                os.path.join(csrc, f) for f in ("qs_env.cuh", "qs_dynamics.cuh", "qs_philox.cuh", "qs_math.cuh", "qs_traj.cuh")]
             if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
                 subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC",
                                        "-o", so, src])
@@ -145,6 +145,14 @@ class HostHarness:
                                    _fp(rew), _fp(done))
         assert rc == 0
         return obs, rew, done
+
+    def traj_info(self, episode, sample_index):
+        n = len(episode)
+        epi = np.ascontiguousarray(episode, dtype=np.uint32); idx = np.ascontiguousarray(sample_index, dtype=np.int32)
+        out = np.zeros((n, 9), np.float32)
+        rc = self.lib().hh_traj_info(C.byref(self.P), n, _fp(epi), _fp(idx), _fp(out))
+        assert rc == 0
+        return out
 
     def physics(self, st, ctrl):
         ctrl = np.ascontiguousarray(ctrl, dtype=np.float32)
@@ -223,6 +231,16 @@ class GpuBackend:
         obs, rew, done = eng.observe(self._up(st), None if action is None else self._up(np.asarray(action, np.float32)))
         torch.cuda.synchronize()
         return obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+
+    def traj_info(self, episode, sample_index):
+        import torch
+        n = len(episode)
+        eng = self._engine(n)
+        st = eng.new_state()
+        out = eng.traj_info(st, episode=self._up(np.asarray(episode, dtype=np.uint32).view(np.int32)),
+                            sample_index=self._up(np.asarray(sample_index, dtype=np.int32)))
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
 
     def physics(self, st, ctrl):
         import torch

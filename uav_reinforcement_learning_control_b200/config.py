@@ -59,6 +59,8 @@ class QsParams(C.Structure):
         ("wp_reach_radius", C.c_float),
         ("rate_wrapper", C.c_int32), ("rate_max", C.c_float), ("rate_kd", C.c_float * 3),
         ("rate_inertia", C.c_float * 3), ("rate_ki", C.c_float), ("rate_imax", C.c_float), ("max_torque", C.c_float),
+        ("spline_duration", C.c_float), ("traj_center_lo", C.c_float * 3), ("traj_center_hi", C.c_float * 3),
+        ("traj_amp", C.c_float * 3),
         ("reserved", C.c_int32 * 5),
     ]
 
@@ -136,6 +138,12 @@ class EnvConfig:
     rate_ki: float = 0.025
     rate_imax: float = 0.01
     rate_inertia: tuple = (4.16e-4, 4.23e-4, 5.37e-4)   # IXX, IYY, IZZ (utils/drone_config.py:15-17)
+    # TrajectoryFollowEnv spline reference (envs/trajectory_follow_env.py:25,55-58,203)
+    spline_duration: float | None = 30.0          # traj_duration_seconds; None: sample times = arange(N) * dt
+    dt_nominal: float = 0.01                      # model timestep, used only when spline_duration is None
+    traj_center_lo: tuple = (-1.0, -1.0, 0.4)
+    traj_center_hi: tuple = (1.0, 1.0, 1.4)
+    traj_amp: tuple = (0.6, 0.6, 0.4)
 
     # ---- the reference's five env variants -------------------------------------------
     @staticmethod
@@ -257,6 +265,8 @@ def pack_params(c: QuadConstants, cfg: EnvConfig) -> QsParams:
     P.rate_max = math.radians(cfg.rate_max_deg)
     put("rate_kd", cfg.rate_kd); put("rate_inertia", cfg.rate_inertia)
     P.rate_ki, P.rate_imax, P.max_torque = cfg.rate_ki, cfg.rate_imax, MAX_TORQUE
+    P.spline_duration = float(cfg.spline_duration) if cfg.spline_duration is not None else 0.0
+    put("traj_center_lo", cfg.traj_center_lo); put("traj_center_hi", cfg.traj_center_hi); put("traj_amp", cfg.traj_amp)
     return P
 
 

@@ -171,7 +171,7 @@ QS_HD void physics_step(const QsParams& P, Body& b, const float ctrl[4]) {
         const float nx = b.w[0], ny = b.w[1], nz = b.w[2];
         const float n2 = fma_(nx, nx, fma_(ny, ny, nz * nz));
         float sn, cs, k;
-        if (n2 > 0.f) {
+        if (n2 > 1e-30f) {                  // |w| < 1e-15 (mjMINVAL): mju_quatIntegrate applies no rotation
             const float inv = rsqrt_(n2);
             const float n = n2 * inv;
             sincos_(0.5f * dt * n, &sn, &cs);

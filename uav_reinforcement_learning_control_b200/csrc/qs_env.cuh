@@ -22,6 +22,12 @@ template <int MODE> struct ModeTraits {
     static constexpr int kObsDim = kGym ? 12 : 21;
 };
 
+// Compile-time feature gates.  FeatAll (default) leaves every optional stage under its run-time QsParams flag;
+// FeatLean folds them away for the plain north-star configuration (no battery sag, no rate wrapper, no waypoint
+// table, no action pre-clip), which the step launcher selects when the handle's flags allow it.
+struct FeatAll { static constexpr bool kBattery = true, kRate = true, kWaypoint = true, kPreClip = true; };
+struct FeatLean { static constexpr bool kBattery = false, kRate = false, kWaypoint = false, kPreClip = false; };
+
 // Per-env registers.  Which members are live (and which planes are touched in HBM) depends on MODE.
 struct Env {
     Body b;
@@ -59,7 +65,7 @@ QS_HD float u2f_(uint32_t u) { union { float f; uint32_t u; } v; v.u = u; return
 // planar state <-> registers.  Only the planes the MODE / flags need are touched, which is
 // what keeps a hover step at 27 words in + 27 words out per env (include/quadsim_abi.h).
 // ---------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, class F = FeatAll>
 QS_HD void load_env(const QsParams& P, const float* __restrict__ st, int n, int i, Env& e, bool for_reset = false) {
     using M = ModeTraits<MODE>;
     const float* s = st + i;
@@ -82,13 +88,13 @@ QS_HD void load_env(const QsParams& P, const float* __restrict__ st, int n, int 
     if constexpr (M::kGym) {
         e.target[0] = s[21 * (size_t)n]; e.target[1] = s[22 * (size_t)n]; e.target[2] = s[23 * (size_t)n];
         e.step_count = f2i_(s[24 * (size_t)n]);
-        if (P.battery) e.voltage = s[25 * (size_t)n];
+        if (F::kBattery && P.battery) e.voltage = s[25 * (size_t)n];
         e.episode = f2u_(s[26 * (size_t)n]);
-        if (P.rate_wrapper) {
+        if (F::kRate && P.rate_wrapper) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) e.rate_int[k] = s[(32 + k) * (size_t)n];
         }
-        if (P.waypoint_mode) {
+        if (F::kWaypoint && P.waypoint_mode) {
             e.wp_idx = f2i_(s[28 * (size_t)n]);
             e.wp_reached = f2i_(s[29 * (size_t)n]);
             e.laps = f2i_(s[30 * (size_t)n]);
@@ -104,7 +110,7 @@ QS_HD void load_env(const QsParams& P, const float* __restrict__ st, int n, int 
     }
 }
 
-template <int MODE>
+template <int MODE, class F = FeatAll>
 QS_HD void store_env(const QsParams& P, float* __restrict__ st, int n, int i, const Env& e) {
     using M = ModeTraits<MODE>;
     float* s = st + i;
@@ -119,15 +125,15 @@ QS_HD void store_env(const QsParams& P, float* __restrict__ st, int n, int i, co
     if constexpr (M::kGym) {
         s[21 * (size_t)n] = e.target[0]; s[22 * (size_t)n] = e.target[1]; s[23 * (size_t)n] = e.target[2];
         s[24 * (size_t)n] = i2f_(e.step_count);
-        if (P.battery) s[25 * (size_t)n] = e.voltage;
+        if (F::kBattery && P.battery) s[25 * (size_t)n] = e.voltage;
         s[26 * (size_t)n] = u2f_(e.episode);
-        if (P.rate_wrapper) {
+        if (F::kRate && P.rate_wrapper) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) s[(32 + k) * (size_t)n] = e.rate_int[k];
 #pragma unroll
             for (int k = 0; k < 4; ++k) s[(35 + k) * (size_t)n] = e.prev_action[k];
         }
-        if (P.waypoint_mode) {
+        if (F::kWaypoint && P.waypoint_mode) {
             s[28 * (size_t)n] = i2f_(e.wp_idx);
             s[29 * (size_t)n] = i2f_(e.wp_reached);
             s[30 * (size_t)n] = i2f_(e.laps);
@@ -146,21 +152,22 @@ QS_HD void store_env(const QsParams& P, float* __restrict__ st, int n, int i, co
 // ---------------------------------------------------------------------------------------
 // action -> motor forces   (hover_env.py:169-177; train_brax_ppo.py:309-314)
 // ---------------------------------------------------------------------------------------
+template <class F = FeatAll>
 QS_HD void action_to_ctrl(const QsParams& P, const float a[4], float& voltage, float ctrl[4]) {
     float u[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         // (a + 1) / 2 * (hi - lo) + lo
         u[i] = fma_((a[i] + 1.0f) * 0.5f, P.act_hi[i] - P.act_lo[i], P.act_lo[i]);
-        if (P.pre_clip_action) u[i] = clamp_(u[i], P.act_lo[i], P.act_hi[i]);   // Q1
+        if (F::kPreClip && P.pre_clip_action) u[i] = clamp_(u[i], P.act_lo[i], P.act_hi[i]);   // Q1
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float F = fma_(P.mix_inv[4 * k], u[0], fma_(P.mix_inv[4 * k + 1], u[1],
-                        fma_(P.mix_inv[4 * k + 2], u[2], P.mix_inv[4 * k + 3] * u[3])));
-        ctrl[k] = clamp_(F, 0.0f, P.max_motor_thrust);
+        const float Fk = fma_(P.mix_inv[4 * k], u[0], fma_(P.mix_inv[4 * k + 1], u[1],
+                         fma_(P.mix_inv[4 * k + 2], u[2], P.mix_inv[4 * k + 3] * u[3])));
+        ctrl[k] = clamp_(Fk, 0.0f, P.max_motor_thrust);
     }
-    if (P.battery) {
+    if (F::kBattery && P.battery) {
         // hover_env.py:102-109,174-176
         const float scale = clamp_(voltage / P.v_nominal, 0.0f, 1.0f);
         float sum = 0.f;
@@ -448,7 +455,7 @@ QS_HD bool waypoint_advance(const QsParams& P, const Tables& T, uint32_t gid, En
 // ---------------------------------------------------------------------------------------
 // DEFER_RESET: the Philox re-sampling of a finished gym env is NOT done here; the caller sees
 // o.needs_reset and performs it (the kernels compact those lanes per block, see block_autoreset).
-template <int MODE, bool DEFER_RESET = false>
+template <int MODE, bool DEFER_RESET = false, class F = FeatAll>
 QS_HD void env_step(const QsParams& P, const Tables& T, uint32_t gid, Env& e, const float a[4],
                     float* obs, float* term_obs, const float* first, int nenv, StepOut& o) {
     using M = ModeTraits<MODE>;
@@ -458,18 +465,18 @@ QS_HD void env_step(const QsParams& P, const Tables& T, uint32_t gid, Env& e, co
     }
     float ctrl[4];
     if constexpr (M::kGym) {
-        if (P.rate_wrapper) {
+        if (F::kRate && P.rate_wrapper) {
             // the policy commands body rates; the base env sees torques, _prev_action keeps the rate action
             float at[4];
             rate_to_torque(P, a, e.b.w, e.rate_int, at);
 #pragma unroll
             for (int k = 0; k < 4; ++k) e.prev_action[k] = a[k];
-            action_to_ctrl(P, at, e.voltage, ctrl);
+            action_to_ctrl<F>(P, at, e.voltage, ctrl);
         } else {
-            action_to_ctrl(P, a, e.voltage, ctrl);
+            action_to_ctrl<F>(P, a, e.voltage, ctrl);
         }
     } else {
-        action_to_ctrl(P, a, e.voltage, ctrl);
+        action_to_ctrl<F>(P, a, e.voltage, ctrl);
     }
     physics_step(P, e.b, ctrl);
     e.step_count += 1;
@@ -483,7 +490,7 @@ QS_HD void env_step(const QsParams& P, const Tables& T, uint32_t gid, Env& e, co
 
     if constexpr (M::kGym) {
         bool lap = false;
-        if (P.waypoint_mode) lap = waypoint_advance(P, T, gid, e);
+        if (F::kWaypoint && P.waypoint_mode) lap = waypoint_advance(P, T, gid, e);
         o.finished = (o.done != 0.f) || (o.truncated != 0.f) || lap;
         if (o.finished) {
             if (term_obs) {

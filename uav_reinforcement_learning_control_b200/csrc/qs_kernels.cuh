@@ -23,6 +23,18 @@ namespace qs {
 #ifndef QS_USE_PDL
 #define QS_USE_PDL 1          /* step kernel: programmatic dependent launch (griddepcontrol) */
 #endif
+#ifndef QS_PREFETCH_AHEAD
+#define QS_PREFETCH_AHEAD 518  /* step kernel: each CTA pulls the state planes / actions of the tile this many CTAs ahead into L2
+                                   (148 SMs x 7 resident CTAs = 1036 per wave; half a wave measured best); 0 = off */
+#endif
+#ifndef QS_STREAM_HINTS
+#define QS_STREAM_HINTS 1      /* step kernel: actions are read and obs / reward / done written with evict-first (.cs) policy so the
+                                   state planes keep the L2 between steps */
+#endif
+#ifndef QS_TMA_STAGE
+#define QS_TMA_STAGE 0         /* step kernel (gym modes): 1 = state planes + actions of a tile arrive through cp.async.bulk into smem
+                                   (measured slower than direct loads + L2 prefetch: 62.7 vs 56.9 us; profiles/README.md) */
+#endif
 #ifndef QS_OBS_DIRECT
 #define QS_OBS_DIRECT 1   /* 1: per-thread 128-bit obs stores (measured 3 % faster: two barriers fewer);
                              0: coalesced through a shared-memory tile */
@@ -262,13 +274,58 @@ __device__ __forceinline__ bool use_compaction(const QsParams& P) {
 // 12-float observation row -> three 128-bit stores
 __device__ __forceinline__ void store_obs12(float* __restrict__ obs, int i, const float* o) {
     float4* d = reinterpret_cast<float4*>(obs + (size_t)i * 12);
+#if QS_STREAM_HINTS
+    __stcs(d, make_float4(o[0], o[1], o[2], o[3]));
+    __stcs(d + 1, make_float4(o[4], o[5], o[6], o[7]));
+    __stcs(d + 2, make_float4(o[8], o[9], o[10], o[11]));
+#else
     d[0] = make_float4(o[0], o[1], o[2], o[3]);
     d[1] = make_float4(o[4], o[5], o[6], o[7]);
     d[2] = make_float4(o[8], o[9], o[10], o[11]);
+#endif
 }
 
+// ------------------------------------------------------------------------------ TMA staging helpers
+// 1-D bulk copies (cp.async.bulk, the TMA engine without a tensor map) global -> shared, completion on an mbarrier.
+__device__ __forceinline__ uint32_t smem_addr_(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr_(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr_(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr_(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr_(bar)) : "memory");
+}
+// bounded spin: a tile is a few microseconds away at worst; trap instead of hanging the GPU if the copy never lands
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_addr_(bar);
+    uint32_t ok = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+// which state planes a gym-mode step reads (block-uniform)
+template <class F>
+__device__ __forceinline__ bool gym_plane_needed(const QsParams& P, int p) {
+    if (p <= 24 || p == 26) return true;
+    if (p == 25) return F::kBattery && P.battery != 0;
+    if (p >= 28 && p <= 30) return F::kWaypoint && P.waypoint_mode != 0;
+    if (p >= 32 && p <= 34) return F::kRate && P.rate_wrapper != 0;
+    return false;
+}
+constexpr int kStagePlanes = 35;          // planes 0..34 can be read by a gym-mode step
+
 // ------------------------------------------------------------------------------ step
-template <int MODE>
+// F = FeatLean: the plain configuration (see qs_env.cuh) with metrics / terminal_obs not requested
+template <int MODE, class F = FeatAll>
 __global__ void __launch_bounds__(kBlock, QS_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int count, float* __restrict__ state,
             const float4* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
@@ -277,6 +334,7 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
     // n = plane stride (all envs of the handle); this launch steps envs [lo, lo + count)
     constexpr int D = ModeTraits<MODE>::kObsDim;
     constexpr bool kGym = ModeTraits<MODE>::kGym;
+    constexpr bool kLean = !F::kWaypoint;           // lean launches never carry metrics / terminal_obs
     // gym modes: reset scratch; brax modes: staging tile for the 21-float observation rows
 #if QS_RESET_STRATEGY == 1 || !QS_OBS_DIRECT
     constexpr size_t kGymScratch = sizeof(ResetScratch<kBlock>);
@@ -293,25 +351,89 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
+#if QS_PREFETCH_AHEAD > 0
+    if constexpr (kGym) {
+        // L2 prefetch of a tile one wave ahead: 27 planes x 4 lines + 16 action lines, one line per thread and pass.
+        // It decouples the DRAM reads from the few warps that are in their load phase at any moment.
+        const int pf_first = block_first + QS_PREFETCH_AHEAD * kBlock;
+        if (pf_first + kBlock <= lo + count) {
+            constexpr int kLines = kBlock * 4 / 128;                 // 128-byte lines per plane per tile
+            for (int l = threadIdx.x; l < 27 * kLines; l += kBlock) {
+                const int p = l / kLines, c = l - p * kLines;
+                if (p != 25 || (F::kBattery && P.battery))
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(state + (size_t)p * n + pf_first + c * 32));
+            }
+            if (threadIdx.x < kBlock / 8)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(action + pf_first + threadIdx.x * 8));
+        }
+    }
+#endif
     float o_[D];
     Env e;
     StepOut so;
     so.needs_reset = false;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool staged = false;
+#if QS_TMA_STAGE
+    if constexpr (kGym) {
+        // Full, 16-byte aligned tiles: all planes and the actions of the CTA are fetched by the TMA engine into shared
+        // memory with one bulk copy per plane (issued by one lane each, all in flight at once, no registers held while
+        // they fly), and every thread then reads its env with immediate-offset shared loads.  Otherwise ptxas splits
+        // the 27 dependent-free global loads into several rounds to stay inside the register budget and the warp eats
+        // the HBM latency once per round.
+        __shared__ __align__(128) float stage[kStagePlanes][kBlock];
+        __shared__ __align__(16) float4 stage_act[kBlock];
+        __shared__ __align__(8) uint64_t stage_bar;
+        staged = (block_first + kBlock <= lo + count) && ((n & 3) == 0) && ((block_first & 3) == 0) &&
+                 ((reinterpret_cast<uintptr_t>(state) & 15u) == 0);
+        if (staged) {                                       // block-uniform
+            if (threadIdx.x == 0) mbar_init_(&stage_bar, 1);
+            __syncthreads();
+            const int t = threadIdx.x;
+            if (t == 0) {
+                uint32_t np = 0;
+                for (int p = 0; p < kStagePlanes; ++p) np += gym_plane_needed<F>(P, p) ? 1u : 0u;
+                mbar_expect_tx_(&stage_bar, np * (uint32_t)(kBlock * sizeof(float)) + (uint32_t)(kBlock * sizeof(float4)));
+            }
+            if (t < kStagePlanes) {
+                if (gym_plane_needed<F>(P, t))
+                    bulk_g2s_(&stage[t][0], state + (size_t)t * n + block_first, (uint32_t)(kBlock * sizeof(float)), &stage_bar);
+            } else if (t == kStagePlanes) {
+                bulk_g2s_(&stage_act[0], action + block_first, (uint32_t)(kBlock * sizeof(float4)), &stage_bar);
+            }
+            mbar_wait_(&stage_bar, 0);
+            load_env<MODE, F>(P, &stage[0][0], kBlock, threadIdx.x, e);
+            a4 = stage_act[threadIdx.x];
+        }
+    }
+#endif
     if (valid) {
-        load_env<MODE>(P, state, n, i, e);
-        const float4 a4 = action[i];
+        if (!staged) {
+            load_env<MODE, F>(P, state, n, i, e);
+#if QS_STREAM_HINTS
+            a4 = __ldcs(action + i);
+#else
+            a4 = action[i];
+#endif
+        }
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         float tobs[D];
-        env_step<MODE, kGym>(P, T, P.env_id_offset + (uint32_t)i, e, a, o_, term_obs ? tobs : nullptr,
-                             first ? first + i : nullptr, n, so);
+        env_step<MODE, kGym, F>(P, T, P.env_id_offset + (uint32_t)i, e, a, o_, (!kLean && term_obs) ? tobs : nullptr,
+                                first ? first + i : nullptr, n, so);
+#if QS_STREAM_HINTS
+        __stcs(reward + i, so.reward);
+        __stcs(done + i, so.done);
+        if (trunc) __stcs(trunc + i, so.truncated);
+#else
         reward[i] = so.reward;
         done[i] = so.done;
         if (trunc) trunc[i] = so.truncated;
-        if (metrics) {
+#endif
+        if (!kLean && metrics) {
             metrics[i] = so.pos_error; metrics[(size_t)n + i] = so.reward_hover;
             metrics[2 * (size_t)n + i] = so.reward_action; metrics[3 * (size_t)n + i] = so.reward;
         }
-        if (term_obs && so.finished) {
+        if (!kLean && term_obs && so.finished) {
 #pragma unroll
             for (int k = 0; k < D; ++k) term_obs[(size_t)i * D + k] = tobs[k];
         }
@@ -321,7 +443,7 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
     }
     if constexpr (kGym) {
         if (P.auto_reset == QS_RESET_RESAMPLE) {
-            if (P.waypoint_mode) {
+            if (F::kWaypoint && P.waypoint_mode) {
                 // waypoint resets draw nothing: do them inline
                 if (so.needs_reset) {
                     float rpy[3];
@@ -347,7 +469,7 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
             }
         }
         // one store sequence for all lanes (splitting it by needs_reset makes nearly every warp run it twice)
-        if (valid) store_env<MODE>(P, state, n, i, e);
+        if (valid) store_env<MODE, F>(P, state, n, i, e);
 #if QS_OBS_DIRECT
         if (valid) store_obs12(obs, i, o_);
 #else
@@ -355,7 +477,7 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
         store_rows<D>(obs, lo + count, block_first, o_, valid, reinterpret_cast<float*>(smem_raw));
 #endif
     } else {
-        if (valid) store_env<MODE>(P, state, n, i, e);
+        if (valid) store_env<MODE, F>(P, state, n, i, e);
         store_rows<D>(obs, lo + count, block_first, o_, valid, reinterpret_cast<float*>(smem_raw));
     }
 }

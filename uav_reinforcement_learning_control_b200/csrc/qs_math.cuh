@@ -29,7 +29,9 @@ QS_HD float fma_(float a, float b, float c) {
 
 QS_HD float rsqrt_(float x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrtf(x);                       // MUFU.RSQ + 0 NR steps, <= 2 ulp
+    float r;                                // one MUFU.RSQ (<= 2 ulp); callers pass normal-range arguments
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
     return 1.0f / sqrtf(x);
 #endif
@@ -37,8 +39,26 @@ QS_HD float rsqrt_(float x) {
 
 QS_HD float sqrt_(float x) { return sqrtf(x); }
 
-// accurate sin/cos (state-carrying quantities)
+// accurate sin/cos (state-carrying quantities).  |x| <= 0.5 -- every call on the hot path: the quaternion step
+// angle |w| dt / 2 and the half Euler angles of a reset -- takes a Taylor pair (sin to x^11, cos to x^10: truncation
+// < 2e-11, i.e. below float32 rounding) instead of libm's range reduction; identical code on host and device.
 QS_HD void sincos_(float x, float* s, float* c) {
+    if (fabsf(x) <= 0.5f) {
+        const float z = x * x;
+        float ps = -2.5052108385441720e-08f;
+        ps = fma_(ps, z, 2.7557319223985893e-06f);
+        ps = fma_(ps, z, -1.9841269841269841e-04f);
+        ps = fma_(ps, z, 8.3333333333333332e-03f);
+        ps = fma_(ps, z, -1.6666666666666666e-01f);
+        float pc = -2.7557319223985888e-07f;
+        pc = fma_(pc, z, 2.4801587301587302e-05f);
+        pc = fma_(pc, z, -1.3888888888888889e-03f);
+        pc = fma_(pc, z, 4.1666666666666664e-02f);
+        pc = fma_(pc, z, -0.5f);
+        *s = fma_(x * z, ps, x);
+        *c = fma_(z, pc, 1.0f);
+        return;
+    }
 #if defined(__CUDA_ARCH__)
     sincosf(x, s, c);
 #else
@@ -65,7 +85,9 @@ QS_HD float exp_(float x) {
 
 QS_HD float rcp_(float x) {
 #if defined(__CUDA_ARCH__)
-    return __frcp_rn(x);
+    float r;                                // one MUFU.RCP (<= 1 ulp); only feeds the atan2 ratio
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
     return 1.0f / x;
 #endif
@@ -77,7 +99,7 @@ QS_HD float rcp_(float x) {
 QS_HD float atan2_(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float t = mx > 0.f ? mn * rcp_(mx) : 0.f;
+    const float t = mx > 1e-30f ? mn * rcp_(mx) : 0.f;     // (also keeps flushed denormals away from MUFU.RCP)
     const float s = t * t;
     float p = -0.004054448804439777f;
     p = fma_(p, s, 0.021862509027492236f);

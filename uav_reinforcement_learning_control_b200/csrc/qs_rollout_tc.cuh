@@ -11,8 +11,12 @@
 //     by the owners themselves: a warp's 16-byte stores for one K chunk are 512 contiguous bytes;
 //   * accumulators are fp32 in TMEM (256 columns): L1 computes actor|critic together (N = 256, K = 16),
 //     L2 is 8 + 8 instructions of M128 N128 K16, L3 is 8 + 8 of M128 N16 K16 (heads padded to 16 columns);
+//   * the biases of layers 1 and 2 ride inside the MMAs: the padded K slots 12 and 13 of the layer-1 A operand carry a
+//     constant 1, and the matching B rows carry the bias split into a bf16 high and a bf16 low part (hi + lo
+//     reproduces the fp32 bias to 2^-17 relative); layer 2 gets one extra K = 16 step  A1 . B2bias  for the same
+//     purpose.  Both epilogues are therefore just TMEM load -> ReLU + bf16 pack -> shared store;
 //   * a single elected thread issues tcgen05.mma and tcgen05.commit -> mbarrier; everybody waits on the
-//     barrier, then runs the epilogue (bias + ReLU + bf16 pack -> next layer's A operand).
+//     barrier, then runs the epilogue (ReLU + bf16 pack -> next layer's A operand).
 // fp32 weights arrive in the same packed vector as the FMA kernel and are converted to bf16 UMMA layout in
 // shared memory once per CTA per launch.  Numerics: bf16 inputs, fp32 accumulation -- the oracle models
 // exactly that rounding (oracle/ppo_ref.py forward(..., bf16=True)).
@@ -92,6 +96,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
     uint32_t done = 0;
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -163,7 +168,9 @@ struct Smem {
     static constexpr int W2C = W2A + 128 * 128 * 2;
     static constexpr int W3A = W2C + 128 * 128 * 2;       // B: [16 x 128]
     static constexpr int W3C = W3A + 16 * 128 * 2;
-    static constexpr int WEND = W3C + 16 * 128 * 2;       // end of the (shared) B operands
+    static constexpr int B2A = W3C + 16 * 128 * 2;        // B: [128 x 16], K rows 12 / 13 = hi / lo halves of the layer-2 bias
+    static constexpr int B2C = B2A + 128 * 16 * 2;
+    static constexpr int WEND = B2C + 128 * 16 * 2;       // end of the (shared) B operands
     // per tile: A1 [128 x 16], A2A / A2C [128 x 128] (A2* are also the A operands of L3)
     static constexpr int A1 = 0, A2A = 128 * 16 * 2, A2C = A2A + 128 * 128 * 2, TILE_BYTES = A2C + 128 * 128 * 2;
     static constexpr int TILE0 = WEND;
@@ -199,19 +206,26 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     for (int idx = gtid; idx < (Smem::WEND) / 4; idx += NT) reinterpret_cast<uint32_t*>(smem)[idx] = 0u;   // zero all B operands
     __syncthreads();
     {
-        __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1);
         // W1cat (n, k): n < 128 actor, n >= 128 critic; params store W[k][n]
         for (int idx = gtid; idx < D * 256; idx += NT) {
             const int k = idx / 256, nn = idx % 256;
             const float w = nn < 128 ? params[L.aW1 + k * kH + nn] : params[L.cW1 + k * kH + (nn - 128)];
             *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(w);
         }
-        (void)w1;
-        // the layer-1 bias rides in the padded K slot 12 (the A operand carries a constant 1 there); it is therefore
-        // rounded to bf16 like the weights
+        // the layer-1 bias rides in the padded K slots 12 (bf16 high part) and 13 (bf16 low part); the A operand
+        // carries a constant 1 in both.  The layer-2 bias uses the same two slots of the B2A / B2C operands.
         for (int nn = gtid; nn < 256; nn += NT) {
             const float bv = nn < 128 ? params[L.ab1 + nn] : params[L.cb1 + (nn - 128)];
-            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, D >> 3) + (D & 7) * 2) = __float2bfloat16_rn(bv);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, 1) + 4 * 2) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, 1) + 5 * 2) = lo;
+            const float b2 = nn < 128 ? params[L.ab2 + nn] : params[L.cb2 + (nn - 128)];
+            const __nv_bfloat16 hi2 = __float2bfloat16_rn(b2);
+            const __nv_bfloat16 lo2 = __float2bfloat16_rn(b2 - __bfloat162float(hi2));
+            const int dst = nn < 128 ? Smem::B2A : Smem::B2C;
+            *reinterpret_cast<__nv_bfloat16*>(smem + dst + op_offset(128, nn & 127, 1) + 4 * 2) = hi2;
+            *reinterpret_cast<__nv_bfloat16*>(smem + dst + op_offset(128, nn & 127, 1) + 5 * 2) = lo2;
         }
         for (int idx = gtid; idx < kH * kH; idx += NT) {
             const int k = idx / kH, nn = idx % kH;
@@ -231,10 +245,6 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         for (int idx = gtid; idx < Smem::kNumF; idx += NT) sF[idx] = 0.f;
     }
     __syncthreads();
-    for (int k = gtid; k < kH; k += NT) {
-        sF[Smem::kB1 + k] = params[L.ab1 + k]; sF[Smem::kB1 + 128 + k] = params[L.cb1 + k];
-        sF[Smem::kB2A + k] = params[L.ab2 + k]; sF[Smem::kB2C + k] = params[L.cb2 + k];
-    }
     if (gtid < Ao) sF[Smem::kB3 + gtid] = params[L.ab3 + gtid];
     if (gtid == 0) sF[Smem::kB3 + 16] = params[L.cb3];
     if (DIST == 0 && gtid < kA) sF[Smem::kLogStd + gtid] = params[L.log_std + gtid];
@@ -283,7 +293,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         {
             float x[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = k < D ? (o[k] - sF[Smem::kMean + k]) * sF[Smem::kInvStd + k] : (k == D ? 1.0f : 0.f);
+            for (int k = 0; k < 16; ++k) x[k] = k < D ? (o[k] - sF[Smem::kMean + k]) * sF[Smem::kInvStd + k] : (k < D + 2 ? 1.0f : 0.f);
             uint4 c0 = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
             uint4 c1 = make_uint4(pack_bf16(x[8], x[9]), pack_bf16(x[10], x[11]), pack_bf16(x[12], x[13]), pack_bf16(x[14], x[15]));
             *reinterpret_cast<uint4*>(tsm + Smem::A1 + op_offset(128, tid, 0)) = c0;
@@ -331,25 +341,23 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 mma_bf16(tmem + 128u, make_desc(tbase + Smem::A2C + j * 4096, 16 * 128, 128),
                          make_desc(sbase + Smem::W2C + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
             }
+            // + b2: the layer-1 A operand (constant 1 in K slots 12 / 13) times the hi / lo bias rows
+            mma_bf16(tmem, dA1, make_desc(sbase + Smem::B2A, 16 * 128, 128), idesc_l2, 1u);
+            mma_bf16(tmem + 128u, dA1, make_desc(sbase + Smem::B2C, 16 * 128, 128), idesc_l2, 1u);
             mma_commit(bar);
         }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
         QS_TCP(3);
-        // epilogue 2: h2 = relu(D2 + b2) -> bf16, written over A2A | A2C (the L2 MMAs have completed)
+        // epilogue 2: h2 = relu(D2) -> bf16, written over A2A | A2C (the L2 MMAs have completed; b2 is inside D2)
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
             float v[32];
             tmem_ld32(my_tmem + (uint32_t)(c * 32), v);
             const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
-            const int bb = (c < 4) ? Smem::kB2A : Smem::kB2C;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float* h = v + q * 8;
-                const float4 ba = *reinterpret_cast<const float4*>(sF + bb + (c & 3) * 32 + q * 8);
-                const float4 bc = *reinterpret_cast<const float4*>(sF + bb + (c & 3) * 32 + q * 8 + 4);
-                add2(h[0], h[1], ba.x, ba.y); add2(h[2], h[3], ba.z, ba.w);
-                add2(h[4], h[5], bc.x, bc.y); add2(h[6], h[7], bc.z, bc.w);
+                const float* h = v + q * 8;
                 *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
                     make_uint4(pack_relu_bf16(h[0], h[1]), pack_relu_bf16(h[2], h[3]), pack_relu_bf16(h[4], h[5]),
                                pack_relu_bf16(h[6], h[7]));
@@ -451,10 +459,12 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                     compute_obs<MODE>(P, e, rpy, obs_);
                 }
             } else {
-                struct TileSync { int t; __device__ __forceinline__ void operator()() const { tile_sync(t); } };
-                block_autoreset<MODE, kM, TileSync>(P, T, P.env_id_offset + (uint32_t)b0, e, obs_, so.needs_reset, t & 1,
-                                                    *reinterpret_cast<ResetScratch<kM>*>(tsm + Smem::A2A), tid, TileSync{tile});
-                tile_sync(tile);      // every owner has read its row before the buffer becomes an MMA operand again
+                // warp-cooperative Philox re-sampling (qs_kernels.cuh: warp_autoreset_smem), no tile barrier.  The
+                // per-warp scratch lives at the start of this tile's A2A buffer, which is idle between the head MMAs
+                // of this step and the first epilogue of the next forward (which every warp reaches only after the
+                // tile barrier that follows the A1 store, i.e. after all warps have left this block).
+                warp_autoreset_smem<MODE>(P, P.env_id_offset + (uint32_t)(b0 + warp * 32), e, obs_, so.needs_reset,
+                                          reinterpret_cast<WarpResetScratch*>(tsm + Smem::A2A)[warp]);
             }
         }
         QS_TCP(9);

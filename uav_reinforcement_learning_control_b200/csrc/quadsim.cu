@@ -14,6 +14,7 @@
 #include "qs_kernels.cuh"
 #include "qs_rollout.cuh"
 #include "qs_rollout_tc.cuh"
+#include "qs_traj.cuh"
 
 namespace {
 
@@ -173,25 +174,27 @@ static int launch_step(QsHandle h, int lo, int count, float* state, const float*
         return check_launch("step_kernel_pf");
     }
 #endif
-#if QS_USE_PDL
-    // Programmatic dependent launch: the step kernel signals launch_dependents at its top and waits for its
-    // predecessors (griddepcontrol.wait) before its first global access, so the launch latency, CTA ramp-up and
+    // Programmatic dependent launch (QS_USE_PDL): the step kernel signals launch_dependents at its top and waits for
+    // its predecessors (griddepcontrol.wait) before its first global access, so the launch latency, CTA ramp-up and
     // parameter set-up of step k+1 overlap the drain of whatever ran before it on the stream.
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
     lc.gridDim = dim3((unsigned)nblocks(count, qs::kBlock)); lc.blockDim = dim3(qs::kBlock); lc.dynamicSmemBytes = 0; lc.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    at[0].val.programmaticStreamSerializationAllowed = QS_USE_PDL ? 1 : 0;
     lc.attrs = at; lc.numAttrs = 1;
     const float4* a4 = (const float4*)action;
-    QS_DISPATCH_MODE(h->P.mode, (cudaLaunchKernelEx(&lc, qs::step_kernel<M_>, h->P, h->tables(), (int)h->n, lo, count, state, a4,
-        obs, reward, done, truncated, metrics, terminal_obs, first_state)));
-#else
-    QS_DISPATCH_MODE(h->P.mode, (qs::step_kernel<M_><<<nblocks(count, qs::kBlock), qs::kBlock, 0, s>>>(
-        h->P, h->tables(), h->n, lo, count, state, (const float4*)action, obs, reward, done, truncated, metrics,
-        terminal_obs, first_state)));
-#endif
+    const QsParams& Pq = h->P;
+    if (Pq.mode == QS_MODE_HOVER_GYM && !Pq.battery && !Pq.rate_wrapper && !Pq.waypoint_mode && !Pq.pre_clip_action &&
+        !metrics && !terminal_obs) {
+        // plain north-star configuration: feature-folded instantiation (qs_env.cuh: FeatLean)
+        cudaLaunchKernelEx(&lc, qs::step_kernel<QS_MODE_HOVER_GYM, qs::FeatLean>, h->P, h->tables(), (int)h->n, lo, count, state, a4,
+                           obs, reward, done, truncated, metrics, terminal_obs, first_state);
+        return check_launch("step_kernel<lean>");
+    }
+    QS_DISPATCH_MODE(h->P.mode, (cudaLaunchKernelEx(&lc, qs::step_kernel<M_, qs::FeatAll>, h->P, h->tables(), (int)h->n, lo, count,
+        state, a4, obs, reward, done, truncated, metrics, terminal_obs, first_state)));
     return check_launch("step_kernel");
 }
 
@@ -204,6 +207,31 @@ int qs_step(QsHandle h, float* state, const float* action, float* obs, float* re
     if (h->P.obs_dim == 12 && ((uintptr_t)obs & 15u) != 0) return fail(QS_EINVAL, "qs_step: obs must be 16-byte aligned");
     return launch_step(h, 0, h->n, state, action, obs, reward, done, truncated, metrics, terminal_obs, first_state,
                        (cudaStream_t)stream);
+}
+
+namespace qs {
+// one thread per env: ~9 Philox blocks, three 3x3 tridiagonal solves and spline evaluations in float64
+__global__ void __launch_bounds__(kBlock)
+traj_info_kernel(const __grid_constant__ QsParams P, int n, const float* __restrict__ state,
+                 const uint32_t* __restrict__ episode, const int32_t* __restrict__ sample_index, float* __restrict__ out9) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t epi = episode ? episode[i] : f2u_(state[26 * (size_t)n + i]);
+    const int idx = sample_index ? sample_index[i] : f2i_(state[24 * (size_t)n + i]) - 1;
+    float o[9];
+    traj_info_eval(P, P.env_id_offset + (uint32_t)i, epi, idx, o);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out9[(size_t)i * 9 + k] = o[k];
+}
+}  // namespace qs
+
+int qs_traj_info(QsHandle h, const float* state, const uint32_t* episode, const int32_t* sample_index, float* out9,
+                 void* stream) {
+    if (!h || !state || !out9) return fail(QS_EINVAL, "qs_traj_info: null");
+    if (h->P.mode != QS_MODE_TRAJ_GYM) return fail(QS_EINVAL, "qs_traj_info: the spline reference exists in QS_MODE_TRAJ_GYM only");
+    qs::traj_info_kernel<<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, (cudaStream_t)stream>>>(h->P, h->n, state, episode,
+                                                                                             sample_index, out9);
+    return check_launch("traj_info_kernel");
 }
 
 int qs_observe(QsHandle h, const float* state, const float* action, float* obs, float* reward, float* done,

@@ -43,6 +43,7 @@ _EXPORTS = {
                           + [C.c_void_p] * 9 + [C.c_void_p, C.c_void_p]),
     "qs_gae": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_int32]
                + [C.c_void_p] * 2 + [C.c_void_p]),
+    "qs_traj_info": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_void_p]),
     "qs_step_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
 }
 
@@ -176,6 +177,19 @@ class Engine:
         self._check(self.lib.qs_observe(self.handle, _ptr(state), _ptr(action), _ptr(obs), _ptr(reward), _ptr(done),
                                         self._stream()))
         return obs, reward, done
+
+    def traj_info(self, state, episode=None, sample_index=None, out=None):
+        """TrajectoryFollowEnv info target | target_vel | target_acc, [n, 9] (include/quadsim_abi.h: qs_traj_info)."""
+        n = self.num_envs
+        self._chk(state, (Q.NPLANES, n), "state")
+        out = self._f32(n, 9) if out is None else out
+        self._chk(out, (n, 9), "out")
+        for name, t, dt in (("episode", episode, self.torch.int32), ("sample_index", sample_index, self.torch.int32)):
+            if t is not None and (t.dtype != dt or tuple(t.shape) != (n,) or not t.is_contiguous() or t.device != out.device):
+                raise QuadSimError(f"{name}: expected a contiguous int32 [{n}] tensor on {out.device}")
+        self._check(self.lib.qs_traj_info(self.handle, _ptr(state), _ptr(episode), _ptr(sample_index), _ptr(out),
+                                          self._stream()))
+        return out
 
     def physics_step(self, state, ctrl):
         self._chk(state, (Q.NPLANES, self.num_envs), "state"); self._chk(ctrl, (self.num_envs, 4), "ctrl")

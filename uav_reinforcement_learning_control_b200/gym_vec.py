@@ -142,9 +142,12 @@ class HoverVecEnv:
     def _rate_int_torque(self):
         return self._planes[32:35].t()
 
-    def _infos(self, finished=None):
+    def _infos(self, finished=None, traj=None):
         info = {"target": self._planes[21:24].t(), "voltage": self._planes[25],
                 "voltage_scale": (self._planes[25] / self.cfg.v_nominal).clamp(0.0, 1.0)}
+        if traj is not None:
+            # TrajectoryFollowEnv: the spline reference of the step that ran (trajectory_follow_env.py:162-168,245-250)
+            info["target"], info["target_vel"], info["target_acc"] = traj[:, 0:3], traj[:, 3:6], traj[:, 6:9]
         if finished is not None:
             info["terminal_observation"] = self._terminal_obs
             info["final_observation"] = self._terminal_obs
@@ -157,7 +160,8 @@ class HoverVecEnv:
         self._episode_seed(seed)
         self.engine.reset(self._planes, obs=self._obs)
         self._prev_action = self.torch.zeros_like(self._prev_action)
-        return self._wrap_obs(self._obs), self._infos()
+        traj = self.engine.traj_info(self._planes) if self.cfg.mode == Q.MODE_TRAJ_GYM else None
+        return self._wrap_obs(self._obs), self._infos(traj=traj)
 
     def step(self, actions):
         """-> (obs, reward, terminated, truncated, infos); torch in -> torch out, NumPy in -> NumPy out."""
@@ -166,12 +170,18 @@ class HoverVecEnv:
         torch = self.torch
         a = torch.as_tensor(actions, dtype=torch.float32, device=self.device).contiguous()
         self._prev_action = a
+        traj = None
+        if self.cfg.mode == Q.MODE_TRAJ_GYM:
+            # info index = step_count - 1 of the episode the step belongs to, also for envs the step auto-resets
+            prev_sc = self._planes[24].view(torch.int32).clone(); prev_ep = self._planes[26].view(torch.int32).clone()
         self.engine.step(self._planes, a, obs=self._obs, reward=self._rew, done=self._term, truncated=self._trunc,
                          terminal_obs=self._terminal_obs)
+        if self.cfg.mode == Q.MODE_TRAJ_GYM:
+            traj = self.engine.traj_info(self._planes, episode=prev_ep, sample_index=prev_sc)
         finished = (self._term != 0) | (self._trunc != 0)
         if self.wrapper == "RelPosActWrapper" and bool(finished.any()):
             self._prev_action = self.torch.where(finished[:, None], self.torch.zeros_like(a), a)   # reset() zeroes it
-        return self._wrap_obs(self._obs), self._rew, self._term != 0, self._trunc != 0, self._infos(finished)
+        return self._wrap_obs(self._obs), self._rew, self._term != 0, self._trunc != 0, self._infos(finished, traj)
 
     def _step_numpy(self, actions):
         torch = self.torch

@@ -92,7 +92,9 @@ def test_lean_step_kernel_matches_general_kernel():
     import torch
     from uav_reinforcement_learning_control_b200.engine import Engine
     cfg = pc.CONFIGS["north_star"]()
-    for n in (4096, 1000):                       # full tiles, and a ragged tail
+    # full tiles; a ragged tail; and a batch large enough for the persistent TMA-pipelined kernel (>= one CTA wave of
+    # 128-env tiles) with a 100-env tail that goes through the plain kernel
+    for n in (4096, 1000, 140004):
         st, act, _ = pc.synth_inputs(cfg, n, seed=5)
         eng = Engine(cfg, n, device=0)
         a_st = torch.from_numpy(st.copy()).cuda(); b_st = torch.from_numpy(st.copy()).cuda()

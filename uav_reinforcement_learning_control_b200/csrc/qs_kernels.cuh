@@ -27,6 +27,10 @@ namespace qs {
 #define QS_PREFETCH_AHEAD 518  /* step kernel: each CTA pulls the state planes / actions of the tile this many CTAs ahead into L2
                                    (148 SMs x 7 resident CTAs = 1036 per wave; half a wave measured best); 0 = off */
 #endif
+#ifndef QS_PREFETCH_L1
+#define QS_PREFETCH_L1 0       /* step kernel: 1 = one L1 prefetch per thread for the CTA's own tile at the top of the kernel
+                                   (as good as the L2 prefetch-ahead, not additive: 56.7 us either way) */
+#endif
 #ifndef QS_STREAM_HINTS
 #define QS_STREAM_HINTS 1      /* step kernel: actions are read and obs / reward / done written with evict-first (.cs) policy so the
                                    state planes keep the L2 between steps */
@@ -368,6 +372,21 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
         }
     }
 #endif
+#if QS_PREFETCH_L1
+    if constexpr (kGym) {
+        // ptxas splits the 27 independent plane loads into three rounds to stay inside the register budget, and the warp
+        // would pay the memory latency once per round; one register-free L1 prefetch per thread at the very top requests
+        // all of the tile's lines at once, so rounds two and three hit in L1.
+        if (block_first + kBlock <= lo + count) {
+            constexpr int kLines = kBlock * 4 / 128;
+            for (int l = threadIdx.x; l < 27 * kLines; l += kBlock) {
+                const int p = l / kLines, c = l - p * kLines;
+                if (p != 25 || (F::kBattery && P.battery))
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(state + (size_t)p * n + block_first + c * 32));
+            }
+        }
+    }
+#endif
     float o_[D];
     Env e;
     StepOut so;
@@ -479,6 +498,99 @@ step_kernel(const __grid_constant__ QsParams P, Tables T, int n, int lo, int cou
     } else {
         if (valid) store_env<MODE, F>(P, state, n, i, e);
         store_rows<D>(obs, lo + count, block_first, o_, valid, reinterpret_cast<float*>(smem_raw));
+    }
+}
+
+// ------------------------------------------------------------------------------ step, persistent TMA-pipelined variant
+// Plain north-star configuration (FeatLean), full 16-byte aligned tiles.  One wave of persistent CTAs walks over the
+// 128-env tiles.  A tile's 26 state planes and its actions are fetched by the TMA engine (cp.async.bulk, 512 B per
+// plane) into ONE shared-memory stage; as soon as every warp has copied its envs from the stage into registers
+// (immediate-offset LDS, then one mbarrier arrive per warp on `empty`), one lane -- the role rotates over the four
+// warps -- re-arms `full` and issues the bulk copies of the CTA's NEXT tile, which then fly during the ~1200
+// instructions of compute and the stores of the current tile.  No warp ever waits on HBM latency after its first
+// tile, there is no block barrier in the loop, and the load phases of the resident CTAs no longer line up (the plain
+// kernel runs in waves: every CTA of an SM loads, computes and stores at the same time).
+#ifndef QS_USE_PIPELINED_STEP
+#define QS_USE_PIPELINED_STEP 0   /* measured 74.5 us vs 56.8 us for the plain kernel on B200: see profiles/README.md */
+#endif
+constexpr int kPpPlanes = 27;                       // planes 0..26 (25 = voltage is skipped)
+
+__device__ __forceinline__ void mbar_arrive_(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr_(bar)) : "memory");
+}
+
+struct PpSmem {
+    float plane[kPpPlanes][kBlock];
+    float4 action[kBlock];
+    WarpResetScratch scratch[kBlock / 32];
+    uint64_t full, empty;
+};
+
+__device__ __forceinline__ void pp_issue(PpSmem& S, const float* __restrict__ state, int n, const float4* __restrict__ action,
+                                         int first) {
+    mbar_expect_tx_(&S.full, (uint32_t)((kPpPlanes - 1) * kBlock * sizeof(float) + kBlock * sizeof(float4)));
+#pragma unroll 1
+    for (int p = 0; p < kPpPlanes; ++p) {
+        if (p == 25) continue;
+        bulk_g2s_(&S.plane[p][0], state + (size_t)p * n + first, (uint32_t)(kBlock * sizeof(float)), &S.full);
+    }
+    bulk_g2s_(&S.action[0], action + first, (uint32_t)(kBlock * sizeof(float4)), &S.full);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, QS_STEP_MIN_BLOCKS)
+step_kernel_pp(const __grid_constant__ QsParams P, Tables T, int n, int lo, int ntiles, float* __restrict__ state,
+               const float4* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
+               float* __restrict__ done, float* __restrict__ trunc) {
+    static_assert(ModeTraits<MODE>::kGym, "pipelined step kernel: gym modes");
+    using F = FeatLean;
+    constexpr int D = 12;
+    __shared__ __align__(128) PpSmem S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { mbar_init_(&S.full, 1); mbar_init_(&S.empty, kBlock / 32); }
+    __syncthreads();
+#if QS_USE_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) pp_issue(S, state, n, action, lo + tile * kBlock);
+    uint32_t ph = 0;
+    int round = 0;
+#pragma unroll 1
+    for (; tile < ntiles; tile += gridDim.x, ph ^= 1u, ++round) {
+        const int i = lo + tile * kBlock + tid;
+        Env e;
+        mbar_wait_(&S.full, ph);
+        load_env<MODE, F>(P, &S.plane[0][0], kBlock, tid, e);
+        const float4 a4 = S.action[tid];
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_(&S.empty);
+            const int nxt = tile + (int)gridDim.x;
+            if (nxt < ntiles && warp == (round & (kBlock / 32 - 1))) {
+                mbar_wait_(&S.empty, ph);                        // all four warps hold their envs in registers
+                pp_issue(S, state, n, action, lo + nxt * kBlock);
+            }
+        }
+        __syncwarp();
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        float o_[D];
+        StepOut so;
+        env_step<MODE, true, F>(P, T, P.env_id_offset + (uint32_t)i, e, a, o_, nullptr, nullptr, n, so);
+#if QS_STREAM_HINTS
+        __stcs(reward + i, so.reward);
+        __stcs(done + i, so.done);
+        if (trunc) __stcs(trunc + i, so.truncated);
+#else
+        reward[i] = so.reward;
+        done[i] = so.done;
+        if (trunc) trunc[i] = so.truncated;
+#endif
+        if (P.auto_reset == QS_RESET_RESAMPLE)
+            warp_autoreset_smem<MODE>(P, P.env_id_offset + (uint32_t)(i - lane), e, o_, so.needs_reset, S.scratch[warp]);
+        store_env<MODE, F>(P, state, n, i, e);
+        store_obs12(obs, i, o_);
     }
 }
 

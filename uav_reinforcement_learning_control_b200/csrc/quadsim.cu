@@ -45,6 +45,7 @@ struct QsEngine {
     double* waypoints;      // device, [shapes][QS_MAX_WP][3] or null
     float* scratch;         // device staging for qs_step_host: action | obs | reward | done
     int pf_grid;            // persistent grid of the prefetching step kernel (SMs x resident CTAs)
+    int pp_grid;            // persistent grid of the TMA-pipelined step kernel (SMs x resident CTAs)
     cudaStream_t hs[2];     // qs_step_host: two copy/compute streams (H2D of chunk k+1 under D2H of chunk k)
     cudaEvent_t hev[3];
     qs::Tables tables() const { return qs::Tables{target_table, waypoints}; }
@@ -113,6 +114,11 @@ int qs_create(const QsParams* params, int32_t num_envs, int32_t device, const fl
         cudaMemcpy(e->waypoints, waypoints_host, bytes, cudaMemcpyHostToDevice);
     }
     e->pf_grid = prop.multiProcessorCount;
+    {
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qs::step_kernel_pp<QS_MODE_HOVER_GYM>, qs::kBlock, 0);
+        e->pp_grid = prop.multiProcessorCount * (per_sm < 1 ? 1 : per_sm);
+    }
 #if QS_USE_PREFETCH_STEP
     {
         const int smem = (int)qs::step_pf_smem_bytes();
@@ -189,6 +195,22 @@ static int launch_step(QsHandle h, int lo, int count, float* state, const float*
     if (Pq.mode == QS_MODE_HOVER_GYM && !Pq.battery && !Pq.rate_wrapper && !Pq.waypoint_mode && !Pq.pre_clip_action &&
         !metrics && !terminal_obs) {
         // plain north-star configuration: feature-folded instantiation (qs_env.cuh: FeatLean)
+#if QS_USE_PIPELINED_STEP
+        // full, 16-byte aligned tiles go through the persistent TMA-pipelined kernel; a ragged tail (if any) through
+        // the plain one
+        const int ntiles = count / qs::kBlock;
+        if (ntiles >= h->pp_grid && (h->n & 3) == 0 && (lo & 3) == 0 && ((uintptr_t)state & 15u) == 0) {
+            cudaLaunchConfig_t lp = lc;
+            lp.gridDim = dim3((unsigned)h->pp_grid);
+            cudaLaunchKernelEx(&lp, qs::step_kernel_pp<QS_MODE_HOVER_GYM>, h->P, h->tables(), (int)h->n, lo, ntiles, state, a4,
+                               obs, reward, done, truncated);
+            const int rem = count - ntiles * qs::kBlock;
+            if (rem == 0) return check_launch("step_kernel_pp");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            lc.gridDim = dim3(1u);
+            lo += ntiles * qs::kBlock; count = rem;
+        }
+#endif
         cudaLaunchKernelEx(&lc, qs::step_kernel<QS_MODE_HOVER_GYM, qs::FeatLean>, h->P, h->tables(), (int)h->n, lo, count, state, a4,
                            obs, reward, done, truncated, metrics, terminal_obs, first_state);
         return check_launch("step_kernel<lean>");

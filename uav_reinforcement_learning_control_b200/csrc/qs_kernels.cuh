@@ -827,8 +827,13 @@ rollout_random_kernel(const __grid_constant__ QsParams P, Tables T, int n, float
         }
         if constexpr (kGym) {
             if (compact) {
+#if QS_RESET_STRATEGY == 3
+                warp_autoreset_smem<MODE>(P, gid - (uint32_t)(threadIdx.x & 31), e, o_, so.needs_reset,
+                                          reinterpret_cast<WarpResetScratch*>(smem_raw)[threadIdx.x >> 5]);
+#else
                 block_autoreset<MODE, kBlock>(P, T, P.env_id_offset + (uint32_t)block_first, e, o_, so.needs_reset, t & 1,
                                               *reinterpret_cast<ResetScratch<kBlock>*>(smem_raw));
+#endif
             } else if (so.needs_reset) {
                 float rpy[3];
                 reset_env<MODE>(P, T, gid, e, rpy);

@@ -337,44 +337,56 @@ inline int launch_rollout_policy(const QsParams& P, const Tables& T, int n, floa
 // ------------------------------------------------------------------------------------------
 // GAE reverse-time scan, one thread per env, [T][B] time-major buffers (coalesced per step).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// The recurrence is sequential in t but its loads are not: each thread fetches kGaeBatch time steps at once (all
+// loads in flight together), then runs the recurrence over them, so the HBM latency is paid once per batch.
+constexpr int kGaeBatch = 8;
+constexpr int kGaeBlock = 32;      // small CTAs: 8192 envs still spread over every SM
+
+__global__ void __launch_bounds__(kGaeBlock)
 gae_kernel(int T, int B, const float* __restrict__ reward, const float* __restrict__ value,
            const float* __restrict__ done, const float* __restrict__ trunc, const float* __restrict__ last_value,
            float gamma, float lam, int brax_form, float* __restrict__ adv, float* __restrict__ ret) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    if (!brax_form) {
-        // SB3 RolloutBuffer.compute_returns_and_advantage: an episode boundary after step t
-        // (terminated or truncated) cuts both the bootstrap and the recursion
-        float next_v = last_value[b], a = 0.f;
-        for (int t = T - 1; t >= 0; --t) {
-            const size_t o = (size_t)t * B + b;
-            float fin = done[o];
-            if (trunc) fin = fmaxf(fin, trunc[o]);
-            const float nnt = 1.0f - fin;
-            const float v = value[o];
-            const float delta = fmaf(gamma * next_v, nnt, reward[o]) - v;
-            a = fmaf(gamma * lam * nnt, a, delta);
-            adv[o] = a;
-            ret[o] = a + v;
-            next_v = v;
+    float next_v = last_value[b], vs_next = next_v, a = 0.f;
+    for (int t1 = T; t1 > 0; t1 -= kGaeBatch) {
+        // time steps t1-1, t1-2, ... (k = 0 is the latest); steps below 0 are masked out
+        float r_[kGaeBatch], v_[kGaeBatch], d_[kGaeBatch], tr_[kGaeBatch];
+#pragma unroll
+        for (int k = 0; k < kGaeBatch; ++k) {
+            const int t = t1 - 1 - k;
+            const size_t o = (size_t)(t < 0 ? 0 : t) * B + b;
+            r_[k] = __ldcs(reward + o); v_[k] = __ldcs(value + o); d_[k] = __ldcs(done + o);
+            tr_[k] = trunc ? __ldcs(trunc + o) : 0.f;
         }
-    } else {
-        // brax.training.agents.ppo.losses.compute_gae with termination = done * (1 - truncation)
-        float v_next = last_value[b], vs_next = last_value[b], acc = 0.f;
-        for (int t = T - 1; t >= 0; --t) {
+#pragma unroll
+        for (int k = 0; k < kGaeBatch; ++k) {
+            const int t = t1 - 1 - k;
+            if (t < 0) break;
             const size_t o = (size_t)t * B + b;
-            const float tr = trunc[o];
-            const float term = done[o] * (1.0f - tr);
-            const float mask = 1.0f - tr;
-            const float v = value[o], r = reward[o];
-            const float disc = gamma * (1.0f - term);
-            const float delta = (fmaf(disc, v_next, r) - v) * mask;
-            acc = fmaf(disc * mask * lam, acc, delta);
-            const float vs = acc + v;
-            adv[o] = (fmaf(disc, vs_next, r) - v) * mask;
-            ret[o] = vs;
-            v_next = v; vs_next = vs;
+            const float v = v_[k], r = r_[k];
+            if (!brax_form) {
+                // SB3 RolloutBuffer.compute_returns_and_advantage: an episode boundary after step t
+                // (terminated or truncated) cuts both the bootstrap and the recursion
+                const float nnt = 1.0f - fmaxf(d_[k], tr_[k]);
+                const float delta = fmaf(gamma * next_v, nnt, r) - v;
+                a = fmaf(gamma * lam * nnt, a, delta);
+                __stcs(adv + o, a);
+                __stcs(ret + o, a + v);
+                next_v = v;
+            } else {
+                // brax.training.agents.ppo.losses.compute_gae with termination = done * (1 - truncation)
+                const float tr = tr_[k];
+                const float term = d_[k] * (1.0f - tr);
+                const float mask = 1.0f - tr;
+                const float disc = gamma * (1.0f - term);
+                const float delta = (fmaf(disc, next_v, r) - v) * mask;
+                a = fmaf(disc * mask * lam, a, delta);
+                const float vs = a + v;
+                __stcs(adv + o, (fmaf(disc, vs_next, r) - v) * mask);
+                __stcs(ret + o, vs);
+                next_v = v; vs_next = vs;
+            }
         }
     }
 }

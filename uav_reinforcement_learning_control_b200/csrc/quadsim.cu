@@ -359,7 +359,7 @@ int qs_gae(int32_t T, int32_t B, const float* reward, const float* value, const 
     if (T <= 0 || B <= 0 || !reward || !value || !done || !last_value || !adv || !ret)
         return fail(QS_EINVAL, "qs_gae: bad argument");
     if (brax_form && !trunc) return fail(QS_EINVAL, "qs_gae: brax form needs truncation flags");
-    qs::gae_kernel<<<nblocks(B, 128), 128, 0, (cudaStream_t)stream>>>(T, B, reward, value, done, trunc, last_value,
+    qs::gae_kernel<<<nblocks(B, qs::kGaeBlock), qs::kGaeBlock, 0, (cudaStream_t)stream>>>(T, B, reward, value, done, trunc, last_value,
                                                                       gamma, lam, brax_form, adv, ret);
     return check_launch("gae_kernel");
 }

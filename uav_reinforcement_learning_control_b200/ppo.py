@@ -15,7 +15,7 @@ from dataclasses import dataclass
 from . import config as Q
 from .parallel import DistContext, flat_allreduce_mean_, reduce_stats
 
-__all__ = ["PPOConfig", "ActorCritic", "PPOTrainer"]
+__all__ = ["PPOConfig", "ActorCritic", "PPOTrainer", "load_sb3_policy_zip", "sb3_state_dict_to_packed"]
 
 H, A = 128, 4
 
@@ -157,3 +157,57 @@ class PPOTrainer:
             s.update(self.episode_stats())
             log.append(s)
         return log
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SB3 policy import ("SB3 .zip policy import for evaluation parity").
+# ``model.save(final_path)`` (train.py:141) writes a zip whose ``policy.pth`` is the torch ``state_dict`` of SB3's
+# ``ActorCriticPolicy`` with ``net_arch=dict(pi=[128,128], vf=[128,128])``, ReLU (train.py:61-64).  Its tensors are
+# plain ``torch.Tensor``s, so no stable-baselines3 install is needed to read them.  torch Linear stores [out][in]; the
+# kernels' packed vector (include/quadsim_abi.h: qs_policy_param_count) stores [in][out].
+_SB3_KEYS = {
+    "aW1": "mlp_extractor.policy_net.0.weight", "ab1": "mlp_extractor.policy_net.0.bias",
+    "aW2": "mlp_extractor.policy_net.2.weight", "ab2": "mlp_extractor.policy_net.2.bias",
+    "aW3": "action_net.weight", "ab3": "action_net.bias",
+    "cW1": "mlp_extractor.value_net.0.weight", "cb1": "mlp_extractor.value_net.0.bias",
+    "cW2": "mlp_extractor.value_net.2.weight", "cb2": "mlp_extractor.value_net.2.bias",
+    "cW3": "value_net.weight", "cb3": "value_net.bias",
+}
+
+
+def sb3_state_dict_to_packed(sd, obs_dim: int = 12, obs_mean=None, obs_var=None, eps: float = 1e-8):
+    """SB3 ActorCriticPolicy state_dict -> float32 packed parameter vector for ``Engine.rollout_policy(dist=0)``.
+
+    ``obs_mean`` / ``obs_var`` are VecNormalize statistics if the run used them (the reference's train.py does not);
+    they become the kernels' (mean, inv_std) observation normaliser."""
+    import torch
+    missing = [k for k in list(_SB3_KEYS.values()) + ["log_std"] if k not in sd]
+    if missing:
+        raise KeyError(f"not an SB3 MlpPolicy [128,128]/[128,128] state_dict, missing: {missing}")
+    f = lambda k: sd[k].detach().to(torch.float32).cpu()
+    shapes = {"aW1": (H, obs_dim), "aW2": (H, H), "aW3": (A, H), "cW1": (H, obs_dim), "cW2": (H, H), "cW3": (1, H)}
+    parts = []
+    for net in ("a", "c"):
+        for layer in ("1", "2", "3"):
+            w = f(_SB3_KEYS[f"{net}W{layer}"]); b = f(_SB3_KEYS[f"{net}b{layer}"])
+            if tuple(w.shape) != shapes[f"{net}W{layer}"]:
+                raise ValueError(f"{_SB3_KEYS[f'{net}W{layer}']}: shape {tuple(w.shape)}, expected {shapes[f'{net}W{layer}']}")
+            parts += [w.t().contiguous().reshape(-1), b.reshape(-1)]
+    parts.append(f("log_std").reshape(-1))
+    mean = torch.zeros(obs_dim) if obs_mean is None else torch.as_tensor(obs_mean, dtype=torch.float32).reshape(-1)
+    inv = torch.ones(obs_dim) if obs_var is None else 1.0 / torch.sqrt(torch.as_tensor(obs_var, dtype=torch.float32).reshape(-1) + eps)
+    parts += [mean, inv]
+    return torch.cat(parts).contiguous()
+
+
+def load_sb3_policy_zip(path: str, obs_dim: int = 12, device=None):
+    """``PPO.save`` zip (train.py:141) -> packed parameter vector on ``device``."""
+    import io
+    import zipfile
+    import torch
+    with zipfile.ZipFile(path) as z:
+        if "policy.pth" not in z.namelist():
+            raise ValueError(f"{path}: no policy.pth inside (not a stable-baselines3 model zip)")
+        sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
+    p = sb3_state_dict_to_packed(sd, obs_dim)
+    return p if device is None else p.to(device)

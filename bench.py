@@ -360,6 +360,28 @@ def main():
             "policy_tflops_bf16": flop * nb * Tp / (ms_roll * 1e-3) / 1e12,
             "note": "tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), 128-env M tiles, 64 of 148 SMs busy at 8192 envs"}
         del eng_p
+        # the same config in MJX-parity mode: JaxMJXQuadBraxEnv (21-D obs, Episode + AutoReset wrappers), tanh-normal
+        # policy, brax GAE -- fp32 FMA path and tcgen05 path
+        cfg_b = Q.EnvConfig.mjx_brax(episode_length=500, auto_reset=Q.RESET_RESTORE_FIRST, seed=3, env_id_offset=rank * nb)
+        eng_b = Engine(cfg_b, nb, device=local)
+        st_b = eng_b.new_state(); first_b = torch.zeros(21, nb, device=dev)
+        eng_b.reset(st_b, first_state=first_b)
+        params_b = make_policy_params(eng_b, torch, dev, seed=0, dist=1)
+        Tb = 256
+        for key, tcf in (("rollout_mjx_brax", False), ("rollout_mjx_brax_tc", True)):
+            bufb = eng_b.rollout_policy(st_b, params_b, T=Tb, t0=0, dist=1, first_state=first_b, tensor_cores=tcf)
+            advb, retb = eng_b.gae(bufb["reward"], bufb["value"], bufb["done"], bufb["trunc"], bufb["last_value"], 0.99, 0.95, brax_form=True)
+            barrier()
+            e0.record(stream)
+            eng_b.rollout_policy(st_b, params_b, T=Tb, t0=Tb, dist=1, first_state=first_b, buffers=bufb, tensor_cores=tcf)
+            eng_b.gae(bufb["reward"], bufb["value"], bufb["done"], bufb["trunc"], bufb["last_value"], 0.99, 0.95, brax_form=True,
+                      adv=advb, ret=retb)
+            e1.record(stream)
+            barrier()
+            ms_b = max_over_ranks(e0.elapsed_time(e1))
+            line[key] = {"value": world * nb * Tb / (ms_b * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb, "T": Tb,
+                         "note": "JaxMJXQuadBraxEnv semantics, 21-D obs, tanh-normal 2x128 actor-critic, brax GAE"}
+        del eng_b, bufb
         # big-batch policy rollout (per-GPU shard of configs[4]): 2^18 envs x 32 steps
         nb2, T2 = 1 << 18, 32
         cfg_q = Q.EnvConfig.north_star(seed=2, env_id_offset=rank * nb2)

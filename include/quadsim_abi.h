@@ -213,7 +213,8 @@ typedef struct QsPolicyDesc {
                                1 = Brax tanh-normal, actor head emits loc|raw_scale (8) */
     int32_t deterministic;  /* 1: action = mean (tanh(mean) for dist 1) */
     float bootstrap_gamma;  /* > 0: SB3 timeout bootstrap, reward += gamma * V(terminal_obs) on truncation */
-    int32_t tensor_cores;   /* 0: fp32 FMA path; 1: tcgen05/TMEM path (bf16 operands, fp32 accumulate; 12-D obs only) */
+    int32_t tensor_cores;   /* 0: fp32 FMA path; 1: tcgen05/TMEM path (bf16 operands, fp32 accumulate): hover_gym dist 0|1,
+                               traj_gym dist 0, mjx_brax / hover_brax dist 1 */
     int32_t reserved[1];
 } QsPolicyDesc;
 

@@ -221,3 +221,49 @@ def test_rollout_tensor_core_path(dist, B, T):
     buf2 = eng.rollout_policy(st2, torch.from_numpy(params).cuda(), T=1, t0=3, dist=dist)
     np.testing.assert_array_equal(buf2["obs"][0].cpu().numpy(), b["obs"][0])
     assert np.abs(buf2["value"][0].cpu().numpy() - b["value"][0]).max() < 0.1
+
+
+@pytest.mark.parametrize("mode,B,T", [("mjx_brax", 300, 6), ("hover_brax", 130, 5), ("mjx_brax", 1100, 5)])
+def test_rollout_tensor_core_path_21d(mode, B, T):
+    """tcgen05/TMEM policy forward on the 21-D raw observation of the Brax envs (layer-1 K = 32, tanh-normal head):
+    same checks as the 12-D case -- the recorded observations through the oracle's bf16-operand forward must give the
+    kernel's actions / values / log-probs -- plus agreement of every recorded stream with the fp32 FMA kernel's
+    bookkeeping (done / trunc flags are functions of the state, which the two paths evolve with the same actions only
+    approximately, so they are compared on the first step, where both start from identical states)."""
+    import torch
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    mk = Q.EnvConfig.mjx_brax if mode == "mjx_brax" else Q.EnvConfig.hover_brax
+    cfg = mk(episode_length=4, auto_reset=Q.RESET_RESTORE_FIRST, seed=31, env_id_offset=9)
+    eng = Engine(cfg, B, device=0)
+    st = eng.new_state(); first = torch.zeros(21, B, device="cuda")
+    eng.reset(st, first_state=first)
+    st0 = st.clone()
+    params = _random_policy(21, 1, seed=5, scale=0.6)
+    d_params = torch.from_numpy(params).cuda()
+    buf = eng.rollout_policy(st, d_params, T=T, t0=11, dist=1, first_state=first, tensor_cores=True)
+    torch.cuda.synchronize()
+    b = {k: v.cpu().numpy() for k, v in buf.items()}
+    pp = ppo_ref.unpack(params, 21, 1)
+    ids = np.arange(B, dtype=np.uint32) + np.uint32(9)
+    for t in range(T):
+        head, value = ppo_ref.forward(pp, b["obs"][t], bf16=True)
+        raw, act, logp = ppo_ref.sample(pp, head, ppo_ref.policy_noise(cfg.seed, ids, 11 + t), 1)
+        assert_close(b["value"][t], value, rtol=2e-3, atol=2e-3, what=f"t={t} value (tcgen05, 21-D)")
+        assert_close(b["act"][t], raw, rtol=3e-3, atol=3e-3, what=f"t={t} action (tcgen05, 21-D)")
+        assert_close(b["logp"][t], logp, rtol=1e-2, atol=1e-2, what=f"t={t} logp (tcgen05, 21-D)")
+    _, v_last = ppo_ref.forward(pp, b["last_obs"], bf16=True)
+    assert_close(b["last_value"], v_last, rtol=2e-3, atol=2e-3, what="last value (tcgen05, 21-D)")
+    assert np.isfinite(b["obs"]).all() and np.isfinite(b["reward"]).all()
+    # EpisodeWrapper: 4-step episodes -> an env that did not terminate earlier is done (truncated) at t = 3 and
+    # restored to its first observation at t = 4 (AutoResetWrapper)
+    full = b["done"][:3].sum(axis=0) == 0
+    assert (b["done"][3][full] == 1).all() and (b["trunc"][3][full] == 1).all()
+    if T > 4:
+        was_done = b["done"][3] == 1
+        np.testing.assert_array_equal(b["obs"][4][was_done], b["obs"][0][was_done])
+    if mode == "mjx_brax":       # (the fp32 FMA kernel is not instantiated for hover_brax)
+        # against the fp32 FMA kernel from the same start: identical first observation, same flags on step 0
+        buf2 = eng.rollout_policy(st0, d_params, T=1, t0=11, dist=1, first_state=first)
+        np.testing.assert_array_equal(buf2["obs"][0].cpu().numpy(), b["obs"][0])
+        np.testing.assert_array_equal(buf2["done"][0].cpu().numpy(), b["done"][0])
+        assert np.abs(buf2["value"][0].cpu().numpy() - b["value"][0]).max() < 0.1

@@ -24,6 +24,11 @@ def run(cfg, n, tc=False, first=False, rollout=True):
     term = torch.zeros(n, cfg.obs_dim, device="cuda")
     for _ in range(3):
         eng.step(st, act, truncated=trunc, metrics=met, terminal_obs=term, first_state=fs)
+    if fs is None:
+        for _ in range(3):
+            eng.step(st, act)                       # lean instantiation where the configuration allows it
+    if cfg.mode == Q.MODE_TRAJ_GYM:
+        eng.traj_info(st)
     eng.observe(st, act)
     stats = torch.zeros(4, n, device="cuda")
     eng.rollout_random(st, 5, t0=0, stats=stats, first_state=fs)
@@ -39,9 +44,11 @@ def run(cfg, n, tc=False, first=False, rollout=True):
 
 
 run(Q.EnvConfig.north_star(max_episode_steps=4), 300, tc=True)
-run(Q.EnvConfig.north_star(max_episode_steps=4), 40000, tc=True)          # 2-tile tcgen05 variant
+if not os.environ.get("QS_SANITIZE_SMALL"):
+    run(Q.EnvConfig.north_star(max_episode_steps=4), 40000, tc=True)      # 2-tile tcgen05 variant
 run(Q.EnvConfig.hover_gym(rate_wrapper=True, auto_reset=Q.RESET_RESAMPLE, max_episode_steps=3), 130)
 run(Q.EnvConfig.mjx_brax(episode_length=3, auto_reset=Q.RESET_RESTORE_FIRST), 130, first=True)
+run(Q.EnvConfig.traj_gym(auto_reset=Q.RESET_RESAMPLE, max_episode_steps=3), 200)
 run(Q.EnvConfig.hover_brax(), 70, rollout=False)
 run(Q.EnvConfig.mjx_playground(), 70, rollout=False)
 run(Q.EnvConfig.waypoint_eval(TJ.default_tables(0.5), auto_reset=Q.RESET_RESAMPLE), 100, rollout=True)

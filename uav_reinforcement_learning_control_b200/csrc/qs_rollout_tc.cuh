@@ -161,34 +161,42 @@ __device__ __forceinline__ uint32_t op_offset(int rows, int row, int kc) {
     return (uint32_t)((kc * (rows >> 3) + (row >> 3)) * 128 + (row & 7) * 16);
 }
 
-// shared-memory map (bytes)
-struct Smem {
-    static constexpr int W1 = 0;                          // B: [256 x 16] bf16
-    static constexpr int W2A = W1 + 256 * 16 * 2;         // B: [128 x 128]
+// shared-memory map (bytes).  K1 = layer-1 K (observation + 2 bias slots, padded to a multiple of 16): 16 for the
+// 12-D gym observation, 32 for the 21-D raw observation of the brax / mjx modes.
+template <int K1>
+struct SmemT {
+    static constexpr int W1 = 0;                          // B: [256 x K1] bf16
+    static constexpr int W2A = W1 + 256 * K1 * 2;         // B: [128 x 128]
     static constexpr int W2C = W2A + 128 * 128 * 2;
     static constexpr int W3A = W2C + 128 * 128 * 2;       // B: [16 x 128]
     static constexpr int W3C = W3A + 16 * 128 * 2;
-    static constexpr int B2A = W3C + 16 * 128 * 2;        // B: [128 x 16], K rows 12 / 13 = hi / lo halves of the layer-2 bias
+    static constexpr int B2A = W3C + 16 * 128 * 2;        // B: [128 x 16], two K rows = hi / lo halves of the layer-2 bias
     static constexpr int B2C = B2A + 128 * 16 * 2;
     static constexpr int WEND = B2C + 128 * 16 * 2;       // end of the (shared) B operands
-    // per tile: A1 [128 x 16], A2A / A2C [128 x 128] (A2* are also the A operands of L3)
-    static constexpr int A1 = 0, A2A = 128 * 16 * 2, A2C = A2A + 128 * 128 * 2, TILE_BYTES = A2C + 128 * 128 * 2;
+    // per tile: A1 [128 x K1], A2A / A2C [128 x 128] (A2* are also the A operands of L3), and for the 21-D modes a
+    // float staging tile for the coalesced trajectory store of the raw observations
+    static constexpr int A1 = 0, A2A = 128 * K1 * 2, A2C = A2A + 128 * 128 * 2;
+    static constexpr int OBS = A2C + 128 * 128 * 2;
+    static constexpr int TILE_BYTES = OBS + (K1 > 16 ? 128 * 21 * 4 : 0);
     static constexpr int TILE0 = WEND;
     __host__ __device__ static constexpr int f32_off(int tiles) { return TILE0 + tiles * TILE_BYTES; }   // fp32 constants, see below
-    static constexpr int kB1 = 0, kB2A = 256, kB2C = 384, kB3 = 512 /*[32]*/, kLogStd = 544, kMean = 548, kInvStd = 560,
-                         kNumF = 576;
+    static constexpr int kB3 = 0 /*[32]*/, kLogStd = 32, kMean = 36, kInvStd = 60, kNumF = 84;
     __host__ __device__ static constexpr int bar_off(int tiles) { return f32_off(tiles) + kNumF * 4; }   // mbarriers (8 B per tile) + tmem base (4 B)
     __host__ __device__ static constexpr int total(int tiles) { return bar_off(tiles) + 8 * tiles + 16; }
 };
 
-// this path is built for the 12-D gym observation (K padded to 16)
 template <int MODE, int DIST, int TILES>
 __global__ void __launch_bounds__(kM * TILES, 1)
 rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restrict__ state,
                          const float* __restrict__ params, int steps, uint32_t t0, int deterministic,
                          float bootstrap_gamma, RolloutBuffers rb, const float* __restrict__ first) {
-    static_assert(ModeTraits<MODE>::kObsDim == 12, "tensor-core rollout is built for the 12-D observation");
-    constexpr int D = 12;
+    constexpr int D = ModeTraits<MODE>::kObsDim;
+    constexpr bool kGym = ModeTraits<MODE>::kGym;
+    constexpr int K1 = (D + 2 <= 16) ? 16 : 32;            // observation + two bias slots
+    constexpr int kS1 = K1 / 16;                           // layer-1 K = 16 steps
+    constexpr int kBiasStep = D / 16, kBiasK = D % 16;     // K step / slot (and slot + 1) that carry the constant 1
+    static_assert(D + 2 <= K1 && kBiasK + 1 < 16, "bias slots must fit one K = 16 step");
+    using Smem = SmemT<K1>;
     constexpr int Ao = DIST == 1 ? 2 * kA : kA;
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr uint32_t kTmemCols = kTileCols * TILES;
@@ -212,20 +220,20 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             const float w = nn < 128 ? params[L.aW1 + k * kH + nn] : params[L.cW1 + k * kH + (nn - 128)];
             *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(w);
         }
-        // the layer-1 bias rides in the padded K slots 12 (bf16 high part) and 13 (bf16 low part); the A operand
-        // carries a constant 1 in both.  The layer-2 bias uses the same two slots of the B2A / B2C operands.
+        // the layer-1 bias rides in the padded K slots D (bf16 high part) and D + 1 (bf16 low part); the A operand
+        // carries a constant 1 in both.  The layer-2 bias uses the same two slots (of that K = 16 step) in B2A / B2C.
         for (int nn = gtid; nn < 256; nn += NT) {
             const float bv = nn < 128 ? params[L.ab1 + nn] : params[L.cb1 + (nn - 128)];
             const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
             const __nv_bfloat16 lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
-            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, 1) + 4 * 2) = hi;
-            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, 1) + 5 * 2) = lo;
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, D >> 3) + (D & 7) * 2) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(smem + Smem::W1 + op_offset(256, nn, (D + 1) >> 3) + ((D + 1) & 7) * 2) = lo;
             const float b2 = nn < 128 ? params[L.ab2 + nn] : params[L.cb2 + (nn - 128)];
             const __nv_bfloat16 hi2 = __float2bfloat16_rn(b2);
             const __nv_bfloat16 lo2 = __float2bfloat16_rn(b2 - __bfloat162float(hi2));
             const int dst = nn < 128 ? Smem::B2A : Smem::B2C;
-            *reinterpret_cast<__nv_bfloat16*>(smem + dst + op_offset(128, nn & 127, 1) + 4 * 2) = hi2;
-            *reinterpret_cast<__nv_bfloat16*>(smem + dst + op_offset(128, nn & 127, 1) + 5 * 2) = lo2;
+            *reinterpret_cast<__nv_bfloat16*>(smem + dst + op_offset(128, nn & 127, kBiasK >> 3) + (kBiasK & 7) * 2) = hi2;
+            *reinterpret_cast<__nv_bfloat16*>(smem + dst + op_offset(128, nn & 127, (kBiasK + 1) >> 3) + ((kBiasK + 1) & 7) * 2) = lo2;
         }
         for (int idx = gtid; idx < kH * kH; idx += NT) {
             const int k = idx / kH, nn = idx % kH;
@@ -266,7 +274,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     const uint32_t tbase = smem_u32(tsm);
     const uint32_t idesc_l1 = make_idesc(128, 256), idesc_l2 = make_idesc(128, 128), idesc_l3 = make_idesc(128, 16);
     // descriptors: LBO = (rows/8)*128 bytes between the two 16-byte K chunks of one instruction, SBO = 128
-    const uint64_t dA1 = make_desc(tbase + Smem::A1, 16 * 128, 128), dW1 = make_desc(sbase + Smem::W1, 32 * 128, 128);
+    const uint64_t dA1b = make_desc(tbase + Smem::A1 + kBiasStep * 4096, 16 * 128, 128);   // the K step with the constant-1 slots
     uint32_t phase = 0;
 
     const bool owner = (b0 + tid) < n;
@@ -275,8 +283,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     float obs_[D];
     if (owner) {
         load_env<MODE>(P, state, n, b0 + tid, e);
-        float rpy[3];
-        quat_to_rpy(e.b.q, rpy);
+        float rpy[3] = {0.f, 0.f, 0.f};
+        if constexpr (kGym) quat_to_rpy(e.b.q, rpy);
         compute_obs<MODE>(P, e, rpy, obs_);
     } else {
 #pragma unroll
@@ -289,22 +297,26 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
 #endif
     // forward pass for the observation in `o`; returns head[Ao] and value
     auto forward = [&](const float* o, float* head, float& value) {
-        // A1: normalised obs, bf16, K padded 12 -> 16
+        // A1: normalised obs, bf16, K padded D -> K1 with a constant 1 in slots D and D + 1
         {
-            float x[16];
+            float x[K1];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = k < D ? (o[k] - sF[Smem::kMean + k]) * sF[Smem::kInvStd + k] : (k < D + 2 ? 1.0f : 0.f);
-            uint4 c0 = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-            uint4 c1 = make_uint4(pack_bf16(x[8], x[9]), pack_bf16(x[10], x[11]), pack_bf16(x[12], x[13]), pack_bf16(x[14], x[15]));
-            *reinterpret_cast<uint4*>(tsm + Smem::A1 + op_offset(128, tid, 0)) = c0;
-            *reinterpret_cast<uint4*>(tsm + Smem::A1 + op_offset(128, tid, 1)) = c1;
+            for (int k = 0; k < K1; ++k) x[k] = k < D ? (o[k] - sF[Smem::kMean + k]) * sF[Smem::kInvStd + k] : (k < D + 2 ? 1.0f : 0.f);
+#pragma unroll
+            for (int c = 0; c < K1 / 8; ++c)
+                *reinterpret_cast<uint4*>(tsm + Smem::A1 + op_offset(128, tid, c)) =
+                    make_uint4(pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
+                               pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
         }
         fence_async_smem();
         fence_before();
         tile_sync(tile);
         if (tid == 0) {
             fence_after();
-            mma_bf16(tmem, dA1, dW1, idesc_l1, 0u);                         // D1[128 x 256] = A1 . W1cat
+#pragma unroll
+            for (int j = 0; j < kS1; ++j)                                   // D1[128 x 256] = A1 . W1cat (+ b1)
+                mma_bf16(tmem, make_desc(tbase + Smem::A1 + j * 4096, 16 * 128, 128),
+                         make_desc(sbase + Smem::W1 + j * 8192, 32 * 128, 128), idesc_l1, j > 0);
             mma_commit(bar);
         }
         QS_TCP(0);
@@ -342,8 +354,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                          make_desc(sbase + Smem::W2C + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
             }
             // + b2: the layer-1 A operand (constant 1 in K slots 12 / 13) times the hi / lo bias rows
-            mma_bf16(tmem, dA1, make_desc(sbase + Smem::B2A, 16 * 128, 128), idesc_l2, 1u);
-            mma_bf16(tmem + 128u, dA1, make_desc(sbase + Smem::B2C, 16 * 128, 128), idesc_l2, 1u);
+            mma_bf16(tmem, dA1b, make_desc(sbase + Smem::B2A, 16 * 128, 128), idesc_l2, 1u);
+            mma_bf16(tmem + 128u, dA1b, make_desc(sbase + Smem::B2C, 16 * 128, 128), idesc_l2, 1u);
             mma_commit(bar);
         }
         mbar_wait(bar, phase); phase ^= 1;
@@ -393,14 +405,30 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(6);
     };
 
+    // trajectory store of this tile's observation rows.  12-D rows are three aligned float4 per thread; the 21-D rows
+    // (84 B, unaligned) go through a shared staging tile and leave as one contiguous, fully coalesced span per tile.
+    auto store_obs_rows = [&](float* dst_tile) {       // dst_tile = &out[(first env of the tile) * D]
+        if constexpr (D == 12) {
+            if (owner) {
+                float4* dd = reinterpret_cast<float4*>(dst_tile + (size_t)tid * D);
+                dd[0] = make_float4(obs_[0], obs_[1], obs_[2], obs_[3]);
+                dd[1] = make_float4(obs_[4], obs_[5], obs_[6], obs_[7]);
+                dd[2] = make_float4(obs_[8], obs_[9], obs_[10], obs_[11]);
+            }
+        } else {
+            float* stage = reinterpret_cast<float*>(tsm + Smem::OBS);
+#pragma unroll
+            for (int k = 0; k < D; ++k) stage[tid * D + k] = obs_[k];
+            tile_sync(tile);
+            const int rows = min(kM, n - b0);
+            for (int idx = tid; idx < rows * D; idx += kM) dst_tile[idx] = stage[idx];
+            tile_sync(tile);                           // the staging tile is rewritten next step
+        }
+    };
+
     for (int t = 0; t < steps; ++t) {
         const size_t o = (size_t)t * n + b0 + tid;
-        if (owner && rb.obs) {
-            float4* dd = reinterpret_cast<float4*>(rb.obs + o * D);
-            dd[0] = make_float4(obs_[0], obs_[1], obs_[2], obs_[3]);
-            dd[1] = make_float4(obs_[4], obs_[5], obs_[6], obs_[7]);
-            dd[2] = make_float4(obs_[8], obs_[9], obs_[10], obs_[11]);
-        }
+        if (rb.obs) store_obs_rows(rb.obs + ((size_t)t * n + b0) * D);
         QS_TCP(11);
         float head[Ao], value;
         forward(obs_, head, value);
@@ -447,11 +475,13 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             QS_TCP(7);
             env_step<MODE, true>(P, T, gid, e, act, obs_, tobs, first ? first + b0 + tid : nullptr, n, so);
             need_boot = bootstrap_gamma > 0.f && so.finished && so.truncated != 0.f && so.done == 0.f;
+            if constexpr (ModeTraits<MODE>::kBrax) need_boot = bootstrap_gamma > 0.f && so.truncated != 0.f;
         }
         QS_TCP(8);
         // Philox re-sampling of finished envs, compacted per tile.  The scratch lives in this tile's A2A buffer,
         // which is idle between the head MMAs of this step and the first epilogue of the next one.
-        if (P.auto_reset == QS_RESET_RESAMPLE) {
+        if constexpr (kGym) {
+          if (P.auto_reset == QS_RESET_RESAMPLE) {
             if (P.waypoint_mode) {
                 if (so.needs_reset) {
                     float rpy[3];
@@ -466,6 +496,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 warp_autoreset_smem<MODE>(P, P.env_id_offset + (uint32_t)(b0 + warp * 32), e, obs_, so.needs_reset,
                                           reinterpret_cast<WarpResetScratch*>(tsm + Smem::A2A)[warp]);
             }
+          }
         }
         QS_TCP(9);
         // SB3 timeout bootstrap: reward += gamma * V(terminal_obs) for truncated-not-terminated episodes
@@ -491,13 +522,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     {
         float head[Ao], value;
         forward(obs_, head, value);
+        if (rb.last_obs) store_obs_rows(rb.last_obs + (size_t)b0 * D);
         if (owner) {
-            if (rb.last_obs) {
-                float4* dd = reinterpret_cast<float4*>(rb.last_obs + (size_t)(b0 + tid) * D);
-                dd[0] = make_float4(obs_[0], obs_[1], obs_[2], obs_[3]);
-                dd[1] = make_float4(obs_[4], obs_[5], obs_[6], obs_[7]);
-                dd[2] = make_float4(obs_[8], obs_[9], obs_[10], obs_[11]);
-            }
             if (rb.last_value) rb.last_value[b0 + tid] = value;
             store_env<MODE>(P, state, n, b0 + tid, e);
         }
@@ -515,6 +541,7 @@ inline int launch_rollout_tc_tt(const QsParams& P, const Tables& T, int n, float
                                 uint32_t t0, const RolloutOpts& opt, const RolloutBuffers& rb, const float* first,
                                 cudaStream_t s) {
     auto kern = rollout_policy_tc_kernel<MODE, DIST, TILES>;
+    using Smem = SmemT<(ModeTraits<MODE>::kObsDim + 2 <= 16) ? 16 : 32>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total(TILES));
     if (ce != cudaSuccess) return (int)ce;
     kern<<<(n + kM * TILES - 1) / (kM * TILES), kM * TILES, Smem::total(TILES), s>>>(
@@ -526,8 +553,11 @@ template <int MODE, int DIST>
 inline int launch_rollout_tc_t(const QsParams& P, const Tables& T, int n, float* state, const float* params, int steps,
                                uint32_t t0, const RolloutOpts& opt, const RolloutBuffers& rb, const float* first,
                                cudaStream_t s) {
-    // two tiles per CTA only when that still gives every SM a CTA
-    if (n >= 148 * 2 * kM) return launch_rollout_tc_tt<MODE, DIST, 2>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    // two tiles per CTA only when that still gives every SM a CTA; the 21-D modes (K1 = 32 operands + the observation
+    // staging tile) do not fit two tiles into 227 KB of shared memory
+    if constexpr (ModeTraits<MODE>::kObsDim == 12) {
+        if (n >= 148 * 2 * kM) return launch_rollout_tc_tt<MODE, DIST, 2>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    }
     return launch_rollout_tc_tt<MODE, DIST, 1>(P, T, n, state, params, steps, t0, opt, rb, first, s);
 }
 
@@ -541,6 +571,11 @@ inline int launch_rollout_policy_tc(const QsParams& P, const Tables& T, int n, f
         return launch_rollout_tc_t<QS_MODE_HOVER_GYM, 1>(P, T, n, state, params, steps, t0, opt, rb, first, s);
     if (P.mode == QS_MODE_TRAJ_GYM && d.dist == 0)
         return launch_rollout_tc_t<QS_MODE_TRAJ_GYM, 0>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    // 21-D raw observation (train_brax_ppo.py:366-368): the Brax trainer's envs with its tanh-normal policy
+    if (P.mode == QS_MODE_MJX_BRAX && d.dist == 1)
+        return launch_rollout_tc_t<QS_MODE_MJX_BRAX, 1>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    if (P.mode == QS_MODE_HOVER_BRAX && d.dist == 1)
+        return launch_rollout_tc_t<QS_MODE_HOVER_BRAX, 1>(P, T, n, state, params, steps, t0, opt, rb, first, s);
     return -100;
 }
 

@@ -342,7 +342,6 @@ int qs_rollout_policy(QsHandle h, float* state, const QsPolicyDesc* desc, const 
     qs::RolloutBuffers rb{last_obs, traj_obs, traj_act, traj_logp, traj_value, traj_reward, traj_done, traj_trunc, last_value};
     int rc;
     if (desc->tensor_cores) {
-        if (h->P.obs_dim != 12) return fail(QS_EUNSUPPORTED, "qs_rollout_policy: the tcgen05 path is built for the 12-D observation");
         rc = qs::tc::launch_rollout_policy_tc(h->P, h->tables(), h->n, state, *desc, policy_params, T, t0, rb, first_state,
                                               (cudaStream_t)stream);
     } else {

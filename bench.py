@@ -286,6 +286,8 @@ def main():
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e = {"value": world * n * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 * n,
            "d2h_bytes_per_step": (48 + 8) * n, "steps": Ke, "ms_per_step": ms_e2e / Ke,
+           "pcie_d2h_gbs_per_gpu": (48 + 8) * n * Ke / (ms_e2e * 1e-3) / 1e9,      # what bounds it: obs/reward/done over PCIe
+           "pcie_h2d_gbs_per_gpu": 16 * n * Ke / (ms_e2e * 1e-3) / 1e9,
            "api": "qs_step_host (C ABI, pinned host buffers; what HoverVecEnv.step(numpy) calls)"}
 
     line = {

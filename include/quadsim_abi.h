@@ -116,6 +116,8 @@ typedef struct QsParams {
     float reset_z;                    /* brax modes: nominal height               */
     uint32_t seed_lo, seed_hi;
     uint32_t env_id_offset;           /* global id of local env 0 (sharding)      */
+    uint32_t philox_key[20];          /* Philox4x32-10 round keys of (seed_lo, seed_hi): [2r] = seed_lo + r*0x9E3779B9,
+                                         [2r+1] = seed_hi + r*0xBB67AE85 -- precomputed so the kernels need no key schedule */
     /* --- waypoint tracking (evaluate.py:440-557) --------------------------- */
     int32_t waypoint_mode;            /* 0 off */
     int32_t wp_num_shapes;

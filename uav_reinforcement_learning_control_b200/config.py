@@ -54,7 +54,7 @@ class QsParams(C.Structure):
         ("init_lo", C.c_float * 12), ("init_hi", C.c_float * 12),
         ("target_lo", C.c_float * 3), ("target_hi", C.c_float * 3),
         ("reset_noise", C.c_float), ("reset_z", C.c_float),
-        ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("env_id_offset", C.c_uint32),
+        ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("env_id_offset", C.c_uint32), ("philox_key", C.c_uint32 * 20),
         ("waypoint_mode", C.c_int32), ("wp_num_shapes", C.c_int32), ("wp_count", C.c_int32 * MAX_SHAPES),
         ("wp_reach_radius", C.c_float),
         ("rate_wrapper", C.c_int32), ("rate_max", C.c_float), ("rate_kd", C.c_float * 3),
@@ -256,6 +256,9 @@ def pack_params(c: QuadConstants, cfg: EnvConfig) -> QsParams:
     P.reset_noise, P.reset_z = cfg.reset_noise, cfg.reset_z
     P.seed_lo, P.seed_hi = cfg.seed & 0xFFFFFFFF, (cfg.seed >> 32) & 0xFFFFFFFF
     P.env_id_offset = cfg.env_id_offset
+    for r in range(10):
+        P.philox_key[2 * r] = (P.seed_lo + r * 0x9E3779B9) & 0xFFFFFFFF
+        P.philox_key[2 * r + 1] = (P.seed_hi + r * 0xBB67AE85) & 0xFFFFFFFF
     P.waypoint_mode = int(cfg.waypoint_mode)
     P.wp_num_shapes = len(cfg.waypoints)
     for s, w in enumerate(cfg.waypoints):

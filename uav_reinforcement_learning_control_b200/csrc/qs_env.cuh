@@ -204,7 +204,7 @@ QS_HD void rate_to_torque(const QsParams& P, const float a[4], const float w[3],
 QS_HD void quat_to_rpy(const float q[4], float rpy[3]) {
     const float w = q[0], x = q[1], y = q[2], z = q[3];
     rpy[0] = atan2_(2.f * fma_(y, z, w * x), fma_(-2.f, fma_(x, x, y * y), 1.f));
-    rpy[1] = asinf(clamp_(2.f * fma_(w, y, -x * z), -1.f, 1.f));
+    rpy[1] = asin_unit_(clamp_(2.f * fma_(w, y, -x * z), -1.f, 1.f));
     rpy[2] = atan2_(2.f * fma_(x, y, w * z), fma_(-2.f, fma_(y, y, z * z), 1.f));
 }
 
@@ -364,7 +364,7 @@ QS_HD void reset_env(const QsParams& P, const Tables& T, uint32_t gid, Env& e, f
         float s12[12];
 #pragma unroll
         for (int blk = 0; blk < 3; ++blk) {
-            const U4 r = philox4x32_10(U4{gid, e.episode, (uint32_t)blk, STREAM_RESET}, P.seed_lo, P.seed_hi);
+            const U4 r = philox4x32_10(U4{gid, e.episode, (uint32_t)blk, STREAM_RESET}, P.philox_key);
             s12[4 * blk + 0] = uniform_(r.x, P.init_lo[4 * blk + 0], P.init_hi[4 * blk + 0]);
             s12[4 * blk + 1] = uniform_(r.y, P.init_lo[4 * blk + 1], P.init_hi[4 * blk + 1]);
             s12[4 * blk + 2] = uniform_(r.z, P.init_lo[4 * blk + 2], P.init_hi[4 * blk + 2]);
@@ -376,7 +376,7 @@ QS_HD void reset_env(const QsParams& P, const Tables& T, uint32_t gid, Env& e, f
         e.b.v[0] = s12[6]; e.b.v[1] = s12[7]; e.b.v[2] = s12[8];
         e.b.w[0] = s12[9]; e.b.w[1] = s12[10]; e.b.w[2] = s12[11];
         if constexpr (MODE == QS_MODE_HOVER_GYM) {
-            const U4 r = philox4x32_10(U4{gid, e.episode, 3u, STREAM_RESET}, P.seed_lo, P.seed_hi);
+            const U4 r = philox4x32_10(U4{gid, e.episode, 3u, STREAM_RESET}, P.philox_key);
             e.target[0] = uniform_(r.x, P.target_lo[0], P.target_hi[0]);
             e.target[1] = uniform_(r.y, P.target_lo[1], P.target_hi[1]);
             e.target[2] = uniform_(r.z, P.target_lo[2], P.target_hi[2]);
@@ -396,7 +396,7 @@ QS_HD void reset_env(const QsParams& P, const Tables& T, uint32_t gid, Env& e, f
         float n21[24];
 #pragma unroll
         for (int blk = 0; blk < 6; ++blk) {
-            const U4 r = philox4x32_10(U4{gid, e.episode, (uint32_t)blk, STREAM_RESET}, P.seed_lo, P.seed_hi);
+            const U4 r = philox4x32_10(U4{gid, e.episode, (uint32_t)blk, STREAM_RESET}, P.philox_key);
             n21[4 * blk + 0] = uniform_(r.x, -P.reset_noise, P.reset_noise);
             n21[4 * blk + 1] = uniform_(r.y, -P.reset_noise, P.reset_noise);
             n21[4 * blk + 2] = uniform_(r.z, -P.reset_noise, P.reset_noise);

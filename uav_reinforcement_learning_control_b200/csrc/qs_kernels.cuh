@@ -164,7 +164,7 @@ __device__ __forceinline__ void warp_autoreset(const QsParams& P, const Tables& 
         const int src = r < npass ? (int)__fns(pending, 0, r + 1) : 0;
         const uint32_t epi_src = __shfl_sync(0xffffffffu, e.episode, src);
         U4 rnd = U4{0u, 0u, 0u, 0u};
-        if (r < npass) rnd = philox4x32_10(U4{gid_warp_first + (uint32_t)src, epi_src, (uint32_t)blk, STREAM_RESET}, P.seed_lo, P.seed_hi);
+        if (r < npass) rnd = philox4x32_10(U4{gid_warp_first + (uint32_t)src, epi_src, (uint32_t)blk, STREAM_RESET}, P.philox_key);
         const int myrank = __popc(pending & ((1u << lane) - 1u));
         const bool mine = need && ((pending >> lane) & 1u) && myrank < 8;
         const int from = (mine ? myrank : 0) * 4;
@@ -233,7 +233,7 @@ __device__ __forceinline__ void warp_autoreset_smem(const QsParams& P, uint32_t 
         const int r = lane >> 2, blk = lane & 3;
         constexpr int kBlocks = (MODE == QS_MODE_HOVER_GYM) ? 4 : 3;
         if (r < npass && blk < kBlocks) {
-            const U4 rnd = philox4x32_10(U4{gid_warp_first + S.src[r], S.epi[r], (uint32_t)blk, STREAM_RESET}, P.seed_lo, P.seed_hi);
+            const U4 rnd = philox4x32_10(U4{gid_warp_first + S.src[r], S.epi[r], (uint32_t)blk, STREAM_RESET}, P.philox_key);
             // words 0..11 -> state12 ranges, 12..14 -> target ranges: both live in one table of 16 (lo, hi) pairs
             const float* lo = blk < 3 ? &P.init_lo[4 * blk] : &P.target_lo[0];
             const float* hi = blk < 3 ? &P.init_hi[4 * blk] : &P.target_hi[0];
@@ -818,7 +818,7 @@ rollout_random_kernel(const __grid_constant__ QsParams P, Tables T, int n, float
         StepOut so;
         so.needs_reset = false;
         if (valid) {
-            const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_ACTION}, P.seed_lo, P.seed_hi);
+            const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_ACTION}, P.philox_key);
             const float a[4] = {uniform_(r.x, -1.f, 1.f), uniform_(r.y, -1.f, 1.f), uniform_(r.z, -1.f, 1.f),
                                 uniform_(r.w, -1.f, 1.f)};
             env_step<MODE, kGym>(P, T, gid, e, a, o_, nullptr, first ? first + i : nullptr, n, so);

@@ -39,6 +39,21 @@ QS_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
     return c;
 }
 
+// the same with the ten round keys precomputed (QsParams.philox_key): two IMAD.WIDE + two LOP3 per round, the keys
+// come straight from the constant bank
+QS_HD U4 philox4x32_10(U4 c, const uint32_t* __restrict__ key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo_(0xD2511F53u, c.x, &hi0, &lo0);
+        mulhilo_(0xCD9E8D57u, c.z, &hi1, &lo1);
+        U4 n;
+        n.x = hi1 ^ c.y ^ key[2 * r]; n.y = lo1; n.z = hi0 ^ c.w ^ key[2 * r + 1]; n.w = lo0;
+        c = n;
+    }
+    return c;
+}
+
 // 24-bit uniform in [0, 1)
 QS_HD float u01_(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
 

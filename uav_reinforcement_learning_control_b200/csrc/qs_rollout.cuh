@@ -211,7 +211,7 @@ rollout_policy_kernel(const __grid_constant__ QsParams P, Tables T, int n, float
         float tobs[D];
         bool need_boot = false;
         if (owner) {
-            const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_POLICY}, P.seed_lo, P.seed_hi);
+            const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_POLICY}, P.philox_key);
             // Box-Muller: two pairs
             float eps[4];
             {

@@ -438,7 +438,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         float tobs[D];
         bool need_boot = false;
         if (owner) {
-            const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_POLICY}, P.seed_lo, P.seed_hi);
+            const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_POLICY}, P.philox_key);
             float eps[4];
             {
                 const float u0 = ((float)(r.x >> 8) + 1.0f) * 5.9604644775390625e-8f;

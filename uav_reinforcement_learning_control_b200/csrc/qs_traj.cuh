@@ -59,10 +59,10 @@ QS_HD void traj_info_eval(const QsParams& P, uint32_t gid, uint32_t episode, int
         T = (double)(N - 1) * (double)P.dt;
         t = (double)idx * (double)P.dt;
     }
-    const U4 r0 = philox4x32_10(U4{gid, episode, 0u, STREAM_RESET}, P.seed_lo, P.seed_hi);
+    const U4 r0 = philox4x32_10(U4{gid, episode, 0u, STREAM_RESET}, P.philox_key);
     const float start[3] = {uniform_(r0.x, P.init_lo[0], P.init_hi[0]), uniform_(r0.y, P.init_lo[1], P.init_hi[1]),
                             uniform_(r0.z, P.init_lo[2], P.init_hi[2])};
-    const U4 rc = philox4x32_10(U4{gid, episode, 0u, STREAM_TRAJ}, P.seed_lo, P.seed_hi);
+    const U4 rc = philox4x32_10(U4{gid, episode, 0u, STREAM_TRAJ}, P.philox_key);
     const float centre[3] = {uniform_(rc.x, P.traj_center_lo[0], P.traj_center_hi[0]),
                              uniform_(rc.y, P.traj_center_lo[1], P.traj_center_hi[1]),
                              uniform_(rc.z, P.traj_center_lo[2], P.traj_center_hi[2])};
@@ -72,7 +72,7 @@ QS_HD void traj_info_eval(const QsParams& P, uint32_t gid, uint32_t episode, int
     uint32_t w[16];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        const U4 r = philox4x32_10(U4{gid, episode, (uint32_t)(b + 1), STREAM_TRAJ}, P.seed_lo, P.seed_hi);
+        const U4 r = philox4x32_10(U4{gid, episode, (uint32_t)(b + 1), STREAM_TRAJ}, P.philox_key);
         w[4 * b] = r.x; w[4 * b + 1] = r.y; w[4 * b + 2] = r.z; w[4 * b + 3] = r.w;
     }
     const double h = T / (double)(n - 1);

@@ -27,6 +27,10 @@
 #include "qs_kernels.cuh"
 #include "qs_rollout.cuh"
 
+#ifndef QS_TC_PARTNER
+#define QS_TC_PARTNER 1
+#endif
+
 namespace qs {
 namespace tc {
 
@@ -79,11 +83,13 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // tile-local barriers (128 threads each): the tiles of a CTA never wait for each other inside the step loop,
 // so one tile's MMA phases overlap the other tile's epilogues / env steps
-__device__ __forceinline__ void tile_sync(int tile) { asm volatile("bar.sync %0, 128;" :: "r"(tile + 1) : "memory"); }
+template <int NTHR = 128>
+__device__ __forceinline__ void tile_sync(int tile) { asm volatile("bar.sync %0, %1;" :: "r"(tile + 1), "n"(NTHR) : "memory"); }
+template <int NTHR = 128>
 __device__ __forceinline__ bool tile_or(int tile, bool pred) {
     uint32_t r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %2, 0;\n\tbar.red.or.pred p, %1, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(r) : "r"(tile + 1), "r"((uint32_t)pred) : "memory");
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %2, 0;\n\tbar.red.or.pred p, %1, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(r) : "r"(tile + 1), "r"((uint32_t)pred), "n"(NTHR) : "memory");
     return r != 0;
 }
 
@@ -163,7 +169,7 @@ __device__ __forceinline__ uint32_t op_offset(int rows, int row, int kc) {
 
 // shared-memory map (bytes).  K1 = layer-1 K (observation + 2 bias slots, padded to a multiple of 16): 16 for the
 // 12-D gym observation, 32 for the 21-D raw observation of the brax / mjx modes.
-template <int K1>
+template <int K1, bool PARTNER = false>
 struct SmemT {
     static constexpr int W1 = 0;                          // B: [256 x K1] bf16
     static constexpr int W2A = W1 + 256 * K1 * 2;         // B: [128 x 128]
@@ -177,7 +183,8 @@ struct SmemT {
     // float staging tile for the coalesced trajectory store of the raw observations
     static constexpr int A1 = 0, A2A = 128 * K1 * 2, A2C = A2A + 128 * 128 * 2;
     static constexpr int OBS = A2C + 128 * 128 * 2;
-    static constexpr int TILE_BYTES = OBS + (K1 > 16 ? 128 * 21 * 4 : 0);
+    static constexpr int EPS = OBS + (K1 > 16 ? 128 * 21 * 4 : 0);      // PARTNER: 2 x [128] float4 sampling noise (double buffer)
+    static constexpr int TILE_BYTES = EPS + (PARTNER ? 2 * 128 * 16 : 0);
     static constexpr int TILE0 = WEND;
     __host__ __device__ static constexpr int f32_off(int tiles) { return TILE0 + tiles * TILE_BYTES; }   // fp32 constants, see below
     static constexpr int kB3 = 0 /*[32]*/, kLogStd = 32, kMean = 36, kInvStd = 60, kNumF = 84;
@@ -185,8 +192,13 @@ struct SmemT {
     __host__ __device__ static constexpr int total(int tiles) { return bar_off(tiles) + 8 * tiles + 16; }
 };
 
-template <int MODE, int DIST, int TILES>
-__global__ void __launch_bounds__(kM * TILES, 1)
+// PARTNER (one tile per CTA, 12-D modes): a second warpgroup shares the tile.  Warp w + 4 reads the same 32 TMEM lanes
+// as warp w, so the partners take the critic half of both epilogues (the owners keep the actor half), and while the
+// owners sample, step and reset their envs the partners draw the NEXT step's Gaussian noise (Philox + Box-Muller)
+// into a double-buffered shared array.  It shortens the per-step latency chain, which is all that matters when the
+// batch is too small to give an SM more than one tile.
+template <int MODE, int DIST, int TILES, bool PARTNER = false>
+__global__ void __launch_bounds__(kM * TILES * (PARTNER ? 2 : 1), 1)
 rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restrict__ state,
                          const float* __restrict__ params, int steps, uint32_t t0, int deterministic,
                          float bootstrap_gamma, RolloutBuffers rb, const float* __restrict__ first) {
@@ -196,15 +208,19 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     constexpr int kS1 = K1 / 16;                           // layer-1 K = 16 steps
     constexpr int kBiasStep = D / 16, kBiasK = D % 16;     // K step / slot (and slot + 1) that carry the constant 1
     static_assert(D + 2 <= K1 && kBiasK + 1 < 16, "bias slots must fit one K = 16 step");
-    using Smem = SmemT<K1>;
+    static_assert(!PARTNER || (TILES == 1 && D == 12), "partner warpgroup: one tile per CTA, 12-D observation");
+    using Smem = SmemT<K1, PARTNER>;
     constexpr int Ao = DIST == 1 ? 2 * kA : kA;
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr uint32_t kTmemCols = kTileCols * TILES;
     float* sF = reinterpret_cast<float*>(smem + Smem::f32_off(TILES));
-    constexpr int NT = kM * TILES;
+    constexpr int kTT = PARTNER ? 2 * kM : kM;             // threads per tile
+    constexpr int NT = kTT * TILES;
     const PolicyLayout L = policy_layout(D, DIST);
     const int gtid = threadIdx.x;                          // thread in the CTA (setup loops)
-    const int tile = gtid / kM, tid = gtid % kM, warp = tid >> 5;   // tile-local thread / warp: TMEM lane = tid
+    const int tile = gtid / kTT, ltid = gtid % kTT;
+    const int half = ltid / kM;                            // 0: owner warpgroup, 1: partner warpgroup
+    const int tid = ltid % kM, warp = tid >> 5;            // row of the tile = TMEM lane; lane-quadrant warp index
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES)) + tile;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::bar_off(TILES) + 8 * TILES);
     unsigned char* tsm = smem + Smem::TILE0 + tile * Smem::TILE_BYTES;   // this tile's A operands
@@ -257,7 +273,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     if (gtid == 0) sF[Smem::kB3 + 16] = params[L.cb3];
     if (DIST == 0 && gtid < kA) sF[Smem::kLogStd + gtid] = params[L.log_std + gtid];
     if (gtid < D) { sF[Smem::kMean + gtid] = params[L.mean + gtid]; sF[Smem::kInvStd + gtid] = params[L.inv_std + gtid]; }
-    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (ltid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (gtid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -277,8 +293,24 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     const uint64_t dA1b = make_desc(tbase + Smem::A1 + kBiasStep * 4096, 16 * 128, 128);   // the K step with the constant-1 slots
     uint32_t phase = 0;
 
-    const bool owner = (b0 + tid) < n;
+    const bool owner = half == 0 && (b0 + tid) < n;
     const uint32_t gid = P.env_id_offset + (uint32_t)(b0 + tid);
+    float4* sEps = reinterpret_cast<float4*>(tsm + Smem::EPS);           // PARTNER only
+    // standard-normal noise of (env gid, step index ts): Philox stream 1 + Box-Muller (fast intrinsics: the noise only
+    // has to be N(0,1) to ~1e-6, it is not a state variable)
+    auto draw_noise = [&](uint32_t ts) {
+        const U4 r = philox4x32_10(U4{gid, ts, 0u, STREAM_POLICY}, P.philox_key);
+        const float u0 = ((float)(r.x >> 8) + 1.0f) * 5.9604644775390625e-8f;
+        const float u1 = (float)(r.y >> 8) * 5.9604644775390625e-8f;
+        const float u2 = ((float)(r.z >> 8) + 1.0f) * 5.9604644775390625e-8f;
+        const float u3 = (float)(r.w >> 8) * 5.9604644775390625e-8f;
+        const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+        float s0, c0, s1, c1;
+        __sincosf(6.283185307179586f * u1, &s0, &c0);
+        __sincosf(6.283185307179586f * u3, &s1, &c1);
+        return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+    };
+    if (PARTNER && half == 1) sEps[tid] = draw_noise(t0);               // noise of the first step
     Env e;
     float obs_[D];
     if (owner) {
@@ -298,7 +330,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     // forward pass for the observation in `o`; returns head[Ao] and value
     auto forward = [&](const float* o, float* head, float& value) {
         // A1: normalised obs, bf16, K padded D -> K1 with a constant 1 in slots D and D + 1
-        {
+        if (half == 0) {
             float x[K1];
 #pragma unroll
             for (int k = 0; k < K1; ++k) x[k] = k < D ? (o[k] - sF[Smem::kMean + k]) * sF[Smem::kInvStd + k] : (k < D + 2 ? 1.0f : 0.f);
@@ -310,8 +342,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         fence_async_smem();
         fence_before();
-        tile_sync(tile);
-        if (tid == 0) {
+        tile_sync<kTT>(tile);
+        if (ltid == 0) {
             fence_after();
 #pragma unroll
             for (int j = 0; j < kS1; ++j)                                   // D1[128 x 256] = A1 . W1cat (+ b1)
@@ -323,9 +355,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
         QS_TCP(1);
-        // epilogue 1: h1 = relu(D1 + b1) -> bf16 A2A | A2C
+        // epilogue 1: h1 = relu(D1 + b1) -> bf16 A2A | A2C  (PARTNER: owners take the actor half, partners the critic half)
+        const int c_lo = PARTNER ? 4 * half : 0, c_hi = PARTNER ? 4 * half + 4 : 8;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
             float v[32];
             tmem_ld32(my_tmem + (uint32_t)(c * 32), v);
             const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
@@ -340,8 +373,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(2);
         fence_async_smem();
         fence_before();
-        tile_sync(tile);
-        if (tid == 0) {
+        tile_sync<kTT>(tile);
+        if (ltid == 0) {
             fence_after();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {                                   // K = 128 in 8 steps of 16 (2 chunks of 2048 B each)
@@ -363,7 +396,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(3);
         // epilogue 2: h2 = relu(D2) -> bf16, written over A2A | A2C (the L2 MMAs have completed; b2 is inside D2)
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
             float v[32];
             tmem_ld32(my_tmem + (uint32_t)(c * 32), v);
             const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
@@ -378,8 +411,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(4);
         fence_async_smem();
         fence_before();
-        tile_sync(tile);
-        if (tid == 0) {
+        tile_sync<kTT>(tile);
+        if (ltid == 0) {
             fence_after();
 #pragma unroll
             for (int j = 0; j < 8; ++j)                                     // heads: N = 16 (B rows/8 = 2 -> LBO 256 B, K step 512 B)
@@ -394,7 +427,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
         QS_TCP(5);
-        {
+        if (half == 0) {
             float v[32];
             tmem_ld32(my_tmem, v);
 #pragma unroll
@@ -419,10 +452,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             float* stage = reinterpret_cast<float*>(tsm + Smem::OBS);
 #pragma unroll
             for (int k = 0; k < D; ++k) stage[tid * D + k] = obs_[k];
-            tile_sync(tile);
+            tile_sync<kTT>(tile);
             const int rows = min(kM, n - b0);
             for (int idx = tid; idx < rows * D; idx += kM) dst_tile[idx] = stage[idx];
-            tile_sync(tile);                           // the staging tile is rewritten next step
+            tile_sync<kTT>(tile);                           // the staging tile is rewritten next step
         }
     };
 
@@ -438,20 +471,9 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         float tobs[D];
         bool need_boot = false;
         if (owner) {
-            const U4 r = philox4x32_10(U4{gid, t0 + (uint32_t)t, 0u, STREAM_POLICY}, P.philox_key);
-            float eps[4];
-            {
-                const float u0 = ((float)(r.x >> 8) + 1.0f) * 5.9604644775390625e-8f;
-                const float u1 = (float)(r.y >> 8) * 5.9604644775390625e-8f;
-                const float u2 = ((float)(r.z >> 8) + 1.0f) * 5.9604644775390625e-8f;
-                const float u3 = (float)(r.w >> 8) * 5.9604644775390625e-8f;
-                // fast intrinsics: the noise only has to be N(0,1) to ~1e-6, it is not a state variable
-                const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
-                float s0, c0, s1, c1;
-                __sincosf(6.283185307179586f * u1, &s0, &c0);
-                __sincosf(6.283185307179586f * u3, &s1, &c1);
-                eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
-            }
+            // PARTNER: the partner warpgroup drew this step's noise during the previous step
+            const float4 e4 = PARTNER ? sEps[(t & 1) * kM + tid] : draw_noise(t0 + (uint32_t)t);
+            const float eps[4] = {e4.x, e4.y, e4.z, e4.w};
             float raw[4], act[4], logp = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -477,11 +499,13 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             need_boot = bootstrap_gamma > 0.f && so.finished && so.truncated != 0.f && so.done == 0.f;
             if constexpr (ModeTraits<MODE>::kBrax) need_boot = bootstrap_gamma > 0.f && so.truncated != 0.f;
         }
+        if (PARTNER && half == 1 && t + 1 < steps)                         // next step's noise, off the owners' critical path
+            sEps[((t + 1) & 1) * kM + tid] = draw_noise(t0 + (uint32_t)(t + 1));
         QS_TCP(8);
         // Philox re-sampling of finished envs, compacted per tile.  The scratch lives in this tile's A2A buffer,
         // which is idle between the head MMAs of this step and the first epilogue of the next one.
         if constexpr (kGym) {
-          if (P.auto_reset == QS_RESET_RESAMPLE) {
+          if (P.auto_reset == QS_RESET_RESAMPLE && half == 0) {
             if (P.waypoint_mode) {
                 if (so.needs_reset) {
                     float rpy[3];
@@ -500,7 +524,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         QS_TCP(9);
         // SB3 timeout bootstrap: reward += gamma * V(terminal_obs) for truncated-not-terminated episodes
-        if (tile_or(tile, need_boot)) {
+        if (tile_or<kTT>(tile, need_boot)) {
             float h2[Ao], vt;
             forward(need_boot ? tobs : obs_, h2, vt);
             if (need_boot) so.reward = fmaf(bootstrap_gamma, vt, so.reward);
@@ -513,7 +537,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(10);
     }
 #ifdef QS_TC_PROFILE
-    if (blockIdx.x == 0 && (gtid == 0 || gtid == NT - 1))
+    if (blockIdx.x == 0 && (gtid == 0 || gtid == kM - 1))
         printf("tcprof tid %d steps %d: A1+sync %lld | L1wait %lld | epi1 %lld | L2 sync+wait %lld | epi2 %lld | L3 sync+wait %lld | head %lld | sample %lld | env %lld | reset %lld | boot+store %lld | obs store %lld (cycles/step)\n",
                gtid, steps, prof_[0] / steps, prof_[1] / steps, prof_[2] / steps, prof_[3] / steps, prof_[4] / steps, prof_[5] / steps,
                prof_[6] / steps, prof_[7] / steps, prof_[8] / steps, prof_[9] / steps, prof_[10] / steps, prof_[11] / steps);
@@ -536,15 +560,15 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     }
 }
 
-template <int MODE, int DIST, int TILES>
+template <int MODE, int DIST, int TILES, bool PARTNER = false>
 inline int launch_rollout_tc_tt(const QsParams& P, const Tables& T, int n, float* state, const float* params, int steps,
                                 uint32_t t0, const RolloutOpts& opt, const RolloutBuffers& rb, const float* first,
                                 cudaStream_t s) {
-    auto kern = rollout_policy_tc_kernel<MODE, DIST, TILES>;
-    using Smem = SmemT<(ModeTraits<MODE>::kObsDim + 2 <= 16) ? 16 : 32>;
+    auto kern = rollout_policy_tc_kernel<MODE, DIST, TILES, PARTNER>;
+    using Smem = SmemT<(ModeTraits<MODE>::kObsDim + 2 <= 16) ? 16 : 32, PARTNER>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total(TILES));
     if (ce != cudaSuccess) return (int)ce;
-    kern<<<(n + kM * TILES - 1) / (kM * TILES), kM * TILES, Smem::total(TILES), s>>>(
+    kern<<<(n + kM * TILES - 1) / (kM * TILES), kM * TILES * (PARTNER ? 2 : 1), Smem::total(TILES), s>>>(
         P, T, n, state, params, steps, t0, opt.deterministic, opt.bootstrap_gamma, rb, first);
     return 0;
 }
@@ -557,6 +581,10 @@ inline int launch_rollout_tc_t(const QsParams& P, const Tables& T, int n, float*
     // staging tile) do not fit two tiles into 227 KB of shared memory
     if constexpr (ModeTraits<MODE>::kObsDim == 12) {
         if (n >= 148 * 2 * kM) return launch_rollout_tc_tt<MODE, DIST, 2>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+#if QS_TC_PARTNER
+        // small batches: one tile per CTA plus a partner warpgroup that shortens the per-step latency chain
+        return launch_rollout_tc_tt<MODE, DIST, 1, true>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+#endif
     }
     return launch_rollout_tc_tt<MODE, DIST, 1>(P, T, n, state, params, steps, t0, opt, rb, first, s);
 }

@@ -28,6 +28,13 @@
 #include "qs_math.cuh"
 #include "../../include/quadsim_abi.h"
 
+#ifndef QS_ROTOR_UNROLL
+#define QS_ROTOR_UNROLL 4      /* unroll factor of the four-rotor drag loop; 1 or 2 cost 19 % of the step kernel's speed:
+                                   the four independent rotors are the ILP that hides the FP32 latency at 7 warps/scheduler */
+#endif
+#define QS_PRAGMA_(x) _Pragma(#x)
+#define QS_UNROLL_(n) QS_PRAGMA_(unroll n)
+
 namespace qs {
 
 struct Body {
@@ -102,7 +109,7 @@ QS_HD void physics_step(const QsParams& P, Body& b, const float ctrl[4]) {
 
     // ---- fluid, rotors: the box frame spins with theta_k --------------------------------
     float th_[4];   // hinge torque tau'_k
-#pragma unroll
+    QS_UNROLL_(QS_ROTOR_UNROLL)
     for (int k = 0; k < 4; ++k) {
         float sn, cs;
         sincos_fast_(b.th[k], &sn, &cs);

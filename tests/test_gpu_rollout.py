@@ -261,9 +261,11 @@ def test_rollout_tensor_core_path_21d(mode, B, T):
     if T > 4:
         was_done = b["done"][3] == 1
         np.testing.assert_array_equal(b["obs"][4][was_done], b["obs"][0][was_done])
-    if mode == "mjx_brax":       # (the fp32 FMA kernel is not instantiated for hover_brax)
-        # against the fp32 FMA kernel from the same start: identical first observation, same flags on step 0
-        buf2 = eng.rollout_policy(st0, d_params, T=1, t0=11, dist=1, first_state=first)
-        np.testing.assert_array_equal(buf2["obs"][0].cpu().numpy(), b["obs"][0])
-        np.testing.assert_array_equal(buf2["done"][0].cpu().numpy(), b["done"][0])
-        assert np.abs(buf2["value"][0].cpu().numpy() - b["value"][0]).max() < 0.1
+    # against the fp32 FMA kernel from the same start: identical first observation, same flags on step 0
+    buf2 = eng.rollout_policy(st0, d_params, T=1, t0=11, dist=1, first_state=first)
+    np.testing.assert_array_equal(buf2["obs"][0].cpu().numpy(), b["obs"][0])
+    np.testing.assert_array_equal(buf2["done"][0].cpu().numpy(), b["done"][0])
+    assert np.abs(buf2["value"][0].cpu().numpy() - b["value"][0]).max() < 0.1
+    # and the FMA path's own numbers against the exact fp32 oracle forward
+    head32, value32 = ppo_ref.forward(pp, b["obs"][0])
+    assert_close(buf2["value"][0].cpu().numpy(), value32, rtol=2e-4, atol=2e-4, what="value (fp32 FMA, 21-D)")

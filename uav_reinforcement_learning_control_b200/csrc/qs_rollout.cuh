@@ -48,6 +48,23 @@ __host__ __device__ inline PolicyLayout policy_layout(int D, int dist) {
 
 inline int policy_param_count(const QsPolicyDesc& d) { return policy_layout(d.obs_dim, d.dist).total; }
 
+#ifndef QS_FMA_PACKED
+#define QS_FMA_PACKED 1
+#endif
+__device__ __forceinline__ unsigned long long pack2_(float lo, float hi) {
+    unsigned long long p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(lo), "f"(hi));
+    return p;
+}
+__device__ __forceinline__ void unpack2_(unsigned long long p, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+__device__ __forceinline__ unsigned long long fma2_(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // ------------------------------------------------------------------------------------------
 // [E x K] x [K x 128] register-tiled layer.  in: sIn[K][ES] (transposed activations), W[K][128],
 // out: sOut[128][ES] = relu(in W + b).  ES = E + 4 (16 B aligned rows, conflict-light stores).
@@ -62,6 +79,37 @@ __device__ __forceinline__ void dense_relu(const float* __restrict__ sIn, int K,
     const int we = warp % kWarpsE, wn = warp / kWarpsE;   // wn in {0,1}: 64-column half
     const int e0 = we * 16 + (lane & 3) * 4;
     const int c0 = wn * 64 + (lane >> 2) * 4;
+#if QS_FMA_PACKED && defined(__CUDA_ARCH__)
+    // Blackwell packed fp32 (fma.rn.f32x2, SASS FFMA2): one instruction = two FMAs on adjacent output columns.  The
+    // weight pairs come packed out of the 128-bit shared loads; only the activation is duplicated into both halves.
+    unsigned long long acc2[4][4];
+    {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + c0);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc2[i][0] = pack2_(b0.x, b0.y); acc2[i][1] = pack2_(b0.z, b0.w);
+            acc2[i][2] = pack2_(b1.x, b1.y); acc2[i][3] = pack2_(b1.z, b1.w);
+        }
+    }
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(sIn + k * ES + e0);
+        const float4 w0 = *reinterpret_cast<const float4*>(W + k * kH + c0);
+        const float4 w1 = *reinterpret_cast<const float4*>(W + k * kH + c0 + 32);
+        const unsigned long long wp[4] = {pack2_(w0.x, w0.y), pack2_(w0.z, w0.w), pack2_(w1.x, w1.y), pack2_(w1.z, w1.w)};
+        const unsigned long long ap[4] = {pack2_(a.x, a.x), pack2_(a.y, a.y), pack2_(a.z, a.z), pack2_(a.w, a.w)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc2[i][j] = fma2_(ap[i], wp[j], acc2[i][j]);
+    }
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) unpack2_(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
+#else
     float acc[4][8];
     {
         const float4 b0 = *reinterpret_cast<const float4*>(bias + c0);
@@ -84,6 +132,7 @@ __device__ __forceinline__ void dense_relu(const float* __restrict__ sIn, int K,
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
     }
+#endif
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = c0 + (j & 3) + (j >> 2) * 32;
@@ -331,6 +380,8 @@ inline int launch_rollout_policy(const QsParams& P, const Tables& T, int n, floa
         return launch_rollout_t<QS_MODE_MJX_BRAX, 1, 32>(P, T, n, state, params, steps, t0, opt, rb, first, s);
     if (P.mode == QS_MODE_MJX_BRAX && d.dist == 0)
         return launch_rollout_t<QS_MODE_MJX_BRAX, 0, 32>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+    if (P.mode == QS_MODE_HOVER_BRAX && d.dist == 1)          // QuadHoverBraxEnv under the Brax trainer (train_brax_ppo.py:39-176)
+        return launch_rollout_t<QS_MODE_HOVER_BRAX, 1, 32>(P, T, n, state, params, steps, t0, opt, rb, first, s);
     return -100;
 }
 

@@ -284,10 +284,26 @@ def main():
     e1.record(stream)
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    # what bounds it: the D2H of obs / reward / done.  Measure the plain pinned D2H copy rate of this box for the same
+    # number of bytes (one cudaMemcpyAsync, all ranks at once, like the e2e loop) so the PCIe fraction is explicit.
+    d_probe = torch.empty((48 + 8) * n // 4, dtype=torch.float32, device=dev)
+    h_probe = torch.empty((48 + 8) * n // 4, dtype=torch.float32).pin_memory()
+    h_probe.copy_(d_probe, non_blocking=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(5):
+        h_probe.copy_(d_probe, non_blocking=True)
+    e1.record(stream)
+    barrier()
+    ms_probe = max_over_ranks(e0.elapsed_time(e1)) / 5
+    pcie_d2h_peak = (48 + 8) * n / (ms_probe * 1e-3) / 1e9
+    del d_probe, h_probe
     e2e = {"value": world * n * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 * n,
            "d2h_bytes_per_step": (48 + 8) * n, "steps": Ke, "ms_per_step": ms_e2e / Ke,
            "pcie_d2h_gbs_per_gpu": (48 + 8) * n * Ke / (ms_e2e * 1e-3) / 1e9,      # what bounds it: obs/reward/done over PCIe
            "pcie_h2d_gbs_per_gpu": 16 * n * Ke / (ms_e2e * 1e-3) / 1e9,
+           "pcie_d2h_copy_peak_gbs_per_gpu": pcie_d2h_peak,                       # measured: same bytes, one plain pinned copy
+           "pcie_frac": ((48 + 8) * n * Ke / (ms_e2e * 1e-3) / 1e9) / pcie_d2h_peak,
            "api": "qs_step_host (C ABI, pinned host buffers; what HoverVecEnv.step(numpy) calls)"}
 
     line = {

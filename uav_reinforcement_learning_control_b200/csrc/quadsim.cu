@@ -2,6 +2,7 @@
 // Built for sm_100a only; there is no CPU code path behind any of these calls.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <new>
@@ -37,6 +38,10 @@ inline int nblocks(int n, int block) { return (n + block - 1) / block; }
 
 }  // namespace
 
+#ifndef QS_HOST_STREAMS
+#define QS_HOST_STREAMS 5
+#endif
+
 struct QsEngine {
     QsParams P;
     int32_t n;
@@ -46,8 +51,8 @@ struct QsEngine {
     float* scratch;         // device staging for qs_step_host: action | obs | reward | done
     int pf_grid;            // persistent grid of the prefetching step kernel (SMs x resident CTAs)
     int pp_grid;            // persistent grid of the TMA-pipelined step kernel (SMs x resident CTAs)
-    cudaStream_t hs[2];     // qs_step_host: two copy/compute streams (H2D of chunk k+1 under D2H of chunk k)
-    cudaEvent_t hev[3];
+    cudaStream_t hs[QS_HOST_STREAMS];     // qs_step_host: copy/compute streams (H2D + kernel of later chunks under the D2H of earlier ones)
+    cudaEvent_t hev[QS_HOST_STREAMS + 1];
     qs::Tables tables() const { return qs::Tables{target_table, waypoints}; }
 };
 
@@ -102,7 +107,8 @@ int qs_create(const QsParams* params, int32_t num_envs, int32_t device, const fl
     QsEngine* e = new (std::nothrow) QsEngine();
     if (!e) return fail(QS_ENOMEM, "qs_create: host allocation failed");
     e->P = P; e->n = num_envs; e->device = device; e->target_table = nullptr; e->waypoints = nullptr; e->scratch = nullptr;
-    e->hs[0] = e->hs[1] = nullptr; e->hev[0] = e->hev[1] = e->hev[2] = nullptr;
+    for (int k = 0; k < QS_HOST_STREAMS; ++k) e->hs[k] = nullptr;
+    for (int k = 0; k <= QS_HOST_STREAMS; ++k) e->hev[k] = nullptr;
     if (table) {
         const size_t bytes = (size_t)P.max_episode_steps * 3 * sizeof(float);
         if (cudaMalloc(&e->target_table, bytes) != cudaSuccess) { delete e; return fail(QS_ENOMEM, "cudaMalloc target table"); }
@@ -140,8 +146,8 @@ int qs_destroy(QsHandle h) {
     if (!h) return QS_OK;
     cudaSetDevice(h->device);
     cudaFree(h->target_table); cudaFree(h->waypoints); cudaFree(h->scratch);
-    for (int k = 0; k < 2; ++k) if (h->hs[k]) cudaStreamDestroy(h->hs[k]);
-    for (int k = 0; k < 3; ++k) if (h->hev[k]) cudaEventDestroy(h->hev[k]);
+    for (int k = 0; k < QS_HOST_STREAMS; ++k) if (h->hs[k]) cudaStreamDestroy(h->hs[k]);
+    for (int k = 0; k <= QS_HOST_STREAMS; ++k) if (h->hev[k]) cudaEventDestroy(h->hev[k]);
     delete h;
     return QS_OK;
 }
@@ -294,32 +300,54 @@ int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_
     const size_t n = (size_t)h->n, D = (size_t)h->P.obs_dim;
     if (!h->scratch) {
         QS_CUDA(cudaMalloc(&h->scratch, n * (4 + D + 2) * sizeof(float)));
-        for (int k = 0; k < 2; ++k) QS_CUDA(cudaStreamCreateWithFlags(&h->hs[k], cudaStreamNonBlocking));
-        for (int k = 0; k < 3; ++k) QS_CUDA(cudaEventCreateWithFlags(&h->hev[k], cudaEventDisableTiming));
+        for (int k = 0; k < QS_HOST_STREAMS; ++k) QS_CUDA(cudaStreamCreateWithFlags(&h->hs[k], cudaStreamNonBlocking));
+        for (int k = 0; k <= QS_HOST_STREAMS; ++k) QS_CUDA(cudaEventCreateWithFlags(&h->hev[k], cudaEventDisableTiming));
     }
     float* d_act = h->scratch; float* d_obs = d_act + 4 * n; float* d_rew = d_obs + D * n; float* d_done = d_rew + n;
     // Chunked, double-streamed: PCIe is full duplex, so the H2D of chunk k+1 and the kernel of chunk k+1 run under the
-    // D2H of chunk k.  Chunks are multiples of the block size; small batches go through as one chunk.
-    const int chunks = n >= (size_t)1 << 17 ? 8 : 1;
-    const size_t per = ((n + chunks - 1) / chunks + qs::kBlock - 1) / qs::kBlock * qs::kBlock;
+    // D2H of chunk k.  The D2H of the observations (48 of the 56 bytes per env) is what bounds the call, so the schedule
+    // is built around keeping that copy engine busy: geometrically growing chunks (1/16, 1/16, 1/8, 1/4, 1/2 of the
+    // batch) start the first D2H after ~20 us instead of ~90 us and keep the number of copies -- each costs ~4.6 us of
+    // set-up on this platform -- small; reward and done leave in one copy each at the end.  Chunk boundaries are
+    // multiples of the block size; small batches go through as one chunk.
+    static const int chunks_env = getenv("QS_HOST_CHUNKS") ? atoi(getenv("QS_HOST_CHUNKS")) : 0;   // tuning override: equal chunks
+    size_t bounds[34];
+    int chunks = 0;
+    bounds[0] = 0;
+    if (chunks_env > 0 || n < ((size_t)1 << 17)) {
+        chunks = chunks_env > 0 ? (chunks_env > 32 ? 32 : chunks_env) : 1;
+        const size_t per = ((n + chunks - 1) / chunks + qs::kBlock - 1) / qs::kBlock * qs::kBlock;
+        for (int c = 1; c <= chunks; ++c) bounds[c] = (size_t)c * per < n ? (size_t)c * per : n;
+    } else {
+        const size_t unit = (n / 16 + qs::kBlock - 1) / qs::kBlock * qs::kBlock;
+        const int mult[5] = {1, 2, 4, 8, 16};
+        chunks = 5;
+        for (int c = 1; c <= chunks; ++c) bounds[c] = unit * mult[c - 1] < n ? unit * mult[c - 1] : n;
+        bounds[chunks] = n;
+    }
     QS_CUDA(cudaEventRecord(h->hev[0], s));                       // state is ready when the caller's stream gets here
-    for (int k = 0; k < 2; ++k) QS_CUDA(cudaStreamWaitEvent(h->hs[k], h->hev[0], 0));
+    for (int k = 0; k < QS_HOST_STREAMS; ++k) QS_CUDA(cudaStreamWaitEvent(h->hs[k], h->hev[0], 0));
+    // one stream per chunk (round robin): nothing of chunk k+1 queues behind the D2H of chunk k, the copy engines see
+    // every H2D / D2H as soon as its own producer is done
     for (int c = 0; c < chunks; ++c) {
-        const size_t lo = (size_t)c * per;
-        if (lo >= n) break;
-        const size_t cnt = (lo + per <= n) ? per : n - lo;
-        cudaStream_t cs = h->hs[c & 1];
+        const size_t lo = bounds[c];
+        if (lo >= n || bounds[c + 1] <= lo) continue;
+        const size_t cnt = bounds[c + 1] - lo;
+        cudaStream_t cs = h->hs[c % QS_HOST_STREAMS];
         QS_CUDA(cudaMemcpyAsync(d_act + 4 * lo, action_host + 4 * lo, 4 * cnt * sizeof(float), cudaMemcpyHostToDevice, cs));
         int rc = launch_step(h, (int)lo, (int)cnt, state, d_act, d_obs, d_rew, d_done, nullptr, nullptr, nullptr, nullptr, cs);
         if (rc != QS_OK) return rc;
         QS_CUDA(cudaMemcpyAsync(obs_host + D * lo, d_obs + D * lo, D * cnt * sizeof(float), cudaMemcpyDeviceToHost, cs));
-        QS_CUDA(cudaMemcpyAsync(reward_host + lo, d_rew + lo, cnt * sizeof(float), cudaMemcpyDeviceToHost, cs));
-        QS_CUDA(cudaMemcpyAsync(done_host + lo, d_done + lo, cnt * sizeof(float), cudaMemcpyDeviceToHost, cs));
     }
-    for (int k = 0; k < 2; ++k) {
+    // reward / done: one copy each on stream 0, after every stream's last kernel (d_rew and d_done are adjacent)
+    for (int k = 1; k < QS_HOST_STREAMS; ++k) {
         QS_CUDA(cudaEventRecord(h->hev[1 + k], h->hs[k]));
-        QS_CUDA(cudaStreamWaitEvent(s, h->hev[1 + k], 0));        // later work on the caller's stream sees the new state
+        QS_CUDA(cudaStreamWaitEvent(h->hs[0], h->hev[1 + k], 0));
     }
+    QS_CUDA(cudaMemcpyAsync(reward_host, d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
+    QS_CUDA(cudaMemcpyAsync(done_host, d_done, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
+    QS_CUDA(cudaEventRecord(h->hev[1], h->hs[0]));
+    QS_CUDA(cudaStreamWaitEvent(s, h->hev[1], 0));                // later work on the caller's stream sees the new state
     QS_CUDA(cudaStreamSynchronize(s));
     return QS_OK;
 }

@@ -184,7 +184,10 @@ struct SmemT {
     static constexpr int A1 = 0, A2A = 128 * K1 * 2, A2C = A2A + 128 * 128 * 2;
     static constexpr int OBS = A2C + 128 * 128 * 2;
     static constexpr int EPS = OBS + (K1 > 16 ? 128 * 21 * 4 : 0);      // PARTNER: 2 x [128] float4 sampling noise (double buffer)
-    static constexpr int TILE_BYTES = EPS + (PARTNER ? 2 * 128 * 16 : 0);
+    static constexpr int CAND = EPS + (PARTNER ? 2 * 128 * 16 : 0);     // PARTNER: speculative reset candidates [128][28] float + episode mailbox [128] u32
+    static constexpr int kCandF = 28;                                   // p3 q4 v3 w3 target3 obs12
+    static constexpr int EPI = CAND + (PARTNER ? 128 * kCandF * 4 : 0);
+    static constexpr int TILE_BYTES = EPI + (PARTNER ? 128 * 4 : 0);
     static constexpr int TILE0 = WEND;
     __host__ __device__ static constexpr int f32_off(int tiles) { return TILE0 + tiles * TILE_BYTES; }   // fp32 constants, see below
     static constexpr int kB3 = 0 /*[32]*/, kLogStd = 32, kMean = 36, kInvStd = 60, kNumF = 84;
@@ -311,6 +314,12 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
     };
     if (PARTNER && half == 1) sEps[tid] = draw_noise(t0);               // noise of the first step
+    // PARTNER, gym modes with Philox re-sampling: the partners also compute, every step and for every env, the state
+    // the env WOULD be reset to (episode + 1) while the owners step their envs; a finished env then just picks its
+    // candidate up from shared memory instead of running the ~310-instruction reset on the owners' critical path.
+    float* sCand = reinterpret_cast<float*>(tsm + Smem::CAND);
+    uint32_t* sEpi = reinterpret_cast<uint32_t*>(tsm + Smem::EPI);
+    const bool spec_reset = PARTNER && kGym && P.auto_reset == QS_RESET_RESAMPLE && !P.waypoint_mode;   // CTA-uniform
     Env e;
     float obs_[D];
     if (owner) {
@@ -322,6 +331,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
 #pragma unroll
         for (int k = 0; k < D; ++k) obs_[k] = 0.f;
     }
+    if (spec_reset && half == 0) sEpi[tid] = owner ? e.episode : 0u;     // visible to the partners after the first tile barrier
 
 #ifdef QS_TC_PROFILE
     long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -501,11 +511,50 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         if (PARTNER && half == 1 && t + 1 < steps)                         // next step's noise, off the owners' critical path
             sEps[((t + 1) & 1) * kM + tid] = draw_noise(t0 + (uint32_t)(t + 1));
+        if constexpr (PARTNER && kGym) {
+            if (spec_reset) {
+                if (half == 1) {
+                    // speculative reset of env `tid` for its next episode (all 128 lanes busy, no divergence)
+                    Env r;
+                    r.episode = sEpi[tid] + 1u;
+                    r.wp_idx = 0; r.wp_reached = 0; r.laps = 0;
+                    float rpy[3], o[D];
+                    reset_env<MODE>(P, T, gid, r, rpy);
+                    compute_obs<MODE>(P, r, rpy, o);
+                    float4* d = reinterpret_cast<float4*>(sCand + tid * Smem::kCandF);
+                    d[0] = make_float4(r.b.p[0], r.b.p[1], r.b.p[2], r.b.q[0]);
+                    d[1] = make_float4(r.b.q[1], r.b.q[2], r.b.q[3], r.b.v[0]);
+                    d[2] = make_float4(r.b.v[1], r.b.v[2], r.b.w[0], r.b.w[1]);
+                    d[3] = make_float4(r.b.w[2], r.target[0], r.target[1], r.target[2]);
+                    d[4] = make_float4(o[0], o[1], o[2], o[3]);
+                    d[5] = make_float4(o[4], o[5], o[6], o[7]);
+                    d[6] = make_float4(o[8], o[9], o[10], o[11]);
+                }
+                tile_sync<kTT>(tile);                                      // candidates of this step are in place
+                if (so.needs_reset) {                                      // (owners only; e.episode was advanced by env_step)
+                    const float4* d = reinterpret_cast<const float4*>(sCand + tid * Smem::kCandF);
+                    const float4 c0 = d[0], c1 = d[1], c2 = d[2], c3 = d[3], c4 = d[4], c5 = d[5], c6 = d[6];
+                    e.b.p[0] = c0.x; e.b.p[1] = c0.y; e.b.p[2] = c0.z; e.b.q[0] = c0.w;
+                    e.b.q[1] = c1.x; e.b.q[2] = c1.y; e.b.q[3] = c1.z; e.b.v[0] = c1.w;
+                    e.b.v[1] = c2.x; e.b.v[2] = c2.y; e.b.w[0] = c2.z; e.b.w[1] = c2.w;
+                    e.b.w[2] = c3.x; e.target[0] = c3.y; e.target[1] = c3.z; e.target[2] = c3.w;
+                    obs_[0] = c4.x; obs_[1] = c4.y; obs_[2] = c4.z; obs_[3] = c4.w;
+                    obs_[4] = c5.x; obs_[5] = c5.y; obs_[6] = c5.z; obs_[7] = c5.w;
+                    obs_[8] = c6.x; obs_[9] = c6.y; obs_[10] = c6.z; obs_[11] = c6.w;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { e.b.th[k] = 0.f; e.b.s[k] = 0.f; e.prev_action[k] = 0.f; }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) e.rate_int[k] = 0.f;
+                    e.step_count = 0; e.ep_steps = 0; e.done_prev = 0.f; e.voltage = P.v_nominal;
+                    sEpi[tid] = e.episode;                                 // read by the partner next step (3+ barriers later)
+                }
+            }
+        }
         QS_TCP(8);
         // Philox re-sampling of finished envs, compacted per tile.  The scratch lives in this tile's A2A buffer,
         // which is idle between the head MMAs of this step and the first epilogue of the next one.
         if constexpr (kGym) {
-          if (P.auto_reset == QS_RESET_RESAMPLE && half == 0) {
+          if (P.auto_reset == QS_RESET_RESAMPLE && half == 0 && !spec_reset) {
             if (P.waypoint_mode) {
                 if (so.needs_reset) {
                     float rpy[3];

@@ -217,6 +217,19 @@ rollout_policy_kernel(const __grid_constant__ QsParams P, Tables T, int n, float
 #pragma unroll
         for (int k = 0; k < D; ++k) obs_[k] = 0.f;
     }
+    // Speculative resets (gym modes with Philox re-sampling).  During the env step only the first E threads of the CTA
+    // have work, so threads E..2E-1 compute, for env (tid - E), the state it WOULD be reset to for its next episode
+    // -- all lanes busy, off the owners' critical path -- into the idle sH1 buffer; a finished env picks its candidate
+    // up after the barrier that follows the env step.  The partner tracks the env's episode counter itself and learns
+    // of a reset through a flag word next to the candidates.
+    constexpr bool kGymMode = ModeTraits<MODE>::kGym;
+    const bool spec_reset = kGymMode && P.auto_reset == QS_RESET_RESAMPLE && !P.waypoint_mode;    // CTA-uniform
+    const bool partner = spec_reset && tid >= E && tid < 2 * E && (b0 + tid - E) < n;
+    constexpr int kCandF = 28;                                   // p3 q4 v3 w3 target3 obs12
+    float* sCand = sH1;                                          // [E][kCandF]
+    uint32_t* sFlag = reinterpret_cast<uint32_t*>(sH1 + E * kCandF);   // [E]
+    uint32_t p_epi = 0u;
+    if (partner) p_epi = f2u_(state[26 * (size_t)n + b0 + tid - E]);
     __syncthreads();
 
     auto publish_obs = [&](const float* o) {
@@ -301,12 +314,61 @@ rollout_policy_kernel(const __grid_constant__ QsParams P, Tables T, int n, float
             if (rb.act) reinterpret_cast<float4*>(rb.act)[o] = make_float4(raw[0], raw[1], raw[2], raw[3]);
             if (rb.logp) rb.logp[o] = logp;
             if (rb.value) rb.value[o] = sVal[tid];
-            env_step<MODE>(P, T, gid, e, act, obs_, tobs, first ? first + b0 + tid : nullptr, n, so);
+            so.needs_reset = false;
+            env_step<MODE, kGymMode>(P, T, gid, e, act, obs_, tobs, first ? first + b0 + tid : nullptr, n, so);
             need_boot = bootstrap_gamma > 0.f && so.finished && so.truncated != 0.f && so.done == 0.f;
             if constexpr (ModeTraits<MODE>::kBrax) need_boot = bootstrap_gamma > 0.f && so.truncated != 0.f;
+            if constexpr (kGymMode) {
+                if (spec_reset) {
+                    sFlag[tid] = so.needs_reset ? 1u : 0u;
+                } else if (so.needs_reset) {                  // waypoint resets draw nothing: inline
+                    float rpy[3];
+                    reset_env<MODE>(P, T, gid, e, rpy);
+                    compute_obs<MODE>(P, e, rpy, obs_);
+                }
+            }
+        } else if (partner) {
+            if constexpr (kGymMode) {
+                Env r;
+                r.episode = p_epi + 1u;
+                r.wp_idx = 0; r.wp_reached = 0; r.laps = 0;
+                float rpy[3], oc[D];
+                reset_env<MODE>(P, T, P.env_id_offset + (uint32_t)(b0 + tid - E), r, rpy);
+                compute_obs<MODE>(P, r, rpy, oc);
+                float4* d = reinterpret_cast<float4*>(sCand + (tid - E) * kCandF);
+                d[0] = make_float4(r.b.p[0], r.b.p[1], r.b.p[2], r.b.q[0]);
+                d[1] = make_float4(r.b.q[1], r.b.q[2], r.b.q[3], r.b.v[0]);
+                d[2] = make_float4(r.b.v[1], r.b.v[2], r.b.w[0], r.b.w[1]);
+                d[3] = make_float4(r.b.w[2], r.target[0], r.target[1], r.target[2]);
+                d[4] = make_float4(oc[0], oc[1], oc[2], oc[3]);
+                d[5] = make_float4(oc[4], oc[5], oc[6], oc[7]);
+                d[6] = make_float4(oc[8], oc[9], oc[10], oc[11]);
+            }
+        }
+        const int boot_any = __syncthreads_or(need_boot ? 1 : 0);
+        if constexpr (kGymMode) {
+            if (spec_reset) {
+                if (owner && so.needs_reset) {                // e.episode was advanced by env_step
+                    const float4* d = reinterpret_cast<const float4*>(sCand + tid * kCandF);
+                    const float4 c0 = d[0], c1 = d[1], c2 = d[2], c3 = d[3], c4 = d[4], c5 = d[5], c6 = d[6];
+                    e.b.p[0] = c0.x; e.b.p[1] = c0.y; e.b.p[2] = c0.z; e.b.q[0] = c0.w;
+                    e.b.q[1] = c1.x; e.b.q[2] = c1.y; e.b.q[3] = c1.z; e.b.v[0] = c1.w;
+                    e.b.v[1] = c2.x; e.b.v[2] = c2.y; e.b.w[0] = c2.z; e.b.w[1] = c2.w;
+                    e.b.w[2] = c3.x; e.target[0] = c3.y; e.target[1] = c3.z; e.target[2] = c3.w;
+                    obs_[0] = c4.x; obs_[1] = c4.y; obs_[2] = c4.z; obs_[3] = c4.w;
+                    obs_[4] = c5.x; obs_[5] = c5.y; obs_[6] = c5.z; obs_[7] = c5.w;
+                    obs_[8] = c6.x; obs_[9] = c6.y; obs_[10] = c6.z; obs_[11] = c6.w;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { e.b.th[k] = 0.f; e.b.s[k] = 0.f; e.prev_action[k] = 0.f; }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) e.rate_int[k] = 0.f;
+                    e.step_count = 0; e.ep_steps = 0; e.done_prev = 0.f; e.voltage = P.v_nominal;
+                }
+                if (partner && sFlag[tid - E]) p_epi += 1u;
+            }
         }
         // SB3 timeout bootstrap: reward += gamma * V(terminal_obs) for truncated-not-terminated episodes
-        if (__syncthreads_or(need_boot ? 1 : 0)) {
+        if (boot_any) {
             publish_obs(need_boot ? tobs : obs_);
             __syncthreads();
             critic();

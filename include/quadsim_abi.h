@@ -250,6 +250,32 @@ int qs_gae(int32_t T, int32_t B, const float* reward, const float* value, const 
            float* adv, float* ret, void* stream);
 
 /*
+ * PPO update on device.  Replaces the caller of the rollout, SB3 ``PPO.train`` as configured by
+ * train.py:50-68 (MlpPolicy pi=[128,128] vf=[128,128] ReLU, Adam eps 1e-5, clip_range, ent_coef, vf_coef, max_grad_norm,
+ * per-minibatch advantage normalisation).  Covers the SB3 policy (obs_dim 12, dist 0); handle-free like qs_gae, runs on
+ * the current device.  All pointers are device memory except the scalars.
+ *
+ * qs_ppo_grad: gradient of   -mean(min(r A, clip(r, 1-c, 1+c) A)) + vf_coef mean((ret - V)^2) - ent_coef H(pi)
+ * over the minibatch rows idx[0..n) (idx == NULL: rows 0..n-1) of the rollout buffers obs [N][12], act [N][4] (raw
+ * Gaussian samples), old_logp / adv / ret [N].  Forward and backward GEMMs run on tcgen05 (bf16 operands, fp32 TMEM
+ * accumulation).  grad receives qs_policy_param_count floats in the packed layout (zeros for obs_mean / obs_inv_std)
+ * followed by 8 statistics: sum policy loss, sum value loss, clipped samples, sum approx-KL, samples, 0, 0, 0.
+ * workspace: qs_ppo_workspace_bytes(desc) bytes, zero-filled once by the caller before the first call.
+ *
+ * qs_ppo_adam: params -= Adam(clip_by_global_norm(grad * grad_scale, max_grad_norm)) on the trained part of the packed
+ * vector (torch.optim.Adam and torch.nn.utils.clip_grad_norm_ semantics; max_grad_norm <= 0: no clipping).  `step` is
+ * the 1-based optimiser step; grad_scale = 1 / world_size after a sum all-reduce.  norm_out (optional): pre-clip norm.
+ */
+int64_t qs_ppo_workspace_bytes(const QsPolicyDesc* desc);
+int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const float* obs, const float* act,
+                const float* old_logp, const float* adv, const float* ret, const int32_t* idx, int32_t n,
+                float clip_range, float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad,
+                void* stream);
+int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* grad, float* m, float* v, int32_t step,
+                float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, float* norm_out,
+                void* stream);
+
+/*
  * qs_traj_info: TrajectoryFollowEnv's info["target" | "target_vel" | "target_acc"] (envs/trajectory_follow_env.py:
  * 162-168 in step, :245-250 in reset), out9 [B][9] float32 = pos(3) | vel(3) | acc(3) of each env's natural-cubic-
  * spline reference (:176-218).  Nothing is stored per env: the spline of an episode is re-derived from the Philox

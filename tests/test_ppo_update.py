@@ -1,0 +1,251 @@
+"""PPO minibatch update: the hand-derived oracle against torch autograd / torch.optim.Adam (CPU), and the
+sm_100a kernels (qs_ppo_grad: tcgen05 forward + backward, qs_ppo_adam) against the oracle (GPU)."""
+import numpy as np
+import pytest
+
+from oracle import ppo_ref, ppo_update_ref as U
+
+CLIP, VF, ENT = 0.1915, 0.5, 9.1e-5          # train.py:53-60
+
+
+def _policy(seed, obs_dim=12):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for out in (4, 1):
+        for (i, o) in ((obs_dim, 128), (128, 128), (128, out)):
+            lim = (3.0 / i) ** 0.5
+            parts += [rng.uniform(-lim, lim, i * o), rng.uniform(-0.1, 0.1, o)]
+    parts.append(rng.uniform(-1.0, -0.3, 4))
+    parts += [rng.uniform(-0.2, 0.2, obs_dim), rng.uniform(0.5, 1.5, obs_dim)]
+    p = np.concatenate(parts).astype(np.float32)
+    assert p.size == ppo_ref.param_count(obs_dim, 0)
+    return p
+
+
+def _batch(params, N, seed):
+    """A synthetic rollout slice that is 'slightly off-policy' so that both clip branches are populated."""
+    rng = np.random.default_rng(seed)
+    obs = rng.uniform(-1, 1, (N, 12)).astype(np.float32)
+    pp = ppo_ref.unpack(params, 12, 0)
+    head, value = ppo_ref.forward(pp, obs)
+    eps = rng.normal(size=(N, 4))
+    act = (head + np.exp(pp["log_std"]) * eps).astype(np.float32)
+    logp = np.sum(-0.5 * eps * eps - pp["log_std"] - ppo_ref.LOG_SQRT_2PI, axis=1)
+    old_logp = (logp + rng.normal(scale=0.15, size=N)).astype(np.float32)      # ratio spread around 1 beyond the clip range
+    # advantages that depend on the action noise and returns that depend on the observation, as in a real rollout: the
+    # minibatch gradient then carries a signal instead of being the 1/sqrt(N) residue of cancelling per-sample terms
+    adv = (2.0 * (eps @ np.array([1.0, -1.0, 0.5, 0.2])) + 0.5 * rng.normal(size=N) + 0.3).astype(np.float32)
+    ret = (value + 0.5 + 0.5 * np.sin(3.0 * obs[:, 0]) + 0.3 * obs[:, 5] + 0.1 * rng.normal(size=N)).astype(np.float32)
+    return obs, act, old_logp, adv, ret
+
+
+def _torch_loss(ac, obs, act, old_logp, adv, ret, normalize=True):
+    import torch
+    a = adv
+    if normalize:
+        a = (a - a.mean()) / (a.std() + 1e-8)
+    logp, value, ent = ac.evaluate(obs, act)
+    ratio = torch.exp(logp - old_logp)
+    pg = torch.max(-a * ratio, -a * torch.clamp(ratio, 1 - CLIP, 1 + CLIP)).mean()
+    vl = torch.nn.functional.mse_loss(value, ret)
+    return pg + VF * vl - ENT * ent, pg, vl
+
+
+def _autograd_grad(params, batch, normalize=True):
+    import torch
+    from uav_reinforcement_learning_control_b200.ppo import ActorCritic
+    ac = ActorCritic(12, "cpu")
+    for group in (ac.actor, ac.critic, [ac.log_std]):
+        for i, t in enumerate(group):
+            group[i] = t.detach().double().requires_grad_(True)
+    ac.log_std = ac.log_std.detach().double().requires_grad_(True)
+    ac.obs_mean, ac.obs_inv_std = ac.obs_mean.double(), ac.obs_inv_std.double()
+    ac.load_packed(torch.from_numpy(params.astype(np.float64)))
+    t = [torch.from_numpy(np.asarray(b, dtype=np.float64)) for b in batch]
+    loss, pg, vl = _torch_loss(ac, *t, normalize=normalize)
+    loss.backward()
+    g = torch.cat([p.grad.reshape(-1) for p in ac.parameters()]).numpy()
+    return np.concatenate([g, np.zeros(24)]), float(pg.detach()), float(vl.detach())
+
+
+@pytest.mark.parametrize("normalize", [True, False])
+def test_oracle_gradient_matches_torch_autograd(normalize):
+    params = _policy(1)
+    batch = _batch(params, 777, 2)
+    g_ref, pg, vl = _autograd_grad(params, batch, normalize)
+    g, st = U.grad(params, *batch, CLIP, VF, ENT, normalize_adv=normalize)
+    assert 0.05 < st["clip_frac"] < 0.95, st       # both branches of the clipped surrogate are exercised
+    np.testing.assert_allclose(g, g_ref, rtol=1e-9, atol=1e-12)
+    assert abs(st["pg_loss"] - pg) < 1e-12 and abs(st["v_loss"] - vl) < 1e-12
+
+
+def test_oracle_adam_matches_torch():
+    import torch
+    rng = np.random.default_rng(3)
+    P, n_train = 500, 470
+    p0 = rng.normal(size=P); lr = 1.5e-4
+    tp = torch.tensor(p0[:n_train], dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([tp], lr=lr, eps=1e-5)
+    p, m, v = p0.copy(), np.zeros(P), np.zeros(P)
+    for step in range(1, 6):
+        g = rng.normal(size=P) * (3.0 if step % 2 else 0.01)
+        tp.grad = torch.tensor(g[:n_train] * 0.5, dtype=torch.float64)
+        norm_t = float(torch.nn.utils.clip_grad_norm_([tp], 0.5))
+        opt.step()
+        p, m, v, norm = U.adam_step(p, g, m, v, step, lr, max_grad_norm=0.5, grad_scale=0.5, n_train=n_train)
+        assert abs(norm - norm_t) < 1e-12
+        np.testing.assert_allclose(p[:n_train], tp.detach().numpy(), rtol=1e-12, atol=1e-15)
+        np.testing.assert_array_equal(p[n_train:], p0[n_train:])
+
+
+def test_bf16_oracle_is_close_to_exact_oracle():
+    """The rounding model of the tensor-core path perturbs the gradient by bf16-level noise only."""
+    params = _policy(4)
+    batch = _batch(params, 2048, 5)
+    g, _ = U.grad(params, *batch, CLIP, VF, ENT)
+    gb, _ = U.grad(params, *batch, CLIP, VF, ENT, bf16=True)
+    a, b = U.split(g), U.split(gb)
+    for k in ("aW1", "aW2", "aW3", "cW1", "cW2", "cW3", "ab1", "ab2", "cb1", "cb2", "log_std"):
+        scale = np.abs(a[k]).max()
+        # log_std's gradient, sum g (z^2 - 1), is a small residue of cancelling terms: looser
+        assert np.abs(a[k] - b[k]).max() < (0.15 if k == "log_std" else 0.03) * scale, k
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU
+
+
+def _report(g, g_ref, tol_rel, tol_log_std=None):
+    a, b = U.split(g), U.split(g_ref)
+    bad = []
+    for k in U.PARAM_ORDER:
+        scale = max(np.abs(b[k]).max(), 1e-12)
+        err = np.abs(a[k] - b[k]).max()
+        tol = tol_log_std if (k == "log_std" and tol_log_std is not None) else tol_rel
+        if not err <= tol * scale + 1e-9:
+            bad.append(f"{k}: max err {err:.3e} vs scale {scale:.3e}")
+    assert not bad, "; ".join(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,n_idx,normalize", [(128, None, True), (1000, None, True), (77, None, False), (40000, None, True),
+                                               (50000, 30011, True)])
+def test_fused_gradient_matches_oracle(N, n_idx, normalize):
+    """qs_ppo_grad vs the bf16-rounding oracle, tensor by tensor (a wrong UMMA descriptor shows up as ONE bad tensor)."""
+    import torch
+    from uav_reinforcement_learning_control_b200.ppo import FusedUpdater
+    params = _policy(10 + N % 7)
+    batch = _batch(params, N, N)
+    up = FusedUpdater("cuda:0")
+    dev = [torch.from_numpy(b).cuda() for b in batch]
+    idx = None
+    sel = slice(None)
+    if n_idx is not None:
+        sel = np.random.default_rng(N).permutation(N)[:n_idx]
+        idx = torch.from_numpy(sel.astype(np.int32)).cuda()
+    for rep in range(2):                                  # second call: workspace re-armed, same answer
+        g = up.grad(torch.from_numpy(params).cuda(), *dev, idx=idx, clip_range=CLIP, vf_coef=VF, ent_coef=ENT,
+                    normalize_adv=normalize)
+        torch.cuda.synchronize()
+        g = g.cpu().numpy().astype(np.float64)
+        sub = [b[sel] for b in batch]
+        g_ref, st = U.grad(params, *sub, CLIP, VF, ENT, normalize_adv=normalize, bf16=True)
+        n = len(sub[0])
+        # fp32 accumulation order and __expf-level differences only: 2e-3 of each tensor's scale
+        _report(g[:up.P], g_ref, 2e-3, tol_log_std=1e-2)
+        stats = g[up.P:]
+        assert stats[4] == n
+        assert abs(stats[0] / n - st["pg_loss"]) < 2e-3 * max(1.0, abs(st["pg_loss"]))
+        assert abs(stats[1] / n - st["v_loss"]) < 2e-3 * max(1.0, abs(st["v_loss"]))
+        assert abs(stats[2] / n - st["clip_frac"]) < 5e-3
+        assert abs(stats[3] / n - st["approx_kl"]) < 1e-3
+        # and against exact arithmetic: bf16-level agreement (minibatches large enough for the gradient to be a mean)
+        if n >= 1000:
+            g_exact, _ = U.grad(params, *sub, CLIP, VF, ENT, normalize_adv=normalize)
+            _report(g[:up.P], g_exact, 0.05, tol_log_std=0.2)
+
+
+@pytest.mark.gpu
+def test_fused_gradient_is_bitwise_reproducible():
+    import torch
+    from uav_reinforcement_learning_control_b200.ppo import FusedUpdater
+    params = _policy(3)
+    batch = _batch(params, 100000, 8)
+    up = FusedUpdater("cuda:0")
+    dev = [torch.from_numpy(b).cuda() for b in batch]
+    p = torch.from_numpy(params).cuda()
+    g1 = up.grad(p, *dev, clip_range=CLIP, vf_coef=VF, ent_coef=ENT).clone()
+    g2 = up.grad(p, *dev, clip_range=CLIP, vf_coef=VF, ent_coef=ENT).clone()
+    assert torch.equal(g1, g2)
+
+
+@pytest.mark.gpu
+def test_fused_adam_matches_oracle():
+    import torch
+    from uav_reinforcement_learning_control_b200.ppo import FusedUpdater
+    rng = np.random.default_rng(0)
+    params = _policy(5)
+    up = FusedUpdater("cuda:0")
+    P = up.P
+    p_dev = torch.from_numpy(params).cuda()
+    p, m, v = params.astype(np.float64), np.zeros(P), np.zeros(P)
+    for step in range(1, 5):
+        g = (rng.normal(size=P) * (1e-2 if step % 2 else 1e-4)).astype(np.float32)
+        up.grad_buf[:P] = torch.from_numpy(g).cuda()
+        norm_dev = up.adam(p_dev, lr=1.5478e-4, max_grad_norm=0.5, grad_scale=0.5)
+        p, m, v, norm = U.adam_step(p, g, m, v, step, 1.5478e-4, max_grad_norm=0.5, grad_scale=0.5, n_train=P - 24)
+        torch.cuda.synchronize()
+        assert abs(float(norm_dev) - norm) < 1e-5 * norm
+        np.testing.assert_allclose(p_dev.cpu().numpy(), p, rtol=2e-6, atol=2e-8)
+    np.testing.assert_array_equal(p_dev.cpu().numpy()[P - 24:], params[P - 24:])       # the obs normaliser is untouched
+
+
+@pytest.mark.gpu
+def test_fused_update_follows_autograd_update():
+    """Three full minibatch updates (same minibatches): fused kernels vs torch autograd + torch.optim.Adam on the GPU."""
+    import torch
+    from uav_reinforcement_learning_control_b200.ppo import ActorCritic, FusedUpdater
+    params = _policy(6)
+    batch = _batch(params, 30000, 9)
+    dev = [torch.from_numpy(b).cuda() for b in batch]
+    up = FusedUpdater("cuda:0")
+    p_fused = torch.from_numpy(params).cuda()
+    ac = ActorCritic(12, "cuda:0")
+    ac.load_packed(torch.from_numpy(params).cuda())
+    opt = torch.optim.Adam(ac.parameters(), lr=3e-4, eps=1e-5)
+    rng = np.random.default_rng(1)
+    for it in range(3):
+        idx = torch.from_numpy(rng.permutation(30000)[:10000].astype(np.int32)).cuda()
+        up.grad(p_fused, *dev, idx=idx, clip_range=CLIP, vf_coef=VF, ent_coef=ENT)
+        up.adam(p_fused, lr=3e-4, max_grad_norm=0.5)
+        il = idx.long()
+        loss, _, _ = _torch_loss(ac, *[d[il] for d in dev])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ac.parameters(), 0.5)
+        opt.step()
+    torch.cuda.synchronize()
+    a, b = p_fused.cpu().numpy(), ac.pack().cpu().numpy()
+    # Adam normalises the step to ~lr per element, so bf16-level gradient noise moves a parameter by at most a
+    # fraction of 3 steps x lr
+    assert np.abs(a - b).max() < 3 * 3e-4
+    assert np.abs(a - params).max() > 2e-4            # ...and the parameters did move
+    moved = np.abs(b - params) > 5e-4
+    assert np.mean(np.sign(a - params)[moved] == np.sign(b - params)[moved]) > 0.98
+
+
+@pytest.mark.gpu
+def test_trainer_fused_improves_reward():
+    """End to end on the device: tcgen05 rollout -> GAE -> fused update, a few iterations; the policy must improve."""
+    import torch
+    from uav_reinforcement_learning_control_b200 import config as Q
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    from uav_reinforcement_learning_control_b200.ppo import PPOConfig, PPOTrainer
+    torch.manual_seed(0)
+    eng = Engine(Q.EnvConfig.north_star(seed=0), 16384, device=0)
+    tr = PPOTrainer(eng, PPOConfig(n_steps=64, learning_rate=1e-3, ent_coef=0.0), seed=0)
+    assert tr.fused and tr.tensor_cores
+    tr.set_log_std(-1.0)
+    log = tr.train(8)
+    assert np.isfinite(log[-1]["mean_reward"]) and np.isfinite(log[-1]["pg_loss"])
+    assert log[-1]["mean_reward"] > log[0]["mean_reward"]
+    assert 0.0 <= log[-1]["clip_frac"] <= 1.0

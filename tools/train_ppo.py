@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--total-envs", type=int, default=65536)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--n-steps", type=int, default=64)
+    ap.add_argument("--autograd", action="store_true", help="torch-autograd update instead of the fused qs_ppo_grad / qs_ppo_adam kernels")
     args = ap.parse_args()
     import torch
     from uav_reinforcement_learning_control_b200 import config as Q
@@ -29,8 +30,9 @@ def main():
     torch.cuda.set_device(ctx.local_rank)
     off, cnt = shard_range(args.total_envs, ctx.world, ctx.rank)
     eng = Engine(Q.EnvConfig.north_star(seed=0, env_id_offset=off), cnt, device=ctx.local_rank)
-    tr = PPOTrainer(eng, PPOConfig(n_steps=args.n_steps, learning_rate=1e-3, ent_coef=0.0), ctx=ctx, seed=0)
-    tr.policy.log_std.data.fill_(-1.0)
+    tr = PPOTrainer(eng, PPOConfig(n_steps=args.n_steps, learning_rate=1e-3, ent_coef=0.0), ctx=ctx, seed=0,
+                    fused=not args.autograd)
+    tr.set_log_std(-1.0)
     torch.manual_seed(1234)                       # same minibatch permutation stream on every rank
     torch.cuda.synchronize()
     t0 = time.time()
@@ -38,7 +40,7 @@ def main():
     torch.cuda.synchronize()
     dt = time.time() - t0
     # all ranks must hold identical parameters after data-parallel training
-    flat = tr.policy.pack()
+    flat = tr.packed_params()
     chk = torch.stack([flat.double().sum(), flat.double().abs().sum()])
     if ctx.world > 1:
         import torch.distributed as dist
@@ -48,7 +50,7 @@ def main():
     else:
         in_sync = True
     if ctx.rank == 0:
-        print(json.dumps({"world": ctx.world, "total_envs": args.total_envs, "iters": args.iters,
+        print(json.dumps({"world": ctx.world, "update": "fused tcgen05 kernels" if tr.fused else "torch autograd", "total_envs": args.total_envs, "iters": args.iters,
                           "env_steps_per_s_incl_update": args.total_envs * args.n_steps * args.iters / dt,
                           "mean_reward_first": log[0]["mean_reward"], "mean_reward_last": log[-1]["mean_reward"],
                           "episodes_last": log[-1]["episodes"], "params_in_sync_across_ranks": in_sync}), flush=True)

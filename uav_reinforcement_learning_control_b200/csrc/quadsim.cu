@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <atomic>
 #include <new>
 
@@ -15,6 +16,7 @@
 #include "qs_kernels.cuh"
 #include "qs_rollout.cuh"
 #include "qs_rollout_tc.cuh"
+#include "qs_ppo.cuh"
 #include "qs_traj.cuh"
 
 namespace {
@@ -389,6 +391,83 @@ int qs_gae(int32_t T, int32_t B, const float* reward, const float* value, const 
     qs::gae_kernel<<<nblocks(B, qs::kGaeBlock), qs::kGaeBlock, 0, (cudaStream_t)stream>>>(T, B, reward, value, done, trunc, last_value,
                                                                       gamma, lam, brax_form, adv, ret);
     return check_launch("gae_kernel");
+}
+
+// ---- PPO update on device: implemented in qs_ppo.cuh ------------------------------------------------
+namespace {
+constexpr size_t kPpoWsHeader = 128;   // bytes: 2 doubles + 1 counter (advantage sums) | 2 floats (mean, 1/std) at byte 32
+
+int ppo_device_sms(int* sms) {
+    int dev = 0, major = 0;
+    QS_CUDA(cudaGetDevice(&dev));
+    QS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return fail(QS_EUNSUPPORTED, "qs_ppo_*: libquadsim is built for sm_100a (B200) only");
+    QS_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+    return QS_OK;
+}
+bool ppo_desc_ok(const QsPolicyDesc* d) {
+    return d && d->obs_dim == qs::ppo::kD && d->hidden == 128 && d->act_dim == 4 && d->dist == 0;
+}
+}  // namespace
+
+int64_t qs_ppo_workspace_bytes(const QsPolicyDesc* desc) {
+    if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, "qs_ppo_workspace_bytes: the fused update covers the SB3 policy (12 -> 128 -> 128 -> 4, dist 0)");
+    int sms = 0;
+    const int rc = ppo_device_sms(&sms);
+    if (rc != QS_OK) return rc;
+    const size_t row = (size_t)qs::ppo::partial_stride(qs::policy_param_count(*desc));
+    return (int64_t)(kPpoWsHeader + (size_t)sms * row * sizeof(float));
+}
+
+int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const float* obs, const float* act,
+                const float* old_logp, const float* adv, const float* ret, const int32_t* idx, int32_t n,
+                float clip_range, float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad,
+                void* stream) {
+    if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, "qs_ppo_grad: the fused update covers the SB3 policy (12 -> 128 -> 128 -> 4, dist 0)");
+    if (!policy_params || !obs || !act || !old_logp || !adv || !ret || !workspace || !grad || n <= 0)
+        return fail(QS_EINVAL, "qs_ppo_grad: bad argument");
+    if ((((uintptr_t)obs | (uintptr_t)act | (uintptr_t)workspace | (uintptr_t)grad) & 15u) != 0)
+        return fail(QS_EINVAL, "qs_ppo_grad: obs, act, workspace and grad must be 16-byte aligned");
+    int sms = 0;
+    const int rc = ppo_device_sms(&sms);
+    if (rc != QS_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    double* adv_scratch = (double*)ws;
+    float* adv_norm = (float*)(ws + 32);
+    float* partial = (float*)(ws + kPpoWsHeader);
+    if (normalize_adv) {
+        const int blocks = nblocks(n, 256) < 4 * sms ? nblocks(n, 256) : 4 * sms;
+        qs::ppo::ppo_adv_stats_kernel<<<blocks, 256, 0, s>>>(adv, idx, n, adv_scratch, adv_norm);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    const int ntiles = nblocks(n, qs::tc::kM);
+    const int grid = ntiles < sms ? ntiles : sms;
+    static const int mn_swap = getenv("QS_PPO_MN_SWAP") ? atoi(getenv("QS_PPO_MN_SWAP")) : 0;   // descriptor debug knob
+    QS_CUDA(cudaFuncSetAttribute(qs::ppo::ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qs::ppo::SmemP::TOTAL));
+    qs::ppo::Batch b{obs, act, old_logp, adv, ret, idx, n};
+    qs::ppo::Hyper hp{clip_range, vf_coef, ent_coef, normalize_adv};
+    qs::ppo::ppo_grad_tc_kernel<<<grid, qs::tc::kM, qs::ppo::SmemP::TOTAL, s>>>(b, hp, policy_params, adv_norm, partial, mn_swap);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const int len = qs::policy_param_count(*desc) + qs::ppo::kPartialStats;
+    qs::ppo::ppo_reduce_kernel<<<nblocks(len, 256), 256, 0, s>>>(partial, grid, qs::ppo::partial_stride(len - qs::ppo::kPartialStats),
+                                                                 len, grad);
+    return check_launch("ppo_grad");
+}
+
+int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* grad, float* m, float* v, int32_t step,
+                float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, float* norm_out,
+                void* stream) {
+    if (!desc || desc->hidden != 128 || desc->act_dim != 4) return fail(QS_EINVAL, "qs_ppo_adam: bad policy description");
+    if (!policy_params || !grad || !m || !v || step <= 0) return fail(QS_EINVAL, "qs_ppo_adam: bad argument");
+    const qs::PolicyLayout L = qs::policy_layout(desc->obs_dim, desc->dist);
+    qs::ppo::AdamArgs a;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_grad_norm = max_grad_norm; a.grad_scale = grad_scale;
+    a.bias1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bias2 = (float)(1.0 - pow((double)beta2, (double)step));
+    a.n_train = L.mean;
+    qs::ppo::ppo_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, policy_params, grad, m, v, norm_out);
+    return check_launch("ppo_adam_kernel");
 }
 
 }  // extern "C"

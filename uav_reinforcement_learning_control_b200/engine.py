@@ -45,6 +45,11 @@ _EXPORTS = {
                + [C.c_void_p] * 2 + [C.c_void_p]),
     "qs_traj_info": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_void_p]),
     "qs_step_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "qs_ppo_workspace_bytes": (C.c_int64, [C.POINTER(Q.QsPolicyDesc)]),
+    "qs_ppo_grad": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 7
+                    + [C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32] + [C.c_void_p] * 3),
+    "qs_ppo_adam": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_float] * 6
+                    + [C.c_void_p] * 2),
 }
 
 

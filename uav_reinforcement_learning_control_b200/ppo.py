@@ -3,9 +3,11 @@
 Replaces the caller side of the hot path: SB3 ``PPO.learn`` (train.py:50-68,133-137: MlpPolicy
 [128,128] ReLU for pi and vf, n_steps 1024, clip 0.19, gamma 0.9906, lambda 0.9079) and Brax
 ``ppo_train.train`` (train_brax_ppo.py:589-620).  Rollout collection and GAE are the sm_100a kernels
-(``qs_rollout_policy``, ``qs_gae``); the clipped-surrogate update itself is ordinary torch autograd on
-the GPU (library GEMMs -- it is not on the rollout hot path), with one flat NCCL all-reduce of the
-gradient per minibatch (parallel.flat_allreduce_mean_).
+(``qs_rollout_policy``, ``qs_gae``).  The clipped-surrogate update is on device too (``FusedUpdater``:
+``qs_ppo_grad`` -- forward + analytic backward of both networks on tcgen05 with the weight gradients accumulating in
+TMEM -- and ``qs_ppo_adam``, csrc/qs_ppo.cuh) for the SB3 policy; ``PPOTrainer(fused=False)`` keeps the torch-autograd
+update (library GEMMs) that the fused one is tested against.  Either way there is one flat NCCL all-reduce of the
+gradient per minibatch and nothing else.
 """
 from __future__ import annotations
 
@@ -15,7 +17,7 @@ from dataclasses import dataclass
 from . import config as Q
 from .parallel import DistContext, flat_allreduce_mean_, reduce_stats
 
-__all__ = ["PPOConfig", "ActorCritic", "PPOTrainer", "load_sb3_policy_zip", "sb3_state_dict_to_packed"]
+__all__ = ["PPOConfig", "ActorCritic", "FusedUpdater", "PPOTrainer", "load_sb3_policy_zip", "sb3_state_dict_to_packed"]
 
 H, A = 128, 4
 
@@ -70,6 +72,17 @@ class ActorCritic:
                      self.log_std, self.obs_mean, self.obs_inv_std]
             return torch.cat([p.reshape(-1).float() for p in parts]).contiguous()
 
+    def load_packed(self, vec):
+        """Inverse of ``pack`` (the obs normaliser included)."""
+        import torch
+        o = 0
+        with torch.no_grad():
+            for group in (self.actor, self.critic, [self.log_std], [self.obs_mean], [self.obs_inv_std]):
+                for t in group:
+                    t.copy_(vec[o:o + t.numel()].reshape(t.shape).to(t.dtype))
+                    o += t.numel()
+        assert o == vec.numel(), (o, vec.numel())
+
     def evaluate(self, obs, raw_action):
         """-> (log_prob, value, entropy) of stored unclipped Gaussian samples (SB3 evaluate_actions)."""
         import torch
@@ -83,16 +96,96 @@ class ActorCritic:
         return logp, value, ent
 
 
-class PPOTrainer:
-    """Data-parallel PPO: every rank owns a shard of envs (engine with env_id_offset) and the full policy."""
+class FusedUpdater:
+    """The PPO minibatch update as sm_100a kernels (include/quadsim_abi.h: qs_ppo_grad / qs_ppo_adam) on the PACKED
+    parameter vector -- the same tensor the rollout kernels read, so there is no pack / unpack between rollout and
+    update.  Holds the Adam moments, the per-CTA partial-gradient workspace and the flat gradient (+ 8 statistics)."""
 
-    def __init__(self, engine, cfg: PPOConfig | None = None, ctx: DistContext | None = None, seed: int = 0):
+    N_STATS = 8
+
+    def __init__(self, device, obs_dim: int = 12):
+        import ctypes as C
+        import torch
+        from .engine import QuadSimError, load_library
+        if not torch.cuda.is_available():
+            raise QuadSimError("no CUDA device: the fused PPO update has no CPU fallback")
+        self.torch, self.C = torch, C
+        self.lib = load_library()
+        self.device = torch.device(device)
+        d = Q.QsPolicyDesc()
+        d.obs_dim, d.hidden, d.act_dim, d.dist = int(obs_dim), H, A, 0
+        self.desc = d
+        with torch.cuda.device(self.device):
+            nbytes = int(self.lib.qs_ppo_workspace_bytes(C.byref(d)))
+        if nbytes <= 0:
+            raise QuadSimError(f"qs_ppo_workspace_bytes: {self.lib.qs_last_error_string().decode()}")
+        self.P = int(self.lib.qs_policy_param_count(C.byref(d)))
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self.grad_buf = torch.zeros(self.P + self.N_STATS, dtype=torch.float32, device=self.device)
+        self.m = torch.zeros(self.P, dtype=torch.float32, device=self.device)
+        self.v = torch.zeros(self.P, dtype=torch.float32, device=self.device)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.step = 0
+
+    def _check(self, rc, what):
+        if rc != 0:
+            from .engine import QuadSimError
+            raise QuadSimError(f"{what}: libquadsim error {rc}: {self.lib.qs_last_error_string().decode()}")
+
+    def _stream(self):
+        return self.C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def grad(self, params, obs, act, old_logp, adv, ret, idx=None, clip_range=0.2, vf_coef=0.5, ent_coef=0.0,
+             normalize_adv=True):
+        """Gradient of the SB3 PPO loss over rows ``idx`` (int32, or None: all rows) of the flattened rollout buffers.
+        Returns the [P + 8] buffer: packed gradient | loss statistics (sums, see quadsim_abi.h)."""
+        torch = self.torch
+        N = old_logp.numel()
+        for name, t, shp in (("params", params, (self.P,)), ("obs", obs, (N, self.desc.obs_dim)), ("act", act, (N, 4)),
+                             ("old_logp", old_logp, (N,)), ("adv", adv, (N,)), ("ret", ret, (N,))):
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shp:
+                raise ValueError(f"{name}: expected contiguous float32 CUDA tensor {shp}, got {t.dtype} {tuple(t.shape)}")
+        if idx is not None and (idx.dtype != torch.int32 or not idx.is_cuda or not idx.is_contiguous() or idx.dim() != 1):
+            raise ValueError("idx: expected a contiguous 1-D int32 CUDA tensor")
+        n = N if idx is None else idx.numel()
+        p = lambda t: None if t is None else self.C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            self._check(self.lib.qs_ppo_grad(self.C.byref(self.desc), p(params), p(obs), p(act), p(old_logp), p(adv), p(ret),
+                                             p(idx), int(n), float(clip_range), float(vf_coef), float(ent_coef),
+                                             int(bool(normalize_adv)), p(self.workspace), p(self.grad_buf), self._stream()),
+                        "qs_ppo_grad")
+        return self.grad_buf
+
+    def adam(self, params, lr, max_grad_norm=0.5, grad_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-5, grad=None):
+        """clip_grad_norm_ + Adam step on ``params`` in place, from ``self.grad_buf`` (after any all-reduce)."""
+        self.step += 1
+        g = self.grad_buf if grad is None else grad
+        p = lambda t: self.C.c_void_p(t.data_ptr())
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.qs_ppo_adam(self.C.byref(self.desc), p(params), p(g), p(self.m), p(self.v), int(self.step),
+                                             float(lr), float(beta1), float(beta2), float(eps), float(max_grad_norm),
+                                             float(grad_scale), p(self.norm), self._stream()), "qs_ppo_adam")
+        return self.norm
+
+
+class PPOTrainer:
+    """Data-parallel PPO: every rank owns a shard of envs (engine with env_id_offset) and the full policy.
+
+    fused=True (default for the 12-D SB3 policy): the update runs as qs_ppo_grad / qs_ppo_adam on the packed parameter
+    vector ``self.params``; fused=False: torch autograd on ``self.policy``."""
+
+    def __init__(self, engine, cfg: PPOConfig | None = None, ctx: DistContext | None = None, seed: int = 0,
+                 fused: bool | None = None, tensor_cores: bool | None = None):
         import torch
         self.torch = torch
         self.engine = engine
         self.cfg = cfg or PPOConfig()
         self.ctx = ctx or DistContext()
         self.policy = ActorCritic(engine.obs_dim, engine.device, seed=seed)     # same seed on every rank
+        self.fused = (engine.obs_dim == 12) if fused is None else bool(fused)
+        self.tensor_cores = self.fused if tensor_cores is None else bool(tensor_cores)
+        self.params = self.policy.pack() if self.fused else None                 # fused: THE master copy of the weights
+        self.updater = FusedUpdater(engine.device, engine.obs_dim) if self.fused else None
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
         self.state = engine.new_state()
         engine.reset(self.state)
@@ -103,8 +196,9 @@ class PPOTrainer:
     def collect(self):
         c, eng = self.cfg, self.engine
         boot = c.gamma if c.timeout_bootstrap else 0.0
-        self.buf = eng.rollout_policy(self.state, self.policy.pack(), T=c.n_steps, t0=self.t, dist=0,
-                                      bootstrap_gamma=boot, buffers=self.buf)
+        self.buf = eng.rollout_policy(self.state, self.params if self.fused else self.policy.pack(), T=c.n_steps,
+                                      t0=self.t, dist=0, bootstrap_gamma=boot, tensor_cores=self.tensor_cores,
+                                      buffers=self.buf)
         self.t += c.n_steps
         b = self.buf
         self.adv, self.ret = eng.gae(b["reward"], b["value"], b["done"], b["trunc"], b["last_value"], c.gamma,
@@ -112,6 +206,35 @@ class PPOTrainer:
         return b
 
     def update(self):
+        return self.update_fused() if self.fused else self.update_autograd()
+
+    def update_fused(self):
+        """n_epochs x num_minibatches of {qs_ppo_grad -> one flat all-reduce -> qs_ppo_adam}; no host sync inside."""
+        torch, c, b, up = self.torch, self.cfg, self.buf, self.updater
+        T, B = b["reward"].shape
+        N = T * B
+        obs = b["obs"].reshape(N, -1); act = b["act"].reshape(N, 4)
+        old_logp = b["logp"].reshape(N); adv = self.adv.reshape(N); ret = self.ret.reshape(N)
+        mb = N // c.num_minibatches
+        acc = torch.zeros(up.N_STATS, dtype=torch.float32, device=obs.device)
+        world = self.ctx.world
+        for _ in range(c.n_epochs):
+            perm = torch.randperm(N, device=obs.device).to(torch.int32)
+            for k in range(c.num_minibatches):
+                g = up.grad(self.params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb],
+                            clip_range=c.clip_range, vf_coef=c.vf_coef, ent_coef=c.ent_coef,
+                            normalize_adv=c.normalize_advantage)
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(g, group=self.ctx.group)       # the ONLY collective: P + 8 floats, sum
+                acc += g[up.P:]
+                up.adam(self.params, c.learning_rate, max_grad_norm=c.max_grad_norm, grad_scale=1.0 / world)
+        s = acc.tolist()                                             # one D2H read per update
+        nb = c.n_epochs * c.num_minibatches
+        return {"pg_loss": s[0] / max(s[4], 1.0) * nb, "v_loss": s[1] / max(s[4], 1.0) * nb,
+                "clip_frac": s[2] / max(s[4], 1.0), "approx_kl": s[3] / max(s[4], 1.0), "n": nb}
+
+    def update_autograd(self):
         torch, c, b = self.torch, self.cfg, self.buf
         T, B = b["reward"].shape
         N = T * B
@@ -139,6 +262,15 @@ class PPOTrainer:
                 self.opt.step()
                 stats["pg_loss"] += float(pg.detach()); stats["v_loss"] += float(vl.detach()); stats["n"] += 1
         return stats
+
+    def packed_params(self):
+        return self.params if self.fused else self.policy.pack()
+
+    def set_log_std(self, value: float):
+        self.policy.log_std.data.fill_(float(value))
+        if self.fused:
+            D = self.engine.obs_dim
+            self.params[self.params.numel() - 2 * D - A:self.params.numel() - 2 * D] = float(value)
 
     def episode_stats(self):
         """Global (all ranks) mean reward per step and episodes finished in the last rollout."""

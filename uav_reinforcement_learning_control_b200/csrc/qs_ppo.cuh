@@ -91,6 +91,44 @@ __device__ __forceinline__ uint32_t pack_mask_bf16(float lo, float hi, uint32_t 
     return pack_bf16(lo, hi);
 }
 
+// tcgen05.ld without the wait (the registers are valid only after tmem_ld_wait on the same array)
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t r[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+// wait for every outstanding tcgen05.ld of this thread; the "+r" operands tie the register array to the wait so that
+// no use of it can be scheduled above
+__device__ __forceinline__ void tmem_ld_wait(uint32_t r[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+// bf16x2(lo, hi) & [h > 0] per half: one F2FP pack, one HSET2 (0xffff per true half), one LOP
+__device__ __forceinline__ uint32_t pack_mask2_bf16(float lo, float hi, uint32_t hpair) {
+    uint32_t m, p;
+    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(hpair), "r"(0u));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+    return p & m;
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16_u(uint32_t lo, uint32_t hi) {
+    return pack_relu_bf16(__uint_as_float(lo), __uint_as_float(hi));
+}
+
+#ifdef QS_PPO_PROFILE
+#define QS_PPOP(k) do { const long long c_ = clock64(); prof_[k] += c_ - pc_; pc_ = c_; } while (0)
+#else
+#define QS_PPOP(k) do { } while (0)
+#endif
+
 struct Sample {
     float4 o0, o1, o2, a;
     float old_logp, adv, ret;
@@ -438,6 +476,495 @@ ppo_grad_tc_kernel(Batch b, Hyper hp, const float* __restrict__ params, const fl
     fence_before();
     __syncthreads();
     if (tid < 32) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ppo_grad_tc2_kernel -- the production schedule.  Same GEMMs, operands and rounding points as ppo_grad_tc_kernel, but
+//   * one network per CTA (even CTAs: actor, odd CTAs: critic; every CTA walks over ALL tiles of its share), which
+//     halves the TMEM accumulator columns (176) and the weight operands (44 KB) a CTA has to hold, so that
+//   * TWO 128-sample tiles are in flight per CTA (two worker warpgroups, each with its own operand buffers and 128
+//     working TMEM columns) and share the gradient accumulators, and
+//   * a dedicated issuer thread (warp 8) owns the tensor pipe: workers hand a phase over with fence + mbarrier.arrive
+//     on ready[slot] and wait on done[slot]; the issuer serves the two slots alternately, so one tile's MMAs run under
+//     the other tile's epilogue (ping-pong), and no worker warp ever spends issue slots on tcgen05.mma.
+//   * D2 / D1 are written IN PLACE over relu(H2) / relu(H1) (their only other readers, the dW3 / dW2 MMAs, are
+//     committed before the workers are released), so a slot needs 72 KB of operands.
+struct SmemQ {
+    static constexpr int W1 = 0, W2 = 4096, W3 = W2 + 32768, B2 = W3 + 4096, WEND = B2 + 4096;
+    static constexpr int A0 = 0, A1 = 2 * 4096, A2 = A1 + 32768, DOUT = A2 + 32768, SLOT_BYTES = DOUT + 4096;   // per slot
+    static constexpr int SLOT0 = WEND;
+    static constexpr int F32 = SLOT0 + 2 * SLOT_BYTES;
+    static constexpr int kB3 = 0, kLogStd = 4, kInvSig = 8, kMean = 12, kInvStd = 24, kNumF = 36;
+    static constexpr int RED = F32 + kNumF * 4;               // [8 warps][16]
+    static constexpr int BAR = RED + 8 * 16 * 4;              // ready[2], done[2], tmem slot
+    // per slot: cp.async landing zone for the next tile's gathered rows: obs [128][12] | act [128][4] | 3 x [128] scalars
+    static constexpr int STG = (BAR + 48 + 15) & ~15;
+    static constexpr int STG_ACT = 128 * 48, STG_SCAL = STG_ACT + 128 * 16, STG_BYTES = STG_SCAL + 3 * 128 * 4;
+    static constexpr int TOTAL = STG + 2 * STG_BYTES;
+};
+constexpr uint32_t kQColW = 0 /* + 128 * slot */, kQColW2 = 256, kQColW1 = 384, kQColW3 = 400, kQColB2 = 416;
+constexpr int kThreads2 = 288;
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// partial: [gridDim.x / 2][partial_stride(P)]; row r = actor CTA 2r (its network's entries, log_std, statistics 0 2 3 4)
+// and critic CTA 2r + 1 (its entries, statistic 1)
+__global__ void __launch_bounds__(kThreads2, 1)
+ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const float* __restrict__ adv_norm,
+                    float* __restrict__ partial, int mn_swap) {
+    using S = SmemQ;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const PolicyLayout L = policy_layout(kD, 0);
+    const int net = blockIdx.x & 1, cta = blockIdx.x >> 1, ncta = gridDim.x >> 1;
+    // warp-uniform role index (the shuffle makes the uniformity visible to ptxas: the issuer warp's descriptors then live
+    // in uniform registers and its tcgen05.mma need no per-lane election loops)
+    const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int gtid = threadIdx.x, wg = warp_id >> 2, tid = gtid & 127, warp = warp_id & 3, lane = gtid & 31;
+    float* sF = reinterpret_cast<float*>(smem + S::F32);
+    float* sRed = reinterpret_cast<float*>(smem + S::RED);
+    uint64_t* bar_ready = reinterpret_cast<uint64_t*>(smem + S::BAR);
+    uint64_t* bar_done = bar_ready + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 32);
+
+    // ---- one-time setup: this network's fp32 weights -> bf16 UMMA operands ------------------------------------------
+    for (int i = gtid; i < S::WEND / 4; i += kThreads2) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    __syncthreads();
+    auto put = [&](int base, int rows, int row, int k, float w) {
+        *reinterpret_cast<__nv_bfloat16*>(smem + base + op_offset(rows, row, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(w);
+    };
+    const int oW1 = net ? L.cW1 : L.aW1, ob1 = net ? L.cb1 : L.ab1, oW2 = net ? L.cW2 : L.aW2, ob2 = net ? L.cb2 : L.ab2;
+    for (int i = gtid; i < kD * kH; i += kThreads2) put(S::W1, 128, i % kH, i / kH, params[oW1 + i]);
+    for (int n = gtid; n < kH; n += kThreads2) {
+        const float bv[2] = {params[ob1 + n], params[ob2 + n]};
+        const int dst[2] = {S::W1, S::B2};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(bv[q]);
+            put(dst[q], 128, n, 12, __bfloat162float(hi));
+            put(dst[q], 128, n, 13, bv[q] - __bfloat162float(hi));
+        }
+    }
+    for (int i = gtid; i < kH * kH; i += kThreads2) put(S::W2, 128, i % kH, i / kH, params[oW2 + i]);
+    if (net == 0) { for (int i = gtid; i < kH * kA; i += kThreads2) put(S::W3, 16, i % kA, i / kA, params[L.aW3 + i]); }
+    else          { for (int k = gtid; k < kH; k += kThreads2) put(S::W3, 16, 0, k, params[L.cW3 + k]); }
+    if (gtid < kA) {
+        sF[S::kB3 + gtid] = net ? (gtid == 0 ? params[L.cb3] : 0.f) : params[L.ab3 + gtid];
+        const float ls = params[L.log_std + gtid];
+        sF[S::kLogStd + gtid] = ls;
+        sF[S::kInvSig + gtid] = expf(-ls);
+    }
+    if (gtid < kD) { sF[S::kMean + gtid] = params[L.mean + gtid]; sF[S::kInvStd + gtid] = params[L.inv_std + gtid]; }
+    if (gtid == 0) {
+        mbar_init(&bar_ready[0], kM); mbar_init(&bar_ready[1], kM); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wg == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    fence_async_smem();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t sb = smem_u32(smem);
+    const int ntiles = (b.n + kM - 1) / kM;
+    const int iters = (ntiles + 2 * ncta - 1) / (2 * ncta);
+
+    float g_b3[kA] = {0.f, 0.f, 0.f, 0.f}, g_ls[kA] = {0.f, 0.f, 0.f, 0.f};
+    float st_loss = 0.f, st_clip = 0.f, st_kl = 0.f, st_n = 0.f;
+
+    if (wg == 2) {
+        // =============================================== issuer ========================================================
+        // the whole warp walks the schedule (uniform control flow); one elected lane issues
+        {
+            // descriptor = per-layout base (start address 0 of the CTA's shared window) + byte offset / 16: one 64-bit add
+            // per operand on the single issuing thread instead of a dozen shifts and ors
+            const uint64_t dK128 = make_desc(sb, 2048u, 128u), dK16 = make_desc(sb, 256u, 128u);
+            const uint64_t dMN2048 = make_desc(sb, 128u, 2048u), dMN256 = make_desc(sb, 128u, 256u);
+            auto dk = [&](int off, int rows) { return (rows == 128 ? dK128 : dK16) + (uint64_t)(off >> 4); };
+            auto dmn = [&](int off, uint32_t grp_stride) { return (grp_stride == 2048u ? dMN2048 : dMN256) + (uint64_t)(off >> 4); };
+            (void)mn_swap;
+            const uint32_t id_kk128 = idesc_mn(128, 128, 0, 0), id_kk16 = idesc_mn(128, 16, 0, 0);
+            const uint32_t id_kmn128 = idesc_mn(128, 128, 0, 1);
+            const uint32_t id_mm128 = idesc_mn(128, 128, 1, 1), id_mm16 = idesc_mn(128, 16, 1, 1);
+            uint32_t ph[2] = {0u, 0u};
+            // Every hand-off is strictly "workers signal ready -> issuer issues -> commit -> workers wait", one phase at
+            // a time per slot: a slot can never run two phases ahead of the issuer, which would alias the mbarrier parity.
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {               // prologue: H1 of each slot's first tile
+                const int base = S::SLOT0 + s * S::SLOT_BYTES;
+                mbar_wait(&bar_ready[s], ph[s]); ph[s] ^= 1u;
+                fence_after();
+                if (elect_one()) {
+                    mma_bf16(tmem + kQColW + (uint32_t)(s * 128), dk(base + S::A0, 128), dk(S::W1, 128), id_kk128, 0u);
+                    mma_commit(&bar_done[s]);
+                }
+                __syncwarp();
+            }
+#ifdef QS_PPO_PROFILE
+            long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            long long pc_ = clock64();
+#endif
+#pragma unroll 1
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+                for (int phase = 1; phase < 6; ++phase) {
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const int base = S::SLOT0 + s * S::SLOT_BYTES;
+                        const int a0 = base + S::A0 + (it & 1) * 4096, a1 = base + S::A1, a2 = base + S::A2, dout = base + S::DOUT;
+                        const uint32_t tw = tmem + kQColW + (uint32_t)(s * 128);
+                        const uint32_t first = (it == 0 && s == 0) ? 0u : 1u;
+                        mbar_wait(&bar_ready[s], ph[s]); ph[s] ^= 1u;
+                        fence_after();
+                        QS_PPOP(phase);
+                        if (elect_one()) {
+                        switch (phase) {
+                        case 1:     // H2 = A1 . W2 + b2
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tw, dk(a1 + j * 4096, 128), dk(S::W2 + j * 4096, 128), id_kk128, j > 0);
+                            mma_bf16(tw, dk(a0, 128), dk(S::B2, 128), id_kk128, 1u);
+                            break;
+                        case 2:     // OUT = A2 . W3
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tw, dk(a2 + j * 4096, 128), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
+                            break;
+                        case 3:     // dH2 = dOUT . W3^T ; dW3 += A2^T . dOUT (must finish before D2 overwrites A2)
+                            mma_bf16(tw, dk(dout, 128), dmn(S::W3, 256u), id_kmn128, 0u);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tmem + kQColW3, dmn(a2 + j * 256, 2048u), dmn(dout + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
+                            break;
+                        case 4:     // dH1 = D2 . W2^T ; dW2 += A1^T . D2 ; db2 += D2^T . A0   (D2 lives in the A2 buffer)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tw, dk(a2 + j * 4096, 128), dmn(S::W2 + j * 256, 2048u), id_kmn128, j > 0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tmem + kQColW2, dmn(a1 + j * 256, 2048u), dmn(a2 + j * 256, 2048u), id_mm128, j > 0 ? 1u : first);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tmem + kQColB2, dmn(a2 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
+                            break;
+                        default:    // dW1^T | db1 += D1^T . A0 (D1 lives in the A1 buffer), then H1 of the slot's NEXT tile,
+                                    // whose A0 the workers wrote into the other A0 buffer together with D1
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tmem + kQColW1, dmn(a1 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
+                            if (it + 1 < iters)
+                                mma_bf16(tw, dk(base + S::A0 + ((it + 1) & 1) * 4096, 128), dk(S::W1, 128), id_kk128, 0u);
+                            break;
+                        }
+                        mma_commit(&bar_done[s]);
+                        }
+                        __syncwarp();
+                        QS_PPOP(5 + phase);
+                    }
+                }
+            }
+#ifdef QS_PPO_PROFILE
+            if (blockIdx.x < 2 && lane == 0)
+                printf("ppoprof net %d issuer (cycles per iteration of 2 tiles) wait-ready p1..p5: %lld %lld %lld %lld %lld | issue p1..p5: %lld %lld %lld %lld %lld\n",
+                       net, prof_[1] / iters, prof_[2] / iters, prof_[3] / iters, prof_[4] / iters, prof_[5] / iters,
+                       prof_[6] / iters, prof_[7] / iters, prof_[8] / iters, prof_[9] / iters, prof_[10] / iters);
+#endif
+        }
+    } else {
+        // =============================================== workers =======================================================
+        const int slot = wg;
+        unsigned char* sl = smem + S::SLOT0 + slot * S::SLOT_BYTES;
+        const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16) + kQColW + (uint32_t)(slot * 128);
+        uint64_t* ready = &bar_ready[slot];
+        uint64_t* done = &bar_done[slot];
+        uint32_t ph = 0u;
+        const float adv_mean = hp.normalize_adv ? adv_norm[0] : 0.f;
+        const float adv_istd = hp.normalize_adv ? adv_norm[1] : 1.f;
+        auto signal = [&]() { fence_async_smem(); fence_before(); mbar_arrive(ready); };
+        auto wait_done = [&]() { mbar_wait(done, ph); ph ^= 1u; fence_after(); };
+        // Epilogues: the TMEM load of column chunk c + 1 is in flight while chunk c is converted and stored.
+        auto epilogue_relu = [&](int dst) {
+            uint32_t r[2][32];
+            tmem_ld32_async(tw, r[0]);
+            tmem_ld_wait(r[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c + 1 < 4) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+                const uint32_t* v = r[c & 1];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t* h = v + q * 8;
+                    *reinterpret_cast<uint4*>(sl + dst + op_offset(128, tid, c * 4 + q)) =
+                        make_uint4(pack_relu_bf16_u(h[0], h[1]), pack_relu_bf16_u(h[2], h[3]), pack_relu_bf16_u(h[4], h[5]),
+                                   pack_relu_bf16_u(h[6], h[7]));
+                }
+                if (c + 1 < 4) tmem_ld_wait(r[(c + 1) & 1]);
+            }
+        };
+        auto epilogue_mask_inplace = [&](int buf) {       // buf <- bf16(working columns * [buf > 0])
+            uint32_t r[2][32];
+            tmem_ld32_async(tw, r[0]);
+            tmem_ld_wait(r[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c + 1 < 4) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+                const uint32_t* v = r[c & 1];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t* g = v + q * 8;
+                    uint4* p4 = reinterpret_cast<uint4*>(sl + buf + op_offset(128, tid, c * 4 + q));
+                    const uint4 h = *p4;
+                    *p4 = make_uint4(pack_mask2_bf16(__uint_as_float(g[0]), __uint_as_float(g[1]), h.x),
+                                     pack_mask2_bf16(__uint_as_float(g[2]), __uint_as_float(g[3]), h.y),
+                                     pack_mask2_bf16(__uint_as_float(g[4]), __uint_as_float(g[5]), h.z),
+                                     pack_mask2_bf16(__uint_as_float(g[6]), __uint_as_float(g[7]), h.w));
+                }
+                if (c + 1 < 4) tmem_ld_wait(r[(c + 1) & 1]);
+            }
+        };
+        // row of this thread's sample in tile `tile` (-1: padding row of a ragged / out-of-range tile)
+        auto row_of = [&](int tile) -> int {
+            const int r = tile * kM + tid;
+            if (r >= b.n) return -1;
+            return b.idx ? __ldg(b.idx + r) : r;
+        };
+        // The gathered rows of the NEXT tile travel global -> shared with cp.async (no registers, no scoreboard: a
+        // register prefetch across the tile made ptxas park the epilogues behind the outstanding gathers, ~2.5 k cycles
+        // per tile).  Every thread copies, waits for and reads only its own row, so no barrier is involved.
+        unsigned char* stg = smem + S::STG + slot * S::STG_BYTES;
+        auto gather_async = [&](int j) {
+            if (j >= 0) {
+                const uint32_t so = smem_u32(stg + tid * 48);
+                const float* o = b.obs + (size_t)j * kD;
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(so + q * 16), "l"(o + q * 4) : "memory");
+                const uint32_t ss = smem_u32(stg + S::STG_SCAL + tid * 4);
+                if (net == 0) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(stg + S::STG_ACT + tid * 16)), "l"(b.act + (size_t)j * 4) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ss), "l"(b.old_logp + j) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ss + 512), "l"(b.adv + j) : "memory");
+                } else {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ss + 1024), "l"(b.ret + j) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto gather_wait = [&](int j, Sample& s) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            s.valid = j >= 0;
+            s.o0 = s.o1 = s.o2 = s.a = make_float4(0.f, 0.f, 0.f, 0.f);
+            s.old_logp = 0.f; s.adv = 0.f; s.ret = 0.f;
+            if (s.valid) {
+                const float4* o = reinterpret_cast<const float4*>(stg + tid * 48);
+                s.o0 = o[0]; s.o1 = o[1]; s.o2 = o[2];
+                const float* sc = reinterpret_cast<const float*>(stg + S::STG_SCAL) + tid;
+                if (net == 0) {
+                    s.a = *reinterpret_cast<const float4*>(stg + S::STG_ACT + tid * 16);
+                    s.old_logp = sc[0]; s.adv = sc[128];
+                } else {
+                    s.ret = sc[256];
+                }
+            }
+        };
+        auto write_a0 = [&](const Sample& sm, int a0) {
+            // bf16 normalised observation, constant 1 in K slots 12 / 13 (0 for the padding rows of a ragged tile)
+            const float o[kD] = {sm.o0.x, sm.o0.y, sm.o0.z, sm.o0.w, sm.o1.x, sm.o1.y, sm.o1.z, sm.o1.w,
+                                 sm.o2.x, sm.o2.y, sm.o2.z, sm.o2.w};
+            float x[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                x[k] = !sm.valid ? 0.f : (k < kD ? (o[k] - sF[S::kMean + k]) * sF[S::kInvStd + k] : (k < kD + 2 ? 1.0f : 0.f));
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                *reinterpret_cast<uint4*>(sl + a0 + op_offset(128, tid, c)) =
+                    make_uint4(pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
+                               pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
+        };
+        Sample cur;
+        {
+            const int j0 = row_of(2 * cta + slot);
+            gather_async(j0);
+            gather_wait(j0, cur);
+        }
+        int j1 = iters > 1 ? row_of(2 * (cta + ncta) + slot) : -1;      // row index one tile ahead
+        gather_async(j1);
+        write_a0(cur, S::A0);
+        signal();
+#ifdef QS_PPO_PROFILE
+        long long prof_[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long pc_ = clock64();
+#endif
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+            const int j2 = it + 2 < iters ? row_of(2 * (cta + (it + 2) * ncta) + slot) : -1;   // consumed next iteration
+            wait_done();                           // H1
+            QS_PPOP(0);
+            epilogue_relu(S::A1);
+            signal();
+            QS_PPOP(1);
+            wait_done();                           // H2
+            QS_PPOP(2);
+            epilogue_relu(S::A2);
+            signal();
+            QS_PPOP(3);
+            wait_done();                           // OUT
+            QS_PPOP(4);
+            {
+                float out[16];
+                tmem_ld16(tw, out);
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                if (net == 0) {
+                    const float a[4] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w};
+                    float z[4], logp = 0.f;
+#pragma unroll
+                    for (int k = 0; k < kA; ++k) {
+                        z[k] = (a[k] - (out[k] + sF[S::kB3 + k])) * sF[S::kInvSig + k];
+                        logp += -0.5f * z[k] * z[k] - sF[S::kLogStd + k] - 0.9189385332046727f;
+                    }
+                    const float lr = logp - cur.old_logp;
+                    const float ratio = expf(lr);
+                    const float A = (cur.adv - adv_mean) * adv_istd;
+                    const float lo = 1.0f - hp.clip_range, hi = 1.0f + hp.clip_range;
+                    const float unclipped = A * ratio, clipped = A * fminf(fmaxf(ratio, lo), hi);
+                    const bool inside = ratio >= lo && ratio <= hi;
+                    const bool active = inside || (unclipped < clipped);
+                    const float g = (cur.valid && active) ? -A * ratio : 0.f;
+#pragma unroll
+                    for (int k = 0; k < kA; ++k) {
+                        d[k] = g * z[k] * sF[S::kInvSig + k];
+                        g_b3[k] += d[k];
+                        g_ls[k] += g * (z[k] * z[k] - 1.0f);
+                    }
+                    if (cur.valid) {
+                        st_loss += -fminf(unclipped, clipped);
+                        st_clip += inside ? 0.f : 1.f;
+                        st_kl += (ratio - 1.0f) - lr;
+                        st_n += 1.f;
+                    }
+                } else {
+                    const float err = out[0] + sF[S::kB3] - cur.ret;
+                    d[0] = cur.valid ? 2.0f * hp.vf_coef * err : 0.f;
+                    g_b3[0] += d[0];
+                    if (cur.valid) st_loss += err * err;
+                }
+                *reinterpret_cast<uint4*>(sl + S::DOUT + op_offset(128, tid, 0)) =
+                    make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), 0u, 0u);
+                *reinterpret_cast<uint4*>(sl + S::DOUT + op_offset(128, tid, 1)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            signal();
+            QS_PPOP(5);
+            wait_done();                           // dH2 (and dW3: A2 may be overwritten)
+            QS_PPOP(6);
+            epilogue_mask_inplace(S::A2);          // D2
+            signal();
+            QS_PPOP(7);
+            wait_done();                           // dH1 (and dW2, db2: A1 may be overwritten)
+            QS_PPOP(8);
+            epilogue_mask_inplace(S::A1);          // D1
+            QS_PPOP(9);
+            Sample nxt;
+            gather_wait(j1, nxt);                  // the next tile's rows, copied a whole tile ago
+            QS_PPOP(10);
+            if (it + 1 < iters) write_a0(nxt, S::A0 + ((it + 1) & 1) * 4096);        // next tile's A0, other buffer
+            QS_PPOP(11);
+            gather_async(j2);                      // the staging rows are in registers now: refill them for tile it + 2
+            QS_PPOP(12);
+            signal();                              // dW1 of this tile + H1 of the next one
+            QS_PPOP(13);
+            cur = nxt;
+            j1 = j2;
+        }
+#ifdef QS_PPO_PROFILE
+        if (blockIdx.x < 2 && tid == 0)
+            printf("ppoprof net %d slot %d iters %d: waitH1 %lld | E1 %lld | waitH2 %lld | E2 %lld | waitOUT %lld | loss %lld | wait3 %lld | E4 %lld | wait4 %lld | E5 %lld | gather_wait %lld | write_a0 %lld | gather_async %lld | signal %lld (cycles/tile)\n",
+                   net, slot, iters, prof_[0] / iters, prof_[1] / iters, prof_[2] / iters, prof_[3] / iters, prof_[4] / iters,
+                   prof_[5] / iters, prof_[6] / iters, prof_[7] / iters, prof_[8] / iters, prof_[9] / iters, prof_[10] / iters,
+                   prof_[11] / iters, prof_[12] / iters, prof_[13] / iters);
+#endif
+        wait_done();                               // the last commit: every accumulator is complete
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    // ---- flush ---------------------------------------------------------------------------------------------------------
+    const int P = L.total;
+    float* out = partial + (size_t)cta * partial_stride(P);
+    const float scale = 1.0f / (float)b.n;
+    if (wg == 0) {
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {           // dW2: lane = input feature k, column = output feature n
+            float v[32];
+            tmem_ld32(tmem + lane_off + kQColW2 + (uint32_t)(c * 32), v);
+            float4* d4 = reinterpret_cast<float4*>(out + oW2 + tid * kH + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                d4[q] = make_float4(v[4 * q] * scale, v[4 * q + 1] * scale, v[4 * q + 2] * scale, v[4 * q + 3] * scale);
+        }
+        float v[16];
+        tmem_ld16(tmem + lane_off + kQColW1, v);  // lane = hidden n, column = obs k | 12: bias
+#pragma unroll
+        for (int k = 0; k < kD; ++k) out[oW1 + k * kH + tid] = v[k] * scale;
+        out[ob1 + tid] = v[kD] * scale;
+        tmem_ld16(tmem + lane_off + kQColB2, v);
+        out[ob2 + tid] = v[kD] * scale;
+        tmem_ld16(tmem + lane_off + kQColW3, v);  // lane = hidden k, column = head output
+        if (net == 0) {
+#pragma unroll
+            for (int j = 0; j < kA; ++j) out[L.aW3 + tid * kA + j] = v[j] * scale;
+        } else {
+            out[L.cW3 + tid] = v[0] * scale;
+        }
+    }
+    if (net == 0 && wg == 1) {
+        for (int i = L.mean + tid; i < P; i += kM) out[i] = 0.f;             // the observation normaliser is not trained
+        if (tid < 3) out[P + 5 + tid] = 0.f;
+    }
+    {
+        float r[12] = {g_b3[0], g_b3[1], g_b3[2], g_b3[3], g_ls[0], g_ls[1], g_ls[2], g_ls[3], st_loss, st_clip, st_kl, st_n};
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+        }
+        if (wg < 2 && lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) sRed[(gtid >> 5) * 16 + k] = r[k];
+        }
+        __syncthreads();
+        if (gtid < 12) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += sRed[w * 16 + gtid];
+            if (net == 0) {
+                if (gtid < 4) out[L.ab3 + gtid] = s * scale;
+                // entropy bonus: H = sum_k (0.5 + 0.5 log 2pi + log_std_k) does not depend on the sample; CTA 0 carries it
+                else if (gtid < 8) out[L.log_std + gtid - 4] = s * scale - (cta == 0 ? hp.ent_coef : 0.f);
+                else if (gtid == 8) out[P + 0] = s;
+                else out[P + gtid - 7] = s;                                     // 9 -> clipped (2), 10 -> KL (3), 11 -> n (4)
+            } else {
+                if (gtid == 0) out[L.cb3] = s * scale;
+                else if (gtid == 8) out[P + 1] = s;
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (wg == 2) {
         fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
     }

@@ -442,16 +442,27 @@ int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const floa
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     const int ntiles = nblocks(n, qs::tc::kM);
-    const int grid = ntiles < sms ? ntiles : sms;
     static const int mn_swap = getenv("QS_PPO_MN_SWAP") ? atoi(getenv("QS_PPO_MN_SWAP")) : 0;   // descriptor debug knob
-    QS_CUDA(cudaFuncSetAttribute(qs::ppo::ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qs::ppo::SmemP::TOTAL));
+    static const int use_v1 = getenv("QS_PPO_V1") ? atoi(getenv("QS_PPO_V1")) : 0;              // A/B: the single-tile schedule
     qs::ppo::Batch b{obs, act, old_logp, adv, ret, idx, n};
     qs::ppo::Hyper hp{clip_range, vf_coef, ent_coef, normalize_adv};
-    qs::ppo::ppo_grad_tc_kernel<<<grid, qs::tc::kM, qs::ppo::SmemP::TOTAL, s>>>(b, hp, policy_params, adv_norm, partial, mn_swap);
+    const int P = qs::policy_param_count(*desc);
+    int rows;
+    if (use_v1) {
+        const int grid = ntiles < sms ? ntiles : sms;
+        QS_CUDA(cudaFuncSetAttribute(qs::ppo::ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qs::ppo::SmemP::TOTAL));
+        qs::ppo::ppo_grad_tc_kernel<<<grid, qs::tc::kM, qs::ppo::SmemP::TOTAL, s>>>(b, hp, policy_params, adv_norm, partial, mn_swap);
+        rows = grid;
+    } else {
+        // one network per CTA, two tiles in flight: CTA pairs (actor, critic), at most one CTA per SM
+        const int pairs_needed = (ntiles + 1) / 2, pairs_max = sms / 2;
+        rows = pairs_needed < pairs_max ? pairs_needed : pairs_max;
+        QS_CUDA(cudaFuncSetAttribute(qs::ppo::ppo_grad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qs::ppo::SmemQ::TOTAL));
+        qs::ppo::ppo_grad_tc2_kernel<<<2 * rows, qs::ppo::kThreads2, qs::ppo::SmemQ::TOTAL, s>>>(b, hp, policy_params, adv_norm, partial, mn_swap);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    const int len = qs::policy_param_count(*desc) + qs::ppo::kPartialStats;
-    qs::ppo::ppo_reduce_kernel<<<nblocks(len, 256), 256, 0, s>>>(partial, grid, qs::ppo::partial_stride(len - qs::ppo::kPartialStats),
-                                                                 len, grad);
+    const int len = P + qs::ppo::kPartialStats;
+    qs::ppo::ppo_reduce_kernel<<<nblocks(len, 256), 256, 0, s>>>(partial, rows, qs::ppo::partial_stride(P), len, grad);
     return check_launch("ppo_grad");
 }
 

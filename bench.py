@@ -377,6 +377,33 @@ def main():
             "ms_rollout": ms_roll, "ms_gae": ms_p - ms_roll, "traj_hbm_gbs": (80.0 * nb * Tp) / (ms_roll * 1e-3) / 1e9,
             "policy_tflops_bf16": flop * nb * Tp / (ms_roll * 1e-3) / 1e12,
             "note": "tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), 128-env M tiles, 64 of 148 SMs busy at 8192 envs"}
+        # one full PPO iteration of configs[2] on the device -- tcgen05 rollout (8192 x 1024) -> GAE ->
+        # 4 epochs x 8 minibatches of 2^20 samples through qs_ppo_grad / qs_ppo_adam (one flat NCCL all-reduce of the
+        # 37 033-float gradient + statistics per minibatch when N > 1); train.py:50-68 hyper-parameters
+        from uav_reinforcement_learning_control_b200.parallel import DistContext
+        from uav_reinforcement_learning_control_b200.ppo import PPOConfig, PPOTrainer
+        torch.manual_seed(1234)
+        tr = PPOTrainer(eng_p, PPOConfig(n_steps=Tp, n_epochs=4, num_minibatches=8), ctx=DistContext(rank, world, local, None), seed=0)
+        tr.collect(); tr.update()                                   # warm-up iteration (allocations, NCCL channels)
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record(stream)
+        tr.collect()
+        ev[1].record(stream)
+        tr.update()
+        ev[2].record(stream)
+        barrier()
+        ms_it = max_over_ranks(ev[0].elapsed_time(ev[2])); ms_col = ev[0].elapsed_time(ev[1])
+        n_mb = 4 * 8; mb = nb * Tp // 8
+        line["train_iter"] = {
+            "value": world * nb * Tp / (ms_it * 1e-3), "unit": "env-steps/s incl. PPO update", "num_envs_per_gpu": nb, "T": Tp,
+            "ms_rollout_gae": ms_col, "ms_update": ms_it - ms_col, "minibatches": n_mb, "samples_per_minibatch": mb,
+            "ms_per_minibatch": (ms_it - ms_col) / n_mb,
+            "update_samples_per_s": world * mb * n_mb / ((ms_it - ms_col) * 1e-3),
+            "update_tflops_bf16": 220672.0 * mb * n_mb / ((ms_it - ms_col) * 1e-3) / 1e12,
+            "note": "qs_rollout_policy (tcgen05) + qs_gae + 32 x {qs_ppo_grad (tcgen05 forward + backward, weight gradients "
+                    "in TMEM) + qs_ppo_adam}; includes the per-epoch qs_ppo_permutation shuffle and the statistics read-back"}
+        del tr
         del eng_p
         # the same config in MJX-parity mode: JaxMJXQuadBraxEnv (21-D obs, Episode + AutoReset wrappers), tanh-normal
         # policy, brax GAE -- fp32 FMA path and tcgen05 path

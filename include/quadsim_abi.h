@@ -265,8 +265,13 @@ int qs_gae(int32_t T, int32_t B, const float* reward, const float* value, const 
  * qs_ppo_adam: params -= Adam(clip_by_global_norm(grad * grad_scale, max_grad_norm)) on the trained part of the packed
  * vector (torch.optim.Adam and torch.nn.utils.clip_grad_norm_ semantics; max_grad_norm <= 0: no clipping).  `step` is
  * the 1-based optimiser step; grad_scale = 1 / world_size after a sum all-reduce.  norm_out (optional): pre-clip norm.
+ *
+ * qs_ppo_permutation: out[0..n) (device, int32) = a pseudo-random permutation of 0..n-1 keyed by (seed, epoch) -- the
+ * per-epoch shuffle of SB3's RolloutBuffer.get (np.random.permutation) as a keyed bijection (4-round Feistel network +
+ * cycle walking) evaluated independently per element; slices of it are the `idx` minibatches of qs_ppo_grad.
  */
 int64_t qs_ppo_workspace_bytes(const QsPolicyDesc* desc);
+int qs_ppo_permutation(int32_t n, uint64_t seed, uint32_t epoch, int32_t* out, void* stream);
 int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const float* obs, const float* act,
                 const float* old_logp, const float* adv, const float* ret, const int32_t* idx, int32_t n,
                 float clip_range, float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad,

@@ -132,3 +132,38 @@ def adam_step(params, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-5, max_g
     denom = np.sqrt(v[:n_train]) / np.sqrt(1 - beta2 ** step) + eps
     p[:n_train] -= step_size * m[:n_train] / denom
     return p, m, v, norm
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Minibatch shuffle: keyed Feistel bijection + cycle walking (csrc/qs_ppo.cuh: feistel_index, quadsim.cu:
+# qs_ppo_permutation).  uint32 arithmetic restated with NumPy; bit-exact parity is tested.
+def _mix(x):
+    x = np.asarray(x, dtype=np.uint64) & 0xFFFFFFFF
+    x ^= x >> 16; x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+    x ^= x >> 13; x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def feistel_permutation(n, seed, epoch):
+    """out[i] for i in 0..n-1: SB3's per-epoch ``np.random.permutation`` (RolloutBuffer.get) as a keyed bijection."""
+    bits = 1
+    while bits < 31 and (1 << bits) < n:
+        bits += 1
+    h = max((bits + 1) // 2, 1)
+    mask = (1 << h) - 1
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    k0 = (int(_mix((seed & 0xFFFFFFFF) ^ 0xA511E9B3)) + epoch * 0x9E3779B9) & 0xFFFFFFFF
+    k1 = int(_mix(((seed >> 32) + 0x632BE5AB) & 0xFFFFFFFF)) ^ int(_mix((epoch + 0x85157AF5) & 0xFFFFFFFF))
+    x = np.arange(n, dtype=np.uint64)
+    todo = np.ones(n, dtype=bool)
+    while todo.any():
+        v = x[todo]
+        l, r = v >> h, v & mask
+        for rnd in range(4):
+            f = _mix((r * 0x9E3779B1 + k0 + rnd * 0x7F4A7C15) & 0xFFFFFFFF) ^ _mix((k1 + rnd) & 0xFFFFFFFF)
+            l, r = r, l ^ (f & mask)
+        v = (l << h) | r
+        x[todo] = v
+        todo[todo] = v >= n
+    return x.astype(np.int64)

@@ -87,16 +87,19 @@ def test_hover_vec_env_gym_and_sb3_contracts():
     assert torch.allclose(ob[:, 3:6], torch.zeros(64, 3, device=env.device), atol=1e-6)
 
 
-def test_ppo_trainer_improves_hover_reward():
-    """End-to-end on one GPU: fused rollout -> GAE -> clipped PPO update.  A few iterations must raise the
+@pytest.mark.parametrize("fused", [True, False])
+def test_ppo_trainer_improves_hover_reward(fused):
+    """End-to-end on one GPU: fused rollout -> GAE -> clipped PPO update (fused: qs_ppo_grad / qs_ppo_adam on the packed
+    vector with the tcgen05 rollout; not fused: torch autograd with the fp32 rollout).  A few iterations must raise the
     mean per-step reward of the hover task clearly above the random-policy level."""
     import torch
     from uav_reinforcement_learning_control_b200.engine import Engine
     from uav_reinforcement_learning_control_b200.ppo import PPOConfig, PPOTrainer
     torch.manual_seed(0)
     eng = Engine(Q.EnvConfig.north_star(seed=0), 4096, device=0)
-    tr = PPOTrainer(eng, PPOConfig(n_steps=64, n_epochs=4, num_minibatches=8, learning_rate=1e-3, ent_coef=0.0), seed=0)
-    tr.policy.log_std.data.fill_(-1.0)
+    tr = PPOTrainer(eng, PPOConfig(n_steps=64, n_epochs=4, num_minibatches=8, learning_rate=1e-3, ent_coef=0.0), seed=0,
+                    fused=fused)
+    tr.set_log_std(-1.0)
     log = tr.train(12)
     r0 = np.mean([l["mean_reward"] for l in log[:2]]); r1 = np.mean([l["mean_reward"] for l in log[-2:]])
     assert np.isfinite(r1) and r1 > r0 * 1.15, (r0, r1)

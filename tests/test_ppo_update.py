@@ -111,7 +111,30 @@ def test_bf16_oracle_is_close_to_exact_oracle():
         assert np.abs(a[k] - b[k]).max() < (0.15 if k == "log_std" else 0.03) * scale, k
 
 
+@pytest.mark.parametrize("n", [1, 2, 5, 128, 1000, 4096, 100003])
+def test_oracle_feistel_permutation_is_a_permutation(n):
+    p0 = U.feistel_permutation(n, 1234, 0)
+    assert np.array_equal(np.sort(p0), np.arange(n))
+    if n >= 128:
+        p1 = U.feistel_permutation(n, 1234, 1)
+        assert np.mean(p0 == p1) < 0.05 and np.mean(p0 == np.arange(n)) < 0.05        # epochs differ, no identity
+        assert abs(np.corrcoef(p0, np.arange(n))[0, 1]) < 0.1
+
+
 # ------------------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed,epoch", [(1, 0, 0), (5, 1, 2), (1000, 7, 0), (1 << 20, 99, 3), (8192 * 1024, (5 << 32) + 77, 1),
+                                          (3000001, 123456789012345, 40)])
+def test_fused_permutation_bit_exact(n, seed, epoch):
+    import torch
+    from uav_reinforcement_learning_control_b200.ppo import FusedUpdater
+    up = FusedUpdater("cuda:0")
+    out = up.permutation(n, seed, epoch)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, U.feistel_permutation(n, seed, epoch))                # integer work: bit-exact
+    assert np.array_equal(np.sort(got), np.arange(n))
+
 
 
 def _report(g, g_ref, tol_rel, tol_log_std=None):

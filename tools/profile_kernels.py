@@ -13,7 +13,7 @@ from uav_reinforcement_learning_control_b200 import config as Q
 from uav_reinforcement_learning_control_b200.engine import Engine
 
 dev = torch.device("cuda", 0)
-which = set(sys.argv[1:]) or {"step", "resident", "fma", "tc", "tc_large", "gae", "tc21"}
+which = set(sys.argv[1:]) or {"step", "resident", "fma", "tc", "tc_large", "gae", "tc21", "ppo"}
 
 if {"step", "resident"} & which:
     n = 1 << 20
@@ -60,4 +60,20 @@ if "tc21" in which:
     params = make_policy_params(eng, torch, dev, seed=0, dist=1)
     buf = eng.rollout_policy(st, params, T=T, t0=0, dist=1, first_state=first, tensor_cores=True)
     torch.cuda.synchronize(); del eng
+if "ppo" in which:
+    # two minibatch updates of the configs[2] shape: 2^20 random rows out of 8192 x 1024 samples
+    from uav_reinforcement_learning_control_b200.ppo import ActorCritic, FusedUpdater
+    N = 8192 * 1024; mb = N // 8
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    obs = torch.rand(N, 12, device=dev, generator=g) * 2 - 1
+    act = torch.randn(N, 4, device=dev, generator=g) * 0.4
+    old_logp = torch.randn(N, device=dev, generator=g) * 0.1 - 1.0
+    adv = torch.randn(N, device=dev, generator=g); ret = torch.randn(N, device=dev, generator=g)
+    params = ActorCritic(12, dev, seed=0, log_std_init=-1.0).pack()
+    up = FusedUpdater(dev)
+    perm = torch.randperm(N, device=dev, generator=g).to(torch.int32)
+    for k in range(2):
+        up.grad(params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb], clip_range=0.19, vf_coef=0.5, ent_coef=1e-4)
+        up.adam(params, 1.5e-4)
+    torch.cuda.synchronize()
 print("profile_kernels done")

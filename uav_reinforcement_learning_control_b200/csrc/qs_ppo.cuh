@@ -123,6 +123,11 @@ __device__ __forceinline__ uint32_t pack_relu_bf16_u(uint32_t lo, uint32_t hi) {
     return pack_relu_bf16(__uint_as_float(lo), __uint_as_float(hi));
 }
 
+#ifndef QS_PPO_DYNAMIC_ISSUE
+#define QS_PPO_DYNAMIC_ISSUE 0   /* 1: the issuer serves whichever slot is ready first (-10 % issuer idle time in the phase
+                                    profile, no gain in the measured minibatch time, and the accumulation order -- hence the
+                                    low bits of the gradient -- then depends on timing); 0: fixed order, bitwise reproducible */
+#endif
 #ifdef QS_PPO_PROFILE
 #define QS_PPOP(k) do { const long long c_ = clock64(); prof_[k] += c_ - pc_; pc_ = c_; } while (0)
 #else
@@ -490,6 +495,10 @@ ppo_grad_tc_kernel(Batch b, Hyper hp, const float* __restrict__ params, const fl
 //   * a dedicated issuer thread (warp 8) owns the tensor pipe: workers hand a phase over with fence + mbarrier.arrive
 //     on ready[slot] and wait on done[slot]; the issuer serves the two slots alternately, so one tile's MMAs run under
 //     the other tile's epilogue (ping-pong), and no worker warp ever spends issue slots on tcgen05.mma.
+//   * a gather warp (warp 9) fetches the next tile's minibatch rows (random rows of the rollout buffers) into a small
+//     shared staging area with cp.async, one tile ahead, and hands them over through full / empty mbarriers: the workers
+//     never have a global load outstanding (ptxas parked the epilogues behind such loads: shared scoreboards) nor a
+//     cp.async of their own (their fence.proxy.async would wait for it);
 //   * D2 / D1 are written IN PLACE over relu(H2) / relu(H1) (their only other readers, the dW3 / dW2 MMAs, are
 //     committed before the workers are released), so a slot needs 72 KB of operands.
 struct SmemQ {
@@ -499,14 +508,14 @@ struct SmemQ {
     static constexpr int F32 = SLOT0 + 2 * SLOT_BYTES;
     static constexpr int kB3 = 0, kLogStd = 4, kInvSig = 8, kMean = 12, kInvStd = 24, kNumF = 36;
     static constexpr int RED = F32 + kNumF * 4;               // [8 warps][16]
-    static constexpr int BAR = RED + 8 * 16 * 4;              // ready[2], done[2], tmem slot
+    static constexpr int BAR = RED + 8 * 16 * 4;              // ready[2], done[2], full[2], empty[2], tmem slot
     // per slot: cp.async landing zone for the next tile's gathered rows: obs [128][12] | act [128][4] | 3 x [128] scalars
-    static constexpr int STG = (BAR + 48 + 15) & ~15;
+    static constexpr int STG = (BAR + 80 + 15) & ~15;
     static constexpr int STG_ACT = 128 * 48, STG_SCAL = STG_ACT + 128 * 16, STG_BYTES = STG_SCAL + 3 * 128 * 4;
     static constexpr int TOTAL = STG + 2 * STG_BYTES;
 };
 constexpr uint32_t kQColW = 0 /* + 128 * slot */, kQColW2 = 256, kQColW1 = 384, kQColW3 = 400, kQColB2 = 416;
-constexpr int kThreads2 = 288;
+constexpr int kThreads2 = 320;       // 2 x 128 workers + issuer warp + gather warp
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -534,7 +543,9 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     float* sRed = reinterpret_cast<float*>(smem + S::RED);
     uint64_t* bar_ready = reinterpret_cast<uint64_t*>(smem + S::BAR);
     uint64_t* bar_done = bar_ready + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 32);
+    uint64_t* bar_full = bar_ready + 4;
+    uint64_t* bar_empty = bar_ready + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 64);
 
     // ---- one-time setup: this network's fp32 weights -> bf16 UMMA operands ------------------------------------------
     for (int i = gtid; i < S::WEND / 4; i += kThreads2) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
@@ -554,7 +565,8 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             put(dst[q], 128, n, 13, bv[q] - __bfloat162float(hi));
         }
     }
-    for (int i = gtid; i < kH * kH; i += kThreads2) put(S::W2, 128, i % kH, i / kH, params[oW2 + i]);
+#pragma unroll 8
+    for (int i = gtid; i < kH * kH; i += kThreads2) put(S::W2, 128, i % kH, i / kH, __ldg(params + oW2 + i));   // 8 loads in flight
     if (net == 0) { for (int i = gtid; i < kH * kA; i += kThreads2) put(S::W3, 16, i % kA, i / kA, params[L.aW3 + i]); }
     else          { for (int k = gtid; k < kH; k += kThreads2) put(S::W3, 16, 0, k, params[L.cW3 + k]); }
     if (gtid < kA) {
@@ -566,9 +578,10 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     if (gtid < kD) { sF[S::kMean + gtid] = params[L.mean + gtid]; sF[S::kInvStd + gtid] = params[L.inv_std + gtid]; }
     if (gtid == 0) {
         mbar_init(&bar_ready[0], kM); mbar_init(&bar_ready[1], kM); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
+        mbar_init(&bar_full[0], 32); mbar_init(&bar_full[1], 32); mbar_init(&bar_empty[0], kM); mbar_init(&bar_empty[1], kM);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (wg == 2) {
+    if (warp_id == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -584,7 +597,46 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     float g_b3[kA] = {0.f, 0.f, 0.f, 0.f}, g_ls[kA] = {0.f, 0.f, 0.f, 0.f};
     float st_loss = 0.f, st_clip = 0.f, st_kl = 0.f, st_n = 0.f;
 
-    if (wg == 2) {
+    if (warp_id == 9) {
+        // =============================================== gather warp ===================================================
+        // tile t of slot s: rows (2 (cta + t ncta) + s) 128 .. + 127 of the minibatch, 4 rows per lane
+        uint32_t ph_e[2] = {0u, 0u};
+#pragma unroll 1
+        for (int t = 0; t < iters; ++t) {
+#pragma unroll 1
+            for (int s = 0; s < 2; ++s) {
+                if (t > 0) { mbar_wait(&bar_empty[s], ph_e[s]); ph_e[s] ^= 1u; }       // the workers have read tile t - 1
+                unsigned char* stg = smem + S::STG + s * S::STG_BYTES;
+                const int row0 = (2 * (cta + t * ncta) + s) * kM;
+                int j[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = row0 + q * 32 + lane;
+                    j[q] = r < b.n ? (b.idx ? __ldg(b.idx + r) : r) : -1;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (j[q] < 0) continue;
+                    const int row = q * 32 + lane;
+                    const uint32_t so = smem_u32(stg + row * 48);
+                    const float* o = b.obs + (size_t)j[q] * kD;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(so + c * 16), "l"(o + c * 4) : "memory");
+                    const uint32_t ss = smem_u32(stg + S::STG_SCAL + row * 4);
+                    if (net == 0) {
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(stg + S::STG_ACT + row * 16)), "l"(b.act + (size_t)j[q] * 4) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ss), "l"(b.old_logp + j[q]) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ss + 512), "l"(b.adv + j[q]) : "memory");
+                    } else {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ss + 1024), "l"(b.ret + j[q]) : "memory");
+                    }
+                }
+                // full[s] completes when the copies of all 32 lanes have landed
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&bar_full[s])) : "memory");
+            }
+        }
+    } else if (warp_id == 8) {
         // =============================================== issuer ========================================================
         // the whole warp walks the schedule (uniform control flow); one elected lane issues
         {
@@ -612,10 +664,97 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 }
                 __syncwarp();
             }
+#if QS_PPO_DYNAMIC_ISSUE
+            // After the prologue the two slots are served in whatever order they become ready (a fixed 0,1,0,1 order made
+            // the pipe wait for the slower slot: ~35 % of the issuer's time).  The ready test is done by lane 0 and
+            // broadcast, so control flow stays warp-uniform.
+            int pnext[2] = {1, 1}, itn[2] = {0, 0};
+            uint32_t acc3 = 0u, acc2 = 0u, acc1 = 0u;          // 0 until the first MMA into the dW3 / dW2,db2 / dW1 accumulators
+            int left = 2 * iters * 5;
 #ifdef QS_PPO_PROFILE
             long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             long long pc_ = clock64();
 #endif
+#pragma unroll 1
+            while (left > 0) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (itn[s] >= iters) continue;
+                    uint32_t ok = 0u;
+                    if (lane == 0) {
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                                     : "=r"(ok) : "r"(smem_u32(&bar_ready[s])), "r"(ph[s]) : "memory");
+                    }
+                    ok = __shfl_sync(0xffffffffu, ok, 0);
+                    if (!ok) continue;
+                    ph[s] ^= 1u;
+                    fence_after();
+                    const int phase = pnext[s], it = itn[s];
+                    const int base = S::SLOT0 + s * S::SLOT_BYTES;
+                    const int a0 = base + S::A0 + (it & 1) * 4096, a1 = base + S::A1, a2 = base + S::A2, dout = base + S::DOUT;
+                    const uint32_t tw = tmem + kQColW + (uint32_t)(s * 128);
+                    QS_PPOP(0);
+                    if (elect_one()) {
+                        switch (phase) {
+                        case 1:     // H2 = A1 . W2 + b2
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tw, dk(a1 + j * 4096, 128), dk(S::W2 + j * 4096, 128), id_kk128, j > 0);
+                            mma_bf16(tw, dk(a0, 128), dk(S::B2, 128), id_kk128, 1u);
+                            break;
+                        case 2:     // OUT = A2 . W3
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tw, dk(a2 + j * 4096, 128), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
+                            break;
+                        case 3:     // dH2 = dOUT . W3^T ; dW3 += A2^T . dOUT (must finish before D2 overwrites A2)
+                            mma_bf16(tw, dk(dout, 128), dmn(S::W3, 256u), id_kmn128, 0u);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tmem + kQColW3, dmn(a2 + j * 256, 2048u), dmn(dout + j * 256, 2048u), id_mm16, j > 0 ? 1u : acc3);
+                            break;
+                        case 4:     // dH1 = D2 . W2^T ; dW2 += A1^T . D2 ; db2 += D2^T . A0   (D2 lives in the A2 buffer)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tw, dk(a2 + j * 4096, 128), dmn(S::W2 + j * 256, 2048u), id_kmn128, j > 0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tmem + kQColW2, dmn(a1 + j * 256, 2048u), dmn(a2 + j * 256, 2048u), id_mm128, j > 0 ? 1u : acc2);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tmem + kQColB2, dmn(a2 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : acc2);
+                            break;
+                        default:    // dW1^T | db1 += D1^T . A0 (D1 lives in the A1 buffer), then H1 of the slot's NEXT tile,
+                                    // whose A0 the workers wrote into the other A0 buffer together with D1
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mma_bf16(tmem + kQColW1, dmn(a1 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : acc1);
+                            if (it + 1 < iters)
+                                mma_bf16(tw, dk(base + S::A0 + ((it + 1) & 1) * 4096, 128), dk(S::W1, 128), id_kk128, 0u);
+                            break;
+                        }
+                        mma_commit(&bar_done[s]);
+                    }
+                    __syncwarp();
+                    if (phase == 3) acc3 = 1u; else if (phase == 4) acc2 = 1u; else if (phase == 5) acc1 = 1u;
+                    if (++pnext[s] == 6) { pnext[s] = 1; ++itn[s]; }
+                    --left;
+                    QS_PPOP(1);
+                }
+                QS_PPOP(2);
+            }
+#ifdef QS_PPO_PROFILE
+            if (blockIdx.x < 2 && lane == 0)
+                printf("ppoprof net %d issuer (cycles per iteration of 2 tiles): issuing %lld | polling %lld\n",
+                       net, prof_[1] / iters, (prof_[0] + prof_[2]) / iters);
+#endif
+#else
+#ifdef QS_PPO_PROFILE
+            long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            long long pc_ = clock64();
+#endif
+            // fixed service order slot 0, slot 1, slot 0, ...: the accumulation order into the gradient accumulators is
+            // then the same in every run, i.e. the gradient is bitwise reproducible
 #pragma unroll 1
             for (int it = 0; it < iters; ++it) {
 #pragma unroll 1
@@ -628,7 +767,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                         const uint32_t first = (it == 0 && s == 0) ? 0u : 1u;
                         mbar_wait(&bar_ready[s], ph[s]); ph[s] ^= 1u;
                         fence_after();
-                        QS_PPOP(phase);
+                        QS_PPOP(0);
                         if (elect_one()) {
                         switch (phase) {
                         case 1:     // H2 = A1 . W2 + b2
@@ -671,15 +810,15 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                         mma_commit(&bar_done[s]);
                         }
                         __syncwarp();
-                        QS_PPOP(5 + phase);
+                        QS_PPOP(1);
                     }
                 }
             }
 #ifdef QS_PPO_PROFILE
             if (blockIdx.x < 2 && lane == 0)
-                printf("ppoprof net %d issuer (cycles per iteration of 2 tiles) wait-ready p1..p5: %lld %lld %lld %lld %lld | issue p1..p5: %lld %lld %lld %lld %lld\n",
-                       net, prof_[1] / iters, prof_[2] / iters, prof_[3] / iters, prof_[4] / iters, prof_[5] / iters,
-                       prof_[6] / iters, prof_[7] / iters, prof_[8] / iters, prof_[9] / iters, prof_[10] / iters);
+                printf("ppoprof net %d issuer (cycles per iteration of 2 tiles): issuing %lld | waiting for ready %lld\n",
+                       net, prof_[1] / iters, prof_[0] / iters);
+#endif
 #endif
         }
     } else {
@@ -734,37 +873,12 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 if (c + 1 < 4) tmem_ld_wait(r[(c + 1) & 1]);
             }
         };
-        // row of this thread's sample in tile `tile` (-1: padding row of a ragged / out-of-range tile)
-        auto row_of = [&](int tile) -> int {
-            const int r = tile * kM + tid;
-            if (r >= b.n) return -1;
-            return b.idx ? __ldg(b.idx + r) : r;
-        };
-        // The gathered rows of the NEXT tile travel global -> shared with cp.async (no registers, no scoreboard: a
-        // register prefetch across the tile made ptxas park the epilogues behind the outstanding gathers, ~2.5 k cycles
-        // per tile).  Every thread copies, waits for and reads only its own row, so no barrier is involved.
+        // this tile's rows arrive through the gather warp's staging area (full / empty mbarriers)
         unsigned char* stg = smem + S::STG + slot * S::STG_BYTES;
-        auto gather_async = [&](int j) {
-            if (j >= 0) {
-                const uint32_t so = smem_u32(stg + tid * 48);
-                const float* o = b.obs + (size_t)j * kD;
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(so + q * 16), "l"(o + q * 4) : "memory");
-                const uint32_t ss = smem_u32(stg + S::STG_SCAL + tid * 4);
-                if (net == 0) {
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(stg + S::STG_ACT + tid * 16)), "l"(b.act + (size_t)j * 4) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ss), "l"(b.old_logp + j) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ss + 512), "l"(b.adv + j) : "memory");
-                } else {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ss + 1024), "l"(b.ret + j) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        auto gather_wait = [&](int j, Sample& s) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            s.valid = j >= 0;
+        uint32_t ph_f = 0u;
+        auto take_rows = [&](int tile, Sample& s) {
+            mbar_wait(&bar_full[slot], ph_f); ph_f ^= 1u;
+            s.valid = tile * kM + tid < b.n;
             s.o0 = s.o1 = s.o2 = s.a = make_float4(0.f, 0.f, 0.f, 0.f);
             s.old_logp = 0.f; s.adv = 0.f; s.ret = 0.f;
             if (s.valid) {
@@ -778,15 +892,21 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                     s.ret = sc[256];
                 }
             }
+            mbar_arrive(&bar_empty[slot]);          // (values are in registers: the loads above have completed? see below)
         };
         auto write_a0 = [&](const Sample& sm, int a0) {
             // bf16 normalised observation, constant 1 in K slots 12 / 13 (0 for the padding rows of a ragged tile)
             const float o[kD] = {sm.o0.x, sm.o0.y, sm.o0.z, sm.o0.w, sm.o1.x, sm.o1.y, sm.o1.z, sm.o1.w,
                                  sm.o2.x, sm.o2.y, sm.o2.z, sm.o2.w};
+            const float4* m4 = reinterpret_cast<const float4*>(sF + S::kMean);        // 6 x LDS.128: mean | inv_std
+            const float4 m0 = m4[0], m1 = m4[1], m2 = m4[2], i0 = m4[3], i1 = m4[4], i2 = m4[5];
+            const float mu[kD] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w};
+            const float is[kD] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w};
+            const float one = sm.valid ? 1.0f : 0.f;
             float x[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                x[k] = !sm.valid ? 0.f : (k < kD ? (o[k] - sF[S::kMean + k]) * sF[S::kInvStd + k] : (k < kD + 2 ? 1.0f : 0.f));
+            for (int k = 0; k < kD; ++k) x[k] = (o[k] - mu[k]) * is[k] * one;          // rows of padding samples are zero
+            x[12] = one; x[13] = one; x[14] = 0.f; x[15] = 0.f;
 #pragma unroll
             for (int c = 0; c < 2; ++c)
                 *reinterpret_cast<uint4*>(sl + a0 + op_offset(128, tid, c)) =
@@ -794,13 +914,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                                pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
         };
         Sample cur;
-        {
-            const int j0 = row_of(2 * cta + slot);
-            gather_async(j0);
-            gather_wait(j0, cur);
-        }
-        int j1 = iters > 1 ? row_of(2 * (cta + ncta) + slot) : -1;      // row index one tile ahead
-        gather_async(j1);
+        take_rows(2 * cta + slot, cur);
         write_a0(cur, S::A0);
         signal();
 #ifdef QS_PPO_PROFILE
@@ -809,7 +923,6 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
 #endif
 #pragma unroll 1
         for (int it = 0; it < iters; ++it) {
-            const int j2 = it + 2 < iters ? row_of(2 * (cta + (it + 2) * ncta) + slot) : -1;   // consumed next iteration
             wait_done();                           // H1
             QS_PPOP(0);
             epilogue_relu(S::A1);
@@ -875,17 +988,17 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             QS_PPOP(8);
             epilogue_mask_inplace(S::A1);          // D1
             QS_PPOP(9);
-            Sample nxt;
-            gather_wait(j1, nxt);                  // the next tile's rows, copied a whole tile ago
-            QS_PPOP(10);
-            if (it + 1 < iters) write_a0(nxt, S::A0 + ((it + 1) & 1) * 4096);        // next tile's A0, other buffer
+            Sample nxt = cur;
+            if (it + 1 < iters) {
+                take_rows(2 * (cta + (it + 1) * ncta) + slot, nxt);                   // copied a whole tile ago
+                QS_PPOP(10);
+                write_a0(nxt, S::A0 + ((it + 1) & 1) * 4096);                         // next tile's A0, other buffer
+            }
             QS_PPOP(11);
-            gather_async(j2);                      // the staging rows are in registers now: refill them for tile it + 2
             QS_PPOP(12);
             signal();                              // dW1 of this tile + H1 of the next one
             QS_PPOP(13);
             cur = nxt;
-            j1 = j2;
         }
 #ifdef QS_PPO_PROFILE
         if (blockIdx.x < 2 && tid == 0)
@@ -964,10 +1077,41 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     }
     fence_before();
     __syncthreads();
-    if (wg == 2) {
+    if (warp_id == 8) {
         fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Minibatch shuffling (SB3 RolloutBuffer.get: one random permutation of the N rollout rows per epoch).  Instead of a
+// sort-based randperm (~1 ms for 2^23 rows) every index is computed independently: a keyed 4-round balanced Feistel
+// network is a bijection of [0, 4^h) (h = ceil(bits(N) / 2)), and cycle-walking it (re-encrypt until the value is < N)
+// restricts it to a bijection of [0, N) -- a pseudo-random permutation evaluated in O(1) per element, memory-bound
+// (4 B written per row).  Integer arithmetic only: bit-exact against oracle/ppo_update_ref.py: feistel_permutation.
+__host__ __device__ inline uint32_t perm_mix(uint32_t x) {          // murmur3 finaliser
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ inline uint32_t feistel_index(uint32_t i, uint32_t n, int half_bits, uint32_t k0, uint32_t k1) {
+    const uint32_t mask = (1u << half_bits) - 1u;
+    uint32_t x = i;
+    do {
+        uint32_t l = x >> half_bits, r = x & mask;
+#pragma unroll
+        for (uint32_t round = 0; round < 4; ++round) {
+            const uint32_t f = perm_mix(r * 0x9E3779B1u + k0 + round * 0x7F4A7C15u) ^ perm_mix(k1 + round);
+            const uint32_t t = l ^ (f & mask);
+            l = r; r = t;
+        }
+        x = (l << half_bits) | r;
+    } while (x >= n);
+    return x;
+}
+__global__ void __launch_bounds__(256)
+ppo_permutation_kernel(uint32_t n, int half_bits, uint32_t k0, uint32_t k1, int32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n) out[i] = (int32_t)feistel_index(i, n, half_bits, k0, k1);
 }
 
 // grad[e] = sum over CTAs of partial[c][e], fixed order (bitwise reproducible); e < len

@@ -466,6 +466,17 @@ int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const floa
     return check_launch("ppo_grad");
 }
 
+int qs_ppo_permutation(int32_t n, uint64_t seed, uint32_t epoch, int32_t* out, void* stream) {
+    if (n <= 0 || !out) return fail(QS_EINVAL, "qs_ppo_permutation: bad argument");
+    int bits = 1;
+    while (bits < 31 && (1u << bits) < (uint32_t)n) ++bits;
+    const int half_bits = (bits + 1) / 2 < 1 ? 1 : (bits + 1) / 2;
+    const uint32_t k0 = qs::ppo::perm_mix((uint32_t)seed ^ 0xA511E9B3u) + epoch * 0x9E3779B9u;
+    const uint32_t k1 = qs::ppo::perm_mix((uint32_t)(seed >> 32) + 0x632BE5ABu) ^ qs::ppo::perm_mix(epoch + 0x85157AF5u);
+    qs::ppo::ppo_permutation_kernel<<<nblocks(n, 256), 256, 0, (cudaStream_t)stream>>>((uint32_t)n, half_bits, k0, k1, out);
+    return check_launch("ppo_permutation_kernel");
+}
+
 int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* grad, float* m, float* v, int32_t step,
                 float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, float* norm_out,
                 void* stream) {

@@ -48,6 +48,7 @@ _EXPORTS = {
     "qs_ppo_workspace_bytes": (C.c_int64, [C.POINTER(Q.QsPolicyDesc)]),
     "qs_ppo_grad": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 7
                     + [C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32] + [C.c_void_p] * 3),
+    "qs_ppo_permutation": (C.c_int, [C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "qs_ppo_adam": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_float] * 6
                     + [C.c_void_p] * 2),
 }

@@ -156,6 +156,17 @@ class FusedUpdater:
                         "qs_ppo_grad")
         return self.grad_buf
 
+    def permutation(self, n: int, seed: int, epoch: int, out=None):
+        """int32 [n] pseudo-random permutation of 0..n-1 keyed by (seed, epoch) (qs_ppo_permutation): the per-epoch shuffle
+        of SB3's RolloutBuffer.get computed element-wise on the device instead of a sort-based randperm."""
+        torch = self.torch
+        if out is None or out.numel() != n:
+            out = torch.empty(n, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.qs_ppo_permutation(int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF,
+                                                    self.C.c_void_p(out.data_ptr()), self._stream()), "qs_ppo_permutation")
+        return out
+
     def adam(self, params, lr, max_grad_norm=0.5, grad_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-5, grad=None):
         """clip_grad_norm_ + Adam step on ``params`` in place, from ``self.grad_buf`` (after any all-reduce)."""
         self.step += 1
@@ -186,6 +197,8 @@ class PPOTrainer:
         self.tensor_cores = self.fused if tensor_cores is None else bool(tensor_cores)
         self.params = self.policy.pack() if self.fused else None                 # fused: THE master copy of the weights
         self.updater = FusedUpdater(engine.device, engine.obs_dim) if self.fused else None
+        self.shuffle_seed = (int(seed) << 20) ^ (0x5EED + 7919 * self.ctx.rank)     # every rank shuffles its own rows
+        self._epochs_done = 0
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
         self.state = engine.new_state()
         engine.reset(self.state)
@@ -219,7 +232,8 @@ class PPOTrainer:
         acc = torch.zeros(up.N_STATS, dtype=torch.float32, device=obs.device)
         world = self.ctx.world
         for _ in range(c.n_epochs):
-            perm = torch.randperm(N, device=obs.device).to(torch.int32)
+            self._perm = perm = up.permutation(N, self.shuffle_seed, self._epochs_done, out=getattr(self, "_perm", None))
+            self._epochs_done += 1
             for k in range(c.num_minibatches):
                 g = up.grad(self.params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb],
                             clip_range=c.clip_range, vf_coef=c.vf_coef, ent_coef=c.ent_coef,

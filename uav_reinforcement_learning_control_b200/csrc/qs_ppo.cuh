@@ -1093,14 +1093,15 @@ __host__ __device__ inline uint32_t perm_mix(uint32_t x) {          // murmur3 f
     x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
     return x;
 }
-__host__ __device__ inline uint32_t feistel_index(uint32_t i, uint32_t n, int half_bits, uint32_t k0, uint32_t k1) {
+struct PermKeys { uint32_t k0; uint32_t rk[4]; };      // rk[round] = perm_mix(k1 + round), hoisted out of the kernel
+__host__ __device__ inline uint32_t feistel_index(uint32_t i, uint32_t n, int half_bits, const PermKeys& K) {
     const uint32_t mask = (1u << half_bits) - 1u;
     uint32_t x = i;
     do {
         uint32_t l = x >> half_bits, r = x & mask;
 #pragma unroll
         for (uint32_t round = 0; round < 4; ++round) {
-            const uint32_t f = perm_mix(r * 0x9E3779B1u + k0 + round * 0x7F4A7C15u) ^ perm_mix(k1 + round);
+            const uint32_t f = perm_mix(r * 0x9E3779B1u + K.k0 + round * 0x7F4A7C15u) ^ K.rk[round];
             const uint32_t t = l ^ (f & mask);
             l = r; r = t;
         }
@@ -1109,9 +1110,9 @@ __host__ __device__ inline uint32_t feistel_index(uint32_t i, uint32_t n, int ha
     return x;
 }
 __global__ void __launch_bounds__(256)
-ppo_permutation_kernel(uint32_t n, int half_bits, uint32_t k0, uint32_t k1, int32_t* __restrict__ out) {
+ppo_permutation_kernel(uint32_t n, int half_bits, PermKeys K, int32_t* __restrict__ out) {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i < n) out[i] = (int32_t)feistel_index(i, n, half_bits, k0, k1);
+    if (i < n) out[i] = (int32_t)feistel_index(i, n, half_bits, K);
 }
 
 // grad[e] = sum over CTAs of partial[c][e], fixed order (bitwise reproducible); e < len
@@ -1174,13 +1175,28 @@ struct AdamArgs {
 // One CTA: global gradient norm (torch clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))) and the torch.optim.Adam
 // step on the packed parameter vector (train.py:50-68 uses SB3's default optimiser: Adam, eps 1e-5, no weight decay).
 // norm_out (optional): the pre-clip norm.
+constexpr int kAdamPerThread = 40;        // 1024 threads x 40 >= the trained part of any supported policy (<= 40 960 floats)
+// grid = ceil(n_train / 1024) CTAs.  Every CTA computes the global norm itself (the whole gradient is 150 KB: 40 loads in
+// flight per thread, identical summation order in every CTA, no grid-wide synchronisation) and then updates its own 1024
+// parameters.  A single CTA doing both passes with dependent trips to L2 took 43 us.
 __global__ void __launch_bounds__(1024)
 ppo_adam_kernel(AdamArgs a, float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m,
                 float* __restrict__ v, float* __restrict__ norm_out) {
     __shared__ double sh[32];
     __shared__ float coef_s;
+    float g[kAdamPerThread];
+#pragma unroll
+    for (int k = 0; k < kAdamPerThread; ++k) {
+        const int i = threadIdx.x + k * 1024;
+        g[k] = i < a.n_train ? __ldg(grad + i) * a.grad_scale : 0.f;
+    }
+    const int mine = blockIdx.x * 1024 + threadIdx.x;
+    const bool ok = mine < a.n_train;
+    const float mi0 = ok ? m[mine] : 0.f, vi0 = ok ? v[mine] : 0.f, p0 = ok ? params[mine] : 0.f;
+    const float gmine = ok ? __ldg(grad + mine) * a.grad_scale : 0.f;
     double ss = 0.0;
-    for (int i = threadIdx.x; i < a.n_train; i += 1024) { const double g = (double)(grad[i] * a.grad_scale); ss += g * g; }
+#pragma unroll
+    for (int k = 0; k < kAdamPerThread; ++k) ss += (double)g[k] * (double)g[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
@@ -1189,20 +1205,18 @@ ppo_adam_kernel(AdamArgs a, float* __restrict__ params, const float* __restrict_
         double t = 0.0;
         for (int w = 0; w < 32; ++w) t += sh[w];
         const float norm = (float)sqrt(t);
-        if (norm_out) *norm_out = norm;
+        if (norm_out && blockIdx.x == 0) *norm_out = norm;
         float coef = 1.0f;
         if (a.max_grad_norm > 0.f) coef = fminf(1.0f, a.max_grad_norm / (norm + 1e-6f));
-        coef_s = coef * a.grad_scale;
+        coef_s = coef;
     }
     __syncthreads();
-    const float coef = coef_s;
-    const float step = a.lr / a.bias1, rb2 = rsqrtf(a.bias2);
-    for (int i = threadIdx.x; i < a.n_train; i += 1024) {
-        const float g = grad[i] * coef;
-        const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * g;
-        const float vi = a.beta2 * v[i] + (1.0f - a.beta2) * g * g;
-        m[i] = mi; v[i] = vi;
-        params[i] -= step * mi / (sqrtf(vi) * rb2 + a.eps);
+    if (ok) {
+        const float gi = gmine * coef_s;
+        const float mi = a.beta1 * mi0 + (1.0f - a.beta1) * gi;
+        const float vi = a.beta2 * vi0 + (1.0f - a.beta2) * gi * gi;
+        m[mine] = mi; v[mine] = vi;
+        params[mine] = p0 - (a.lr / a.bias1) * mi / (sqrtf(vi) * rsqrtf(a.bias2) + a.eps);
     }
 }
 

@@ -473,7 +473,10 @@ int qs_ppo_permutation(int32_t n, uint64_t seed, uint32_t epoch, int32_t* out, v
     const int half_bits = (bits + 1) / 2 < 1 ? 1 : (bits + 1) / 2;
     const uint32_t k0 = qs::ppo::perm_mix((uint32_t)seed ^ 0xA511E9B3u) + epoch * 0x9E3779B9u;
     const uint32_t k1 = qs::ppo::perm_mix((uint32_t)(seed >> 32) + 0x632BE5ABu) ^ qs::ppo::perm_mix(epoch + 0x85157AF5u);
-    qs::ppo::ppo_permutation_kernel<<<nblocks(n, 256), 256, 0, (cudaStream_t)stream>>>((uint32_t)n, half_bits, k0, k1, out);
+    qs::ppo::PermKeys K;
+    K.k0 = k0;
+    for (uint32_t r = 0; r < 4; ++r) K.rk[r] = qs::ppo::perm_mix(k1 + r);
+    qs::ppo::ppo_permutation_kernel<<<nblocks(n, 256), 256, 0, (cudaStream_t)stream>>>((uint32_t)n, half_bits, K, out);
     return check_launch("ppo_permutation_kernel");
 }
 
@@ -488,7 +491,8 @@ int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* gra
     a.bias1 = (float)(1.0 - pow((double)beta1, (double)step));
     a.bias2 = (float)(1.0 - pow((double)beta2, (double)step));
     a.n_train = L.mean;
-    qs::ppo::ppo_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, policy_params, grad, m, v, norm_out);
+    if (a.n_train > qs::ppo::kAdamPerThread * 1024) return fail(QS_EUNSUPPORTED, "qs_ppo_adam: policy too large for the single-CTA optimiser step");
+    qs::ppo::ppo_adam_kernel<<<nblocks(a.n_train, 1024), 1024, 0, (cudaStream_t)stream>>>(a, policy_params, grad, m, v, norm_out);
     return check_launch("ppo_adam_kernel");
 }
 

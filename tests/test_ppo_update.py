@@ -272,3 +272,43 @@ def test_trainer_fused_improves_reward():
     assert np.isfinite(log[-1]["mean_reward"]) and np.isfinite(log[-1]["pg_loss"])
     assert log[-1]["mean_reward"] > log[0]["mean_reward"]
     assert 0.0 <= log[-1]["clip_frac"] <= 1.0
+
+
+@pytest.mark.gpu
+def test_fused_update_respects_buffer_bounds():
+    """compute-sanitizer is closed on the GPU pool, so bounds are checked by hand: every buffer the kernels write
+    (workspace, gradient, Adam moments, parameters) is carved out of a canary-filled arena and the canaries must survive
+    a ragged multi-tile update; the read-only inputs are exactly sized, so an out-of-range gather would fault."""
+    import torch
+    from uav_reinforcement_learning_control_b200.ppo import FusedUpdater
+    params = _policy(8)
+    N = 33333
+    batch = _batch(params, N, 12)
+    dev = [torch.from_numpy(b).cuda() for b in batch]
+    up = FusedUpdater("cuda:0")
+    P, G = up.P, 4096                                        # G = guard floats between the carved buffers
+    ws_floats = (up.workspace.numel() + 3) // 4
+    sizes = {"ws": ws_floats, "grad": P + up.N_STATS, "m": P, "v": P, "params": P}
+    canary = 1234567.0
+    total = sum((n + G + 63) // 64 * 64 for n in sizes.values()) + G
+    arena = torch.full((total,), canary, dtype=torch.float32, device="cuda")
+    views, o = {}, G
+    for k, n in sizes.items():
+        views[k] = arena[o:o + n]
+        o += (n + G + 63) // 64 * 64
+    views["ws"].zero_(); views["grad"].zero_(); views["m"].zero_(); views["v"].zero_()
+    views["params"].copy_(torch.from_numpy(params).cuda())
+    up.workspace = views["ws"].view(torch.uint8)[:up.workspace.numel()]
+    up.grad_buf, up.m, up.v = views["grad"], views["m"], views["v"]
+    idx = up.permutation(N, 3, 0)[:20001].contiguous()
+    for _ in range(2):
+        up.grad(views["params"], *dev, idx=idx, clip_range=CLIP, vf_coef=VF, ent_coef=ENT)
+        up.adam(views["params"], lr=1e-3)
+    torch.cuda.synchronize()
+    mask = torch.ones(total, dtype=torch.bool, device="cuda")
+    o = G
+    for k, n in sizes.items():
+        mask[o:o + n] = False
+        o += (n + G + 63) // 64 * 64
+    assert bool((arena[mask] == canary).all()), "a PPO kernel wrote outside its buffers"
+    assert torch.isfinite(views["params"]).all() and torch.isfinite(views["grad"]).all()

@@ -446,6 +446,45 @@ def main():
                          ("policy_tflops_bf16" if tcf else "policy_tflops_fp32"): flop * nb2 * T2 / (ms_q * 1e-3) / 1e12,
                          "traj_hbm_gbs": (80.0 * nb2 * T2) / (ms_q * 1e-3) / 1e9}
         del eng_q, bufq
+        # BASELINE.json configs[3]: circle / figure-8 / square waypoint tracking (utils/trajectories.py tables, evaluate.py's
+        # advance rule and lap reset fused in the step), 262 144 envs, policy rollout on tcgen05
+        from uav_reinforcement_learning_control_b200 import trajectories as TJ
+        cfg_w = Q.EnvConfig.waypoint_eval(TJ.default_tables(0.5), auto_reset=Q.RESET_RESAMPLE, seed=4, env_id_offset=rank * nb2)
+        eng_w = Engine(cfg_w, nb2, device=local)
+        st_w = eng_w.new_state()
+        eng_w.reset(st_w)
+        bufw = eng_w.rollout_policy(st_w, params, T=T2, t0=0, dist=0, tensor_cores=True)
+        barrier()
+        e0.record(stream)
+        eng_w.rollout_policy(st_w, params, T=T2, t0=T2, dist=0, buffers=bufw, tensor_cores=True)
+        e1.record(stream)
+        barrier()
+        ms_w = max_over_ranks(e0.elapsed_time(e1))
+        line["rollout_waypoint_tc"] = {"value": world * nb2 * T2 / (ms_w * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb2, "T": T2,
+                                       "waypoints_reached": sum_over_ranks(st_w[29].view(torch.int32).sum().item()),
+                                       "note": "waypoint tables circle / eight / square (13 / 13 / 12 points), reach radius 0.25, battery sag on"}
+        del eng_w, bufw
+        # BASELINE.json configs[4], this GPU's shard: 2^20 envs x 128 steps per PPO iteration (8 M envs across 8 GPUs), the
+        # 37 033-float gradient all-reduce per minibatch being the only NCCL traffic
+        nb3, T3 = 1 << 20, 128
+        eng_s = Engine(Q.EnvConfig.north_star(seed=5, env_id_offset=rank * nb3), nb3, device=local)
+        trs = PPOTrainer(eng_s, PPOConfig(n_steps=T3, n_epochs=4, num_minibatches=8), ctx=DistContext(rank, world, local, None), seed=0)
+        trs.collect(); trs.update()
+        barrier()
+        ev[0].record(stream)
+        trs.collect()
+        ev[1].record(stream)
+        trs.update()
+        ev[2].record(stream)
+        barrier()
+        ms_s = max_over_ranks(ev[0].elapsed_time(ev[2])); ms_sc = ev[0].elapsed_time(ev[1])
+        line["sharded_ppo"] = {"value": world * nb3 * T3 / (ms_s * 1e-3), "unit": "env-steps/s incl. PPO update",
+                               "num_envs_per_gpu": nb3, "global_envs": world * nb3, "T": T3, "ms_rollout_gae": ms_sc,
+                               "ms_update": ms_s - ms_sc, "samples_per_minibatch": nb3 * T3 // 8,
+                               "update_samples_per_s": world * nb3 * T3 * 4 / ((ms_s - ms_sc) * 1e-3),
+                               "collectives_per_iteration": 32 if world > 1 else 0}
+        del trs, eng_s
+        torch.cuda.empty_cache()
         if rank == 0:
             cb, _, _ = cpu_baseline(Q.EnvConfig.north_star(seed=0), target_seconds=args.cpu_seconds)
             line["cpu_baseline"] = cb

@@ -526,15 +526,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-// partial: [gridDim.x / 2][partial_stride(P)]; row r = actor CTA 2r (its network's entries, log_std, statistics 0 2 3 4)
-// and critic CTA 2r + 1 (its entries, statistic 1)
+// partial: [max(n_actor, n_critic)][partial_stride(P)]; row r = actor CTA r (its network's entries, log_std, the
+// untrained tail, statistics 0 2 3 4) and critic CTA r (its entries, statistic 1)
 __global__ void __launch_bounds__(kThreads2, 1)
 ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const float* __restrict__ adv_norm,
-                    float* __restrict__ partial, int mn_swap) {
+                    float* __restrict__ partial, int n_actor) {
     using S = SmemQ;
     extern __shared__ __align__(1024) unsigned char smem[];
     const PolicyLayout L = policy_layout(kD, 0);
-    const int net = blockIdx.x & 1, cta = blockIdx.x >> 1, ncta = gridDim.x >> 1;
+    // the first n_actor CTAs own the actor, the rest the critic (the actor's tiles cost ~13 % more: loss math, more
+    // gathered columns, so it gets ~53 % of the SMs); every CTA walks over all tiles with its network's stride
+    const int net = (int)blockIdx.x >= n_actor ? 1 : 0;
+    const int cta = net ? (int)blockIdx.x - n_actor : (int)blockIdx.x, ncta = net ? (int)gridDim.x - n_actor : n_actor;
     // warp-uniform role index (the shuffle makes the uniformity visible to ptxas: the issuer warp's descriptors then live
     // in uniform registers and its tcgen05.mma need no per-lane election loops)
     const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -646,7 +649,6 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             const uint64_t dMN2048 = make_desc(sb, 128u, 2048u), dMN256 = make_desc(sb, 128u, 256u);
             auto dk = [&](int off, int rows) { return (rows == 128 ? dK128 : dK16) + (uint64_t)(off >> 4); };
             auto dmn = [&](int off, uint32_t grp_stride) { return (grp_stride == 2048u ? dMN2048 : dMN256) + (uint64_t)(off >> 4); };
-            (void)mn_swap;
             const uint32_t id_kk128 = idesc_mn(128, 128, 0, 0), id_kk16 = idesc_mn(128, 16, 0, 0);
             const uint32_t id_kmn128 = idesc_mn(128, 128, 0, 1);
             const uint32_t id_mm128 = idesc_mn(128, 128, 1, 1), id_mm16 = idesc_mn(128, 16, 1, 1);
@@ -744,7 +746,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 QS_PPOP(2);
             }
 #ifdef QS_PPO_PROFILE
-            if (blockIdx.x < 2 && lane == 0)
+            if (cta == 0 && lane == 0)
                 printf("ppoprof net %d issuer (cycles per iteration of 2 tiles): issuing %lld | polling %lld\n",
                        net, prof_[1] / iters, (prof_[0] + prof_[2]) / iters);
 #endif
@@ -815,7 +817,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 }
             }
 #ifdef QS_PPO_PROFILE
-            if (blockIdx.x < 2 && lane == 0)
+            if (cta == 0 && lane == 0)
                 printf("ppoprof net %d issuer (cycles per iteration of 2 tiles): issuing %lld | waiting for ready %lld\n",
                        net, prof_[1] / iters, prof_[0] / iters);
 #endif
@@ -1001,7 +1003,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             cur = nxt;
         }
 #ifdef QS_PPO_PROFILE
-        if (blockIdx.x < 2 && tid == 0)
+        if (cta == 0 && tid == 0)
             printf("ppoprof net %d slot %d iters %d: waitH1 %lld | E1 %lld | waitH2 %lld | E2 %lld | waitOUT %lld | loss %lld | wait3 %lld | E4 %lld | wait4 %lld | E5 %lld | gather_wait %lld | write_a0 %lld | gather_async %lld | signal %lld (cycles/tile)\n",
                    net, slot, iters, prof_[0] / iters, prof_[1] / iters, prof_[2] / iters, prof_[3] / iters, prof_[4] / iters,
                    prof_[5] / iters, prof_[6] / iters, prof_[7] / iters, prof_[8] / iters, prof_[9] / iters, prof_[10] / iters,
@@ -1117,9 +1119,12 @@ ppo_permutation_kernel(uint32_t n, int half_bits, PermKeys K, int32_t* __restric
 
 // grad[e] = sum over CTAs of partial[c][e], fixed order (bitwise reproducible); e < len
 __global__ void __launch_bounds__(256)
-ppo_reduce_kernel(const float* __restrict__ partial, int rows, int stride, int len, float* __restrict__ grad) {
+ppo_reduce_kernel(const float* __restrict__ partial, int rows_a, int rows_c, int crit_lo, int crit_hi, int crit_stat,
+                  int stride, int len, float* __restrict__ grad) {
+    // entries [crit_lo, crit_hi) and crit_stat were written by the rows_c critic CTAs, everything else by the rows_a actor CTAs
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e >= len) return;
+    const int rows = ((e >= crit_lo && e < crit_hi) || e == crit_stat) ? rows_c : rows_a;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int r = 0;
     for (; r + 4 <= rows; r += 4) {

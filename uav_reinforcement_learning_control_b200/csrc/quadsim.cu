@@ -447,22 +447,27 @@ int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const floa
     qs::ppo::Batch b{obs, act, old_logp, adv, ret, idx, n};
     qs::ppo::Hyper hp{clip_range, vf_coef, ent_coef, normalize_adv};
     const int P = qs::policy_param_count(*desc);
-    int rows;
+    const qs::PolicyLayout L = qs::policy_layout(desc->obs_dim, desc->dist);
+    const int len = P + qs::ppo::kPartialStats;
+    int rows_a, rows_c;
     if (use_v1) {
         const int grid = ntiles < sms ? ntiles : sms;
         QS_CUDA(cudaFuncSetAttribute(qs::ppo::ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qs::ppo::SmemP::TOTAL));
         qs::ppo::ppo_grad_tc_kernel<<<grid, qs::tc::kM, qs::ppo::SmemP::TOTAL, s>>>(b, hp, policy_params, adv_norm, partial, mn_swap);
-        rows = grid;
+        rows_a = rows_c = grid;
     } else {
-        // one network per CTA, two tiles in flight: CTA pairs (actor, critic), at most one CTA per SM
-        const int pairs_needed = (ntiles + 1) / 2, pairs_max = sms / 2;
-        rows = pairs_needed < pairs_max ? pairs_needed : pairs_max;
+        // one network per CTA, two tiles in flight, at most one CTA per SM; the actor's tiles cost ~13 % more than the
+        // critic's (loss math, more gathered columns), so it gets ~53 % of the SMs
+        const int pairs_needed = (ntiles + 1) / 2;
+        const int a_max = (sms * 53 + 50) / 100 > sms - 1 ? sms - 1 : (sms * 53 + 50) / 100, c_max = sms - a_max;
+        rows_a = pairs_needed < a_max ? pairs_needed : a_max;
+        rows_c = pairs_needed < c_max ? pairs_needed : c_max;
         QS_CUDA(cudaFuncSetAttribute(qs::ppo::ppo_grad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qs::ppo::SmemQ::TOTAL));
-        qs::ppo::ppo_grad_tc2_kernel<<<2 * rows, qs::ppo::kThreads2, qs::ppo::SmemQ::TOTAL, s>>>(b, hp, policy_params, adv_norm, partial, mn_swap);
+        qs::ppo::ppo_grad_tc2_kernel<<<rows_a + rows_c, qs::ppo::kThreads2, qs::ppo::SmemQ::TOTAL, s>>>(b, hp, policy_params, adv_norm, partial, rows_a);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    const int len = P + qs::ppo::kPartialStats;
-    qs::ppo::ppo_reduce_kernel<<<nblocks(len, 256), 256, 0, s>>>(partial, rows, qs::ppo::partial_stride(P), len, grad);
+    qs::ppo::ppo_reduce_kernel<<<nblocks(len, 256), 256, 0, s>>>(partial, rows_a, rows_c, L.cW1, L.log_std, P + 1,
+                                                                 qs::ppo::partial_stride(P), len, grad);
     return check_launch("ppo_grad");
 }
 

@@ -91,36 +91,12 @@ __device__ __forceinline__ uint32_t pack_mask_bf16(float lo, float hi, uint32_t 
     return pack_bf16(lo, hi);
 }
 
-// tcgen05.ld without the wait (the registers are valid only after tmem_ld_wait on the same array)
-__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t r[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr));
-}
-// wait for every outstanding tcgen05.ld of this thread; the "+r" operands tie the register array to the wait so that
-// no use of it can be scheduled above
-__device__ __forceinline__ void tmem_ld_wait(uint32_t r[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :: "memory");
-}
 // bf16x2(lo, hi) & [h > 0] per half: one F2FP pack, one HSET2 (0xffff per true half), one LOP
 __device__ __forceinline__ uint32_t pack_mask2_bf16(float lo, float hi, uint32_t hpair) {
     uint32_t m, p;
     asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(hpair), "r"(0u));
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
     return p & m;
-}
-__device__ __forceinline__ uint32_t pack_relu_bf16_u(uint32_t lo, uint32_t hi) {
-    return pack_relu_bf16(__uint_as_float(lo), __uint_as_float(hi));
 }
 
 #ifndef QS_PPO_DYNAMIC_ISSUE

@@ -148,6 +148,31 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// tcgen05.ld without the wait (the registers are valid only after tmem_ld_wait on the same array)
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t r[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+// wait for every outstanding tcgen05.ld of this thread; the "+r" operands tie the register array to the wait so that
+// no use of it can be scheduled above
+__device__ __forceinline__ void tmem_ld_wait(uint32_t r[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16_u(uint32_t lo, uint32_t hi) {
+    return pack_relu_bf16(__uint_as_float(lo), __uint_as_float(hi));
+}
+
 // two fp32 adds in one instruction (FADD2, Blackwell packed fp32)
 __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
     unsigned long long p, q;
@@ -337,6 +362,31 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long pc_ = clock64();
 #endif
+    // relu + bf16 pack epilogue of a hidden layer (the bias is already inside the MMA): TMEM -> A2A | A2C.  PARTNER: the
+    // owners take the actor half, the partners the critic half.  The TMEM load of chunk i + 1 is in flight while chunk i
+    // is converted and stored.
+    auto relu_epilogue = [&]() {
+        constexpr int kChunks = PARTNER ? 4 : 8;
+        const int c_lo = PARTNER ? 4 * half : 0;
+        uint32_t r[2][32];
+        tmem_ld32_async(my_tmem + (uint32_t)(c_lo * 32), r[0]);
+        tmem_ld_wait(r[0]);
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            const int c = c_lo + i;
+            if (i + 1 < kChunks) tmem_ld32_async(my_tmem + (uint32_t)((c + 1) * 32), r[(i + 1) & 1]);
+            const uint32_t* v = r[i & 1];
+            const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t* h = v + q * 8;
+                *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
+                    make_uint4(pack_relu_bf16_u(h[0], h[1]), pack_relu_bf16_u(h[2], h[3]), pack_relu_bf16_u(h[4], h[5]),
+                               pack_relu_bf16_u(h[6], h[7]));
+            }
+            if (i + 1 < kChunks) tmem_ld_wait(r[(i + 1) & 1]);
+        }
+    };
     // forward pass for the observation in `o`; returns head[Ao] and value
     auto forward = [&](const float* o, float* head, float& value) {
         // A1: normalised obs, bf16, K padded D -> K1 with a constant 1 in slots D and D + 1
@@ -366,20 +416,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         fence_after();
         QS_TCP(1);
         // epilogue 1: h1 = relu(D1 + b1) -> bf16 A2A | A2C  (PARTNER: owners take the actor half, partners the critic half)
-        const int c_lo = PARTNER ? 4 * half : 0, c_hi = PARTNER ? 4 * half + 4 : 8;
-#pragma unroll 1
-        for (int c = c_lo; c < c_hi; ++c) {
-            float v[32];
-            tmem_ld32(my_tmem + (uint32_t)(c * 32), v);
-            const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {                  // bias is already inside the MMA: relu + bf16 pack only
-                const float* h = v + q * 8;
-                *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
-                    make_uint4(pack_relu_bf16(h[0], h[1]), pack_relu_bf16(h[2], h[3]), pack_relu_bf16(h[4], h[5]),
-                               pack_relu_bf16(h[6], h[7]));
-            }
-        }
+        relu_epilogue();
         QS_TCP(2);
         fence_async_smem();
         fence_before();
@@ -405,19 +442,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         fence_after();
         QS_TCP(3);
         // epilogue 2: h2 = relu(D2) -> bf16, written over A2A | A2C (the L2 MMAs have completed; b2 is inside D2)
-#pragma unroll 1
-        for (int c = c_lo; c < c_hi; ++c) {
-            float v[32];
-            tmem_ld32(my_tmem + (uint32_t)(c * 32), v);
-            const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float* h = v + q * 8;
-                *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
-                    make_uint4(pack_relu_bf16(h[0], h[1]), pack_relu_bf16(h[2], h[3]), pack_relu_bf16(h[4], h[5]),
-                               pack_relu_bf16(h[6], h[7]));
-            }
-        }
+        relu_epilogue();
         QS_TCP(4);
         fence_async_smem();
         fence_before();

@@ -173,6 +173,14 @@ __device__ __forceinline__ uint32_t pack_relu_bf16_u(uint32_t lo, uint32_t hi) {
     return pack_relu_bf16(__uint_as_float(lo), __uint_as_float(hi));
 }
 
+// one lane of a converged warp (warp-uniform control flow around it keeps tcgen05.mma free of per-lane election loops and
+// lets ptxas hold the descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // two fp32 adds in one instruction (FADD2, Blackwell packed fp32)
 __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
     unsigned long long p, q;
@@ -249,6 +257,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     const int tile = gtid / kTT, ltid = gtid % kTT;
     const int half = ltid / kM;                            // 0: owner warpgroup, 1: partner warpgroup
     const int tid = ltid % kM, warp = tid >> 5;            // row of the tile = TMEM lane; lane-quadrant warp index
+    const int lwarp = __shfl_sync(0xffffffffu, ltid >> 5, 0);   // warp index within the tile, visibly warp-uniform: warp 0 issues the MMAs
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES)) + tile;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::bar_off(TILES) + 8 * TILES);
     unsigned char* tsm = smem + Smem::TILE0 + tile * Smem::TILE_BYTES;   // this tile's A operands
@@ -403,13 +412,16 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         fence_async_smem();
         fence_before();
         tile_sync<kTT>(tile);
-        if (ltid == 0) {
+        if (lwarp == 0) {
             fence_after();
+            if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < kS1; ++j)                                   // D1[128 x 256] = A1 . W1cat (+ b1)
                 mma_bf16(tmem, make_desc(tbase + Smem::A1 + j * 4096, 16 * 128, 128),
                          make_desc(sbase + Smem::W1 + j * 8192, 32 * 128, 128), idesc_l1, j > 0);
             mma_commit(bar);
+            }
+            __syncwarp();
         }
         QS_TCP(0);
         mbar_wait(bar, phase); phase ^= 1;
@@ -421,8 +433,9 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         fence_async_smem();
         fence_before();
         tile_sync<kTT>(tile);
-        if (ltid == 0) {
+        if (lwarp == 0) {
             fence_after();
+            if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {                                   // K = 128 in 8 steps of 16 (2 chunks of 2048 B each)
                 mma_bf16(tmem, make_desc(tbase + Smem::A2A + j * 4096, 16 * 128, 128),
@@ -437,6 +450,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             mma_bf16(tmem, dA1b, make_desc(sbase + Smem::B2A, 16 * 128, 128), idesc_l2, 1u);
             mma_bf16(tmem + 128u, dA1b, make_desc(sbase + Smem::B2C, 16 * 128, 128), idesc_l2, 1u);
             mma_commit(bar);
+            }
+            __syncwarp();
         }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
@@ -447,8 +462,9 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         fence_async_smem();
         fence_before();
         tile_sync<kTT>(tile);
-        if (ltid == 0) {
+        if (lwarp == 0) {
             fence_after();
+            if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)                                     // heads: N = 16 (B rows/8 = 2 -> LBO 256 B, K step 512 B)
                 mma_bf16(tmem, make_desc(tbase + Smem::A2A + j * 4096, 16 * 128, 128),
@@ -458,6 +474,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 mma_bf16(tmem + 16u, make_desc(tbase + Smem::A2C + j * 4096, 16 * 128, 128),
                          make_desc(sbase + Smem::W3C + j * 512, 2 * 128, 128), idesc_l3, j > 0);
             mma_commit(bar);
+            }
+            __syncwarp();
         }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();

@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--total-envs", type=int, default=65536)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--n-steps", type=int, default=64)
+    ap.add_argument("--lr", type=float, default=1e-3)
+    ap.add_argument("--log-json", default=None, help="write the per-iteration log (mean reward, losses, clip fraction) here")
     ap.add_argument("--autograd", action="store_true", help="torch-autograd update instead of the fused qs_ppo_grad / qs_ppo_adam kernels")
     args = ap.parse_args()
     import torch
@@ -30,7 +32,7 @@ def main():
     torch.cuda.set_device(ctx.local_rank)
     off, cnt = shard_range(args.total_envs, ctx.world, ctx.rank)
     eng = Engine(Q.EnvConfig.north_star(seed=0, env_id_offset=off), cnt, device=ctx.local_rank)
-    tr = PPOTrainer(eng, PPOConfig(n_steps=args.n_steps, learning_rate=1e-3, ent_coef=0.0), ctx=ctx, seed=0,
+    tr = PPOTrainer(eng, PPOConfig(n_steps=args.n_steps, learning_rate=args.lr, ent_coef=0.0), ctx=ctx, seed=0,
                     fused=not args.autograd)
     tr.set_log_std(-1.0)
     torch.manual_seed(1234)                       # same minibatch permutation stream on every rank
@@ -49,6 +51,10 @@ def main():
         in_sync = bool(torch.allclose(lo, hi, rtol=0, atol=0))
     else:
         in_sync = True
+    if ctx.rank == 0 and args.log_json:
+        with open(args.log_json, "w") as f:
+            json.dump({"total_envs": args.total_envs, "n_steps": args.n_steps, "iters": args.iters, "seconds": dt,
+                       "env_steps": args.total_envs * args.n_steps * args.iters, "log": log}, f, indent=1)
     if ctx.rank == 0:
         print(json.dumps({"world": ctx.world, "update": "fused tcgen05 kernels" if tr.fused else "torch autograd", "total_envs": args.total_envs, "iters": args.iters,
                           "env_steps_per_s_incl_update": args.total_envs * args.n_steps * args.iters / dt,

@@ -464,7 +464,7 @@ ppo_grad_tc_kernel(Batch b, Hyper hp, const float* __restrict__ params, const fl
 
 // ---------------------------------------------------------------------------------------------------------------------
 // ppo_grad_tc2_kernel -- the production schedule.  Same GEMMs, operands and rounding points as ppo_grad_tc_kernel, but
-//   * one network per CTA (even CTAs: actor, odd CTAs: critic; every CTA walks over ALL tiles of its share), which
+//   * one network per CTA (the first n_actor CTAs: actor, the rest: critic; every CTA walks over ALL tiles with its network's stride), which
 //     halves the TMEM accumulator columns (176) and the weight operands (44 KB) a CTA has to hold, so that
 //   * TWO 128-sample tiles are in flight per CTA (two worker warpgroups, each with its own operand buffers and 128
 //     working TMEM columns) and share the gradient accumulators, and

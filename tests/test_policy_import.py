@@ -57,3 +57,20 @@ def test_sb3_import_rejects_other_files(tmp_path):
         ppo.load_sb3_policy_zip(str(p))
     with pytest.raises(KeyError):
         ppo.sb3_state_dict_to_packed({"log_std": torch.zeros(4)})
+
+
+def test_sb3_export_round_trip(tmp_path):
+    """packed -> SB3 state_dict -> zip -> packed is the identity, and the exported tensors have torch.nn.Linear's layout."""
+    path, sd = _fake_sb3_zip(tmp_path, seed=3)
+    packed = ppo.load_sb3_policy_zip(path)
+    sd2 = ppo.packed_to_sb3_state_dict(packed)
+    assert set(sd2) == set(sd)
+    for k in sd:
+        assert sd2[k].shape == sd[k].shape, k
+        np.testing.assert_array_equal(sd2[k].numpy(), sd[k].numpy())
+    out = str(tmp_path / "exported.zip")
+    ppo.save_sb3_policy_zip(out, packed)
+    np.testing.assert_array_equal(ppo.load_sb3_policy_zip(out).numpy(), packed.numpy())
+    bad = packed.clone(); bad[-1] = 2.0            # a non-identity observation normaliser cannot be exported
+    with pytest.raises(ValueError):
+        ppo.packed_to_sb3_state_dict(bad)

@@ -17,7 +17,8 @@ from dataclasses import dataclass
 from . import config as Q
 from .parallel import DistContext, flat_allreduce_mean_, reduce_stats
 
-__all__ = ["PPOConfig", "ActorCritic", "FusedUpdater", "PPOTrainer", "load_sb3_policy_zip", "sb3_state_dict_to_packed"]
+__all__ = ["PPOConfig", "ActorCritic", "FusedUpdater", "PPOTrainer", "load_sb3_policy_zip", "sb3_state_dict_to_packed",
+           "packed_to_sb3_state_dict", "save_sb3_policy_zip"]
 
 H, A = 128, 4
 
@@ -357,3 +358,46 @@ def load_sb3_policy_zip(path: str, obs_dim: int = 12, device=None):
         sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
     p = sb3_state_dict_to_packed(sd, obs_dim)
     return p if device is None else p.to(device)
+
+
+def packed_to_sb3_state_dict(packed, obs_dim: int = 12):
+    """Inverse of ``sb3_state_dict_to_packed``: the kernels' packed vector (e.g. ``PPOTrainer.packed_params()`` after
+    training) -> the ``state_dict`` of SB3's ``ActorCriticPolicy`` with ``net_arch=dict(pi=[128,128], vf=[128,128])``
+    (train.py:61-64), so that a policy trained here can go back through ``model.policy.load_state_dict`` into the
+    reference's evaluate.py.  The observation normaliser must be the identity (the reference uses no VecNormalize)."""
+    import torch
+    v = packed.detach().to(torch.float32).cpu()
+    sizes = [("aW1", (obs_dim, H)), ("ab1", (H,)), ("aW2", (H, H)), ("ab2", (H,)), ("aW3", (H, A)), ("ab3", (A,)),
+             ("cW1", (obs_dim, H)), ("cb1", (H,)), ("cW2", (H, H)), ("cb2", (H,)), ("cW3", (H, 1)), ("cb3", (1,)),
+             ("log_std", (A,)), ("mean", (obs_dim,)), ("inv_std", (obs_dim,))]
+    t, o = {}, 0
+    for name, shp in sizes:
+        n = 1
+        for d in shp:
+            n *= d
+        t[name] = v[o:o + n].reshape(shp)
+        o += n
+    if o != v.numel():
+        raise ValueError(f"packed vector has {v.numel()} floats, expected {o} for obs_dim {obs_dim}")
+    if bool((t["mean"] != 0).any()) or bool((t["inv_std"] != 1).any()):
+        raise ValueError("the packed policy carries a non-identity observation normaliser, which an SB3 MlpPolicy cannot hold")
+    sd = {"log_std": t["log_std"].clone()}
+    for net in ("a", "c"):
+        for layer in ("1", "2", "3"):
+            sd[_SB3_KEYS[f"{net}W{layer}"]] = t[f"{net}W{layer}"].t().contiguous()      # torch Linear stores [out][in]
+            sd[_SB3_KEYS[f"{net}b{layer}"]] = t[f"{net}b{layer}"].clone()
+    return sd
+
+
+def save_sb3_policy_zip(path: str, packed, obs_dim: int = 12):
+    """Write ``policy.pth`` (the state_dict above) into a zip laid out like ``PPO.save`` (train.py:141).  It carries the
+    policy weights only -- no optimiser state or hyper-parameter blob -- i.e. what ``load_sb3_policy_zip`` reads back and
+    what ``model.policy.load_state_dict(torch.load(...))`` needs on the reference side."""
+    import io
+    import zipfile
+    import torch
+    buf = io.BytesIO()
+    torch.save(packed_to_sb3_state_dict(packed, obs_dim), buf)
+    with zipfile.ZipFile(path, "w") as z:
+        z.writestr("policy.pth", buf.getvalue())
+        z.writestr("data", "{}")

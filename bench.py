@@ -462,7 +462,8 @@ def main():
         ms_w = max_over_ranks(e0.elapsed_time(e1))
         line["rollout_waypoint_tc"] = {"value": world * nb2 * T2 / (ms_w * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb2, "T": T2,
                                        "waypoints_reached": sum_over_ranks(st_w[29].view(torch.int32).sum().item()),
-                                       "note": "waypoint tables circle / eight / square (13 / 13 / 12 points), reach radius 0.25, battery sag on"}
+                                       "note": "waypoint tables circle / eight / square (13 / 13 / 12 points), reach radius 0.25, battery sag on; random-init "
+                                               "policy here (it leaves the bounds before reaching a waypoint) -- tools/waypoint_demo.py flies a trained one"}
         del eng_w, bufw
         # BASELINE.json configs[4], this GPU's shard: 2^20 envs x 128 steps per PPO iteration (8 M envs across 8 GPUs), the
         # 37 033-float gradient all-reduce per minibatch being the only NCCL traffic

@@ -312,3 +312,25 @@ def test_fused_update_respects_buffer_bounds():
         o += (n + G + 63) // 64 * 64
     assert bool((arena[mask] == canary).all()), "a PPO kernel wrote outside its buffers"
     assert torch.isfinite(views["params"]).all() and torch.isfinite(views["grad"]).all()
+
+
+@pytest.mark.gpu
+def test_trainer_fused_on_trajectory_follow_env_and_unsupported_policies():
+    """The fused update serves every 12-D Gaussian-policy env (TrajectoryFollowEnv too); the 21-D Brax policies are refused
+    loudly instead of being routed through some fallback."""
+    import torch
+    from uav_reinforcement_learning_control_b200 import config as Q
+    from uav_reinforcement_learning_control_b200.engine import Engine, QuadSimError
+    from uav_reinforcement_learning_control_b200.ppo import FusedUpdater, PPOConfig, PPOTrainer
+    eng = Engine(Q.EnvConfig.traj_gym(auto_reset=Q.RESET_RESAMPLE, seed=2), 4096, device=0)
+    tr = PPOTrainer(eng, PPOConfig(n_steps=32, learning_rate=3e-4), seed=1)
+    assert tr.fused
+    tr.set_log_std(-1.0)
+    before = tr.packed_params().clone()
+    log = tr.train(3)
+    assert all(np.isfinite(l["mean_reward"]) and np.isfinite(l["pg_loss"]) and np.isfinite(l["v_loss"]) for l in log)
+    assert torch.isfinite(tr.packed_params()).all() and (tr.packed_params() != before).any()
+    with pytest.raises(QuadSimError):
+        FusedUpdater("cuda:0", obs_dim=21)
+    eng21 = Engine(Q.EnvConfig.mjx_brax(), 256, device=0)
+    assert not PPOTrainer(eng21, PPOConfig(n_steps=8), seed=0).fused          # falls back to the torch-autograd learner by design

@@ -7,7 +7,8 @@ global env ids [offset_r, offset_r + count_r) and steps them with ZERO per-step 
 Philox streams are keyed by the GLOBAL env id, so any sharding reproduces the single-GPU run bit for
 bit.  NCCL is used for exactly two things: one all-reduce of the flattened ~37.5 k-float PPO gradient
 per minibatch, and one all-reduce of a handful of episode statistics per rollout.  Both are latency
-bound (<= 150 KB) -- there is no compute/collective fusion to be had on this path.
+bound (<= 150 KB); fusing the gradient reduction, a peer-memory all-reduce and the Adam step into one kernel is the next
+multi-GPU step.
 """
 from __future__ import annotations
 

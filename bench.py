@@ -379,11 +379,13 @@ def main():
             "note": "tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), 128-env M tiles, 64 of 148 SMs busy at 8192 envs"}
         # one full PPO iteration of configs[2] on the device -- tcgen05 rollout (8192 x 1024) -> GAE ->
         # 4 epochs x 8 minibatches of 2^20 samples through qs_ppo_grad / qs_ppo_adam (one flat NCCL all-reduce of the
-        # 37 033-float gradient + statistics per minibatch when N > 1); train.py:50-68 hyper-parameters
+        # 37 033-float gradient + statistics per minibatch when N > 1 -- or, by default, no collective at all: the gradients meet in
+        # NVLink peer memory inside the optimiser kernel, qs_ppo_adam_peer); train.py:50-68 hyper-parameters
         from uav_reinforcement_learning_control_b200.parallel import DistContext
         from uav_reinforcement_learning_control_b200.ppo import PPOConfig, PPOTrainer
         torch.manual_seed(1234)
-        tr = PPOTrainer(eng_p, PPOConfig(n_steps=Tp, n_epochs=4, num_minibatches=8), ctx=DistContext(rank, world, local, None), seed=0)
+        tr = PPOTrainer(eng_p, PPOConfig(n_steps=Tp, n_epochs=4, num_minibatches=8), ctx=DistContext(rank, world, local, None), seed=0,
+                        peer=True)
         tr.collect(); tr.update()                                   # warm-up iteration (allocations, NCCL channels)
         barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -401,8 +403,11 @@ def main():
             "ms_per_minibatch": (ms_it - ms_col) / n_mb,
             "update_samples_per_s": world * mb * n_mb / ((ms_it - ms_col) * 1e-3),
             "update_tflops_bf16": 220672.0 * mb * n_mb / ((ms_it - ms_col) * 1e-3) / 1e12,
+            "gradient_exchange": "none (1 GPU)" if world == 1 else ("NVLink peer memory inside the optimiser kernel (qs_ppo_adam_peer)"
+                                                                    if tr.updater.comm is not None else "NCCL all-reduce"),
             "note": "qs_rollout_policy (tcgen05) + qs_gae + 32 x {qs_ppo_grad (tcgen05 forward + backward, weight gradients "
                     "in TMEM) + qs_ppo_adam}; includes the per-epoch qs_ppo_permutation shuffle and the statistics read-back"}
+        tr.updater.close()
         del tr
         del eng_p
         # the same config in MJX-parity mode: JaxMJXQuadBraxEnv (21-D obs, Episode + AutoReset wrappers), tanh-normal
@@ -469,7 +474,8 @@ def main():
         # 37 033-float gradient all-reduce per minibatch being the only NCCL traffic
         nb3, T3 = 1 << 20, 128
         eng_s = Engine(Q.EnvConfig.north_star(seed=5, env_id_offset=rank * nb3), nb3, device=local)
-        trs = PPOTrainer(eng_s, PPOConfig(n_steps=T3, n_epochs=4, num_minibatches=8), ctx=DistContext(rank, world, local, None), seed=0)
+        trs = PPOTrainer(eng_s, PPOConfig(n_steps=T3, n_epochs=4, num_minibatches=8), ctx=DistContext(rank, world, local, None), seed=0,
+                         peer=True)
         trs.collect(); trs.update()
         barrier()
         ev[0].record(stream)
@@ -483,7 +489,11 @@ def main():
                                "num_envs_per_gpu": nb3, "global_envs": world * nb3, "T": T3, "ms_rollout_gae": ms_sc,
                                "ms_update": ms_s - ms_sc, "samples_per_minibatch": nb3 * T3 // 8,
                                "update_samples_per_s": world * nb3 * T3 * 4 / ((ms_s - ms_sc) * 1e-3),
-                               "collectives_per_iteration": 32 if world > 1 else 0}
+                               "collectives_per_iteration": 32 if (world > 1 and trs.updater.comm is None) else 0,
+                               "gradient_exchange": "none (1 GPU)" if world == 1 else (
+                                   "NVLink peer memory inside the optimiser kernel (qs_ppo_adam_peer)" if trs.updater.comm is not None
+                                   else "NCCL all-reduce")}
+        trs.updater.close()
         del trs, eng_s
         torch.cuda.empty_cache()
         if rank == 0:

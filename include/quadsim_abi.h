@@ -281,6 +281,30 @@ int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* gra
                 void* stream);
 
 /*
+ * Multi-GPU form of the update's gradient exchange (one process per GPU; what brax's ``lax.pmean`` of the gradients does
+ * inside ``ppo_train.train``, train_brax_ppo.py:589-620, and what a data-parallel SB3 learner would need): instead of
+ * reduce -> NCCL all-reduce -> Adam, every rank leaves its gradient in a slot of a CUDA-IPC-exported buffer and ONE
+ * kernel per rank waits for the peers' slots (flags in peer memory), sums them over NVLink in rank order, clips by the
+ * global norm and applies Adam -- the parameters stay bitwise identical on all ranks by construction.
+ *   qs_ppo_comm_create  : allocates this rank's buffer (world <= 8)
+ *   qs_ppo_comm_export  : writes the 64-byte IPC handle of it (exchange it with any host-side all-gather)
+ *   qs_ppo_comm_import  : maps rank `peer`'s buffer from its handle
+ *   qs_ppo_comm_slot    : device pointer to pass as `grad` to qs_ppo_grad for update number `epoch` (1, 2, 3, ...;
+ *                         the same count on every rank; slots alternate by parity)
+ *   qs_ppo_adam_peer    : the fused wait + sum + clip + Adam for that `epoch`; stats_acc (optional, device, 8 floats)
+ *                         += the world-summed loss statistics.  A peer that never arrives traps the kernel (bounded wait).
+ */
+typedef struct QsPpoComm QsPpoComm;
+int qs_ppo_comm_create(const QsPolicyDesc* desc, int32_t world, int32_t rank, QsPpoComm** out);
+int qs_ppo_comm_export(QsPpoComm* comm, void* handle64);
+int qs_ppo_comm_import(QsPpoComm* comm, int32_t peer, const void* handle64);
+void* qs_ppo_comm_slot(QsPpoComm* comm, uint32_t epoch);
+int qs_ppo_adam_peer(const QsPolicyDesc* desc, QsPpoComm* comm, uint32_t epoch, float* policy_params, float* m, float* v,
+                     int32_t step, float lr, float beta1, float beta2, float eps, float max_grad_norm, float* norm_out,
+                     float* stats_acc, void* stream);
+int qs_ppo_comm_destroy(QsPpoComm* comm);
+
+/*
  * qs_traj_info: TrajectoryFollowEnv's info["target" | "target_vel" | "target_acc"] (envs/trajectory_follow_env.py:
  * 162-168 in step, :245-250 in reset), out9 [B][9] float32 = pos(3) | vel(3) | acc(3) of each env's natural-cubic-
  * spline reference (:176-218).  Nothing is stored per env: the spline of an episode is re-derived from the Philox

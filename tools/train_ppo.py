@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--n-steps", type=int, default=64)
     ap.add_argument("--lr", type=float, default=1e-3)
     ap.add_argument("--log-json", default=None, help="write the per-iteration log (mean reward, losses, clip fraction) here")
+    ap.add_argument("--nccl", action="store_true", help="exchange gradients with an NCCL all-reduce instead of the peer-memory kernel")
     ap.add_argument("--autograd", action="store_true", help="torch-autograd update instead of the fused qs_ppo_grad / qs_ppo_adam kernels")
     args = ap.parse_args()
     import torch
@@ -33,7 +34,7 @@ def main():
     off, cnt = shard_range(args.total_envs, ctx.world, ctx.rank)
     eng = Engine(Q.EnvConfig.north_star(seed=0, env_id_offset=off), cnt, device=ctx.local_rank)
     tr = PPOTrainer(eng, PPOConfig(n_steps=args.n_steps, learning_rate=args.lr, ent_coef=0.0), ctx=ctx, seed=0,
-                    fused=not args.autograd)
+                    fused=not args.autograd, peer=not args.nccl)
     tr.set_log_std(-1.0)
     torch.manual_seed(1234)                       # same minibatch permutation stream on every rank
     torch.cuda.synchronize()

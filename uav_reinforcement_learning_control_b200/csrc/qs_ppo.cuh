@@ -1196,5 +1196,112 @@ ppo_adam_kernel(AdamArgs a, float* __restrict__ params, const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Multi-GPU: the update's one compute -> collective pair as ONE kernel over NVLink peer memory.  Every rank's
+// ppo_reduce_kernel leaves its gradient (+ statistics) in a slot of its own CUDA-IPC-exported buffer; this kernel then
+//   1. posts "my slot of epoch e is complete" into every peer's flag array (st.release.sys) and waits until all ranks
+//      have posted (ld.acquire.sys, bounded spin -> trap instead of a hang),
+//   2. sums the world's slots element-wise straight out of peer memory in rank order (identical order on every rank, so
+//      the parameters stay bitwise in sync by construction -- no broadcast, no NCCL launch),
+//   3. computes the global gradient norm (per-CTA partials -> device-wide counter barrier -> fixed-order sum) and
+//   4. applies the Adam step to its 1024 parameters (every rank redundantly).
+// Slots are double-buffered by epoch parity: a rank can only be one epoch ahead of a peer that still reads (it posts epoch
+// e + 1 after finishing epoch e, and nobody passes the barrier of e + 1 before everybody has posted it).
+struct PeerLayout {              // offsets (bytes) inside every rank's buffer; F = floats per slot (multiple of 32)
+    int F;
+    __host__ __device__ size_t slot(int parity) const { return (size_t)parity * F * sizeof(float); }
+    __host__ __device__ size_t flags() const { return 2 * (size_t)F * sizeof(float); }                    // uint32[64]
+    __host__ __device__ size_t partials(int parity) const { return flags() + 256 + (size_t)parity * 64 * sizeof(double); }
+    __host__ __device__ size_t counters() const { return flags() + 256 + 2 * 64 * sizeof(double); }     // uint32[2]
+    __host__ __device__ size_t total() const { return counters() + 64; }
+};
+constexpr int kMaxPeers = 8;
+struct PeerPtrs { unsigned char* base[kMaxPeers]; };
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// grid = ceil(F / 1024) CTAs of 1024 threads (all co-resident).  stats_acc (optional, device): += the 8 summed statistics.
+__global__ void __launch_bounds__(1024)
+ppo_peer_adam_kernel(AdamArgs a, PeerLayout L, PeerPtrs peers, int world, int rank, uint32_t epoch, int P,
+                     float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, float* __restrict__ norm_out,
+                     float* __restrict__ stats_acc) {
+    __shared__ double sh[32];
+    __shared__ float coef_s;
+    const int parity = (int)(epoch & 1u);
+    unsigned char* self = peers.base[rank];
+    uint32_t* counters = reinterpret_cast<uint32_t*>(self + L.counters());
+    double* partials = reinterpret_cast<double*>(self + L.partials(parity));
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[parity ^ 1] = 0u;        // re-arm the other epoch's grid barrier
+    // 1. post + wait
+    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + L.flags()) + rank, epoch);
+    }
+    if ((int)threadIdx.x < world) {
+        const uint32_t* f = reinterpret_cast<const uint32_t*>(self + L.flags()) + threadIdx.x;
+        bool ok = false;
+#pragma unroll 1
+        for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+            if ((int32_t)(ld_acquire_sys(f) - epoch) >= 0) { ok = true; break; }
+        }
+        if (!ok) __trap();                                                       // a peer never arrived: fail loudly, do not hang
+    }
+    __syncthreads();
+    // 2. element-wise sum over the ranks' slots, rank order
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    float g = 0.f;
+    if (i < L.F) {
+        for (int p = 0; p < world; ++p) g += ld_relaxed_sys(reinterpret_cast<const float*>(peers.base[p] + L.slot(parity)) + i);
+    }
+    if (stats_acc && i >= P && i < P + kPartialStats) stats_acc[i - P] += g;
+    g *= a.grad_scale;
+    // 3. global norm: per-CTA partial -> counter barrier -> every CTA sums the partials in the same order
+    double ss = (i < a.n_train) ? (double)g * (double)g : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += sh[w];
+        partials[blockIdx.x] = t;
+        __threadfence();
+        atomicAdd(&counters[parity], 1u);
+        bool ok = false;
+#pragma unroll 1
+        for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+            if (*reinterpret_cast<volatile uint32_t*>(&counters[parity]) >= gridDim.x) { ok = true; break; }
+        }
+        if (!ok) __trap();
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) tot += *reinterpret_cast<volatile double*>(&partials[b]);
+        const float norm = (float)sqrt(tot);
+        if (norm_out && blockIdx.x == 0) *norm_out = norm;
+        coef_s = a.max_grad_norm > 0.f ? fminf(1.0f, a.max_grad_norm / (norm + 1e-6f)) : 1.0f;
+    }
+    __syncthreads();
+    // 4. Adam
+    if (i < a.n_train) {
+        const float gi = g * coef_s;
+        const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * gi;
+        const float vi = a.beta2 * v[i] + (1.0f - a.beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        params[i] -= (a.lr / a.bias1) * mi / (sqrtf(vi) * rsqrtf(a.bias2) + a.eps);
+    }
+}
+
 }  // namespace ppo
 }  // namespace qs

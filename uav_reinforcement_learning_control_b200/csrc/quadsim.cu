@@ -501,4 +501,90 @@ int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* gra
     return check_launch("ppo_adam_kernel");
 }
 
+// ---- multi-GPU PPO update over NVLink peer memory (qs_ppo.cuh: ppo_peer_adam_kernel) ------------------------------------
+struct QsPpoComm {
+    int world, rank, P, device;
+    qs::ppo::PeerLayout L;
+    unsigned char* local;
+    qs::ppo::PeerPtrs peers;
+    bool opened[qs::ppo::kMaxPeers];
+};
+
+int qs_ppo_comm_create(const QsPolicyDesc* desc, int32_t world, int32_t rank, QsPpoComm** out) {
+    if (!ppo_desc_ok(desc) || !out || world < 1 || world > qs::ppo::kMaxPeers || rank < 0 || rank >= world)
+        return fail(QS_EINVAL, "qs_ppo_comm_create: bad argument (1 <= world <= 8, SB3 policy)");
+    int sms = 0;
+    const int rc = ppo_device_sms(&sms);
+    if (rc != QS_OK) return rc;
+    QsPpoComm* c = new (std::nothrow) QsPpoComm();
+    if (!c) return fail(QS_ENOMEM, "qs_ppo_comm_create: host allocation failed");
+    c->world = world; c->rank = rank; c->P = qs::policy_param_count(*desc);
+    QS_CUDA(cudaGetDevice(&c->device));
+    c->L.F = qs::ppo::partial_stride(c->P);
+    for (int p = 0; p < qs::ppo::kMaxPeers; ++p) { c->peers.base[p] = nullptr; c->opened[p] = false; }
+    if (cudaMalloc(&c->local, c->L.total()) != cudaSuccess) { delete c; return fail(QS_ENOMEM, "qs_ppo_comm_create: cudaMalloc"); }
+    QS_CUDA(cudaMemset(c->local, 0, c->L.total()));
+    QS_CUDA(cudaDeviceSynchronize());
+    c->peers.base[rank] = c->local;
+    *out = c;
+    return QS_OK;
+}
+
+int qs_ppo_comm_export(QsPpoComm* c, void* handle64) {
+    if (!c || !handle64) return fail(QS_EINVAL, "qs_ppo_comm_export: null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    QS_CUDA(cudaIpcGetMemHandle(&h, c->local));
+    memcpy(handle64, &h, sizeof(h));
+    return QS_OK;
+}
+
+int qs_ppo_comm_import(QsPpoComm* c, int32_t peer, const void* handle64) {
+    if (!c || !handle64 || peer < 0 || peer >= c->world) return fail(QS_EINVAL, "qs_ppo_comm_import: bad argument");
+    if (peer == c->rank) return QS_OK;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* ptr = nullptr;
+    QS_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peers.base[peer] = (unsigned char*)ptr;
+    c->opened[peer] = true;
+    return QS_OK;
+}
+
+void* qs_ppo_comm_slot(QsPpoComm* c, uint32_t epoch) {
+    if (!c) return nullptr;
+    return c->local + c->L.slot((int)(epoch & 1u));
+}
+
+int qs_ppo_adam_peer(const QsPolicyDesc* desc, QsPpoComm* c, uint32_t epoch, float* policy_params, float* m, float* v,
+                     int32_t step, float lr, float beta1, float beta2, float eps, float max_grad_norm, float* norm_out,
+                     float* stats_acc, void* stream) {
+    if (!ppo_desc_ok(desc) || !c || !policy_params || !m || !v || step <= 0 || epoch == 0)
+        return fail(QS_EINVAL, "qs_ppo_adam_peer: bad argument (epoch counts from 1)");
+    for (int p = 0; p < c->world; ++p)
+        if (!c->peers.base[p]) return fail(QS_EINVAL, "qs_ppo_adam_peer: a peer buffer has not been imported");
+    const qs::PolicyLayout L = qs::policy_layout(desc->obs_dim, desc->dist);
+    qs::ppo::AdamArgs a;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_grad_norm = max_grad_norm; a.grad_scale = 1.0f / (float)c->world;
+    a.bias1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bias2 = (float)(1.0 - pow((double)beta2, (double)step));
+    a.n_train = L.mean;
+    const int grid = nblocks(c->L.F, 1024);
+    if (grid > 64) return fail(QS_EUNSUPPORTED, "qs_ppo_adam_peer: policy too large");
+    qs::ppo::ppo_peer_adam_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(a, c->L, c->peers, c->world, c->rank, epoch, c->P,
+                                                                           policy_params, m, v, norm_out, stats_acc);
+    return check_launch("ppo_peer_adam_kernel");
+}
+
+int qs_ppo_comm_destroy(QsPpoComm* c) {
+    if (!c) return QS_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < c->world; ++p)
+        if (c->opened[p]) cudaIpcCloseMemHandle(c->peers.base[p]);
+    cudaFree(c->local);
+    delete c;
+    return QS_OK;
+}
+
 }  // extern "C"

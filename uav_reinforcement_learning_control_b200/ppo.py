@@ -127,11 +127,39 @@ class FusedUpdater:
         self.v = torch.zeros(self.P, dtype=torch.float32, device=self.device)
         self.norm = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.step = 0
+        self.comm = None          # multi-GPU: peer-memory exchange (enable_peer)
+        self.epoch = 0
 
     def _check(self, rc, what):
         if rc != 0:
             from .engine import QuadSimError
             raise QuadSimError(f"{what}: libquadsim error {rc}: {self.lib.qs_last_error_string().decode()}")
+
+    def enable_peer(self, world: int, rank: int, group=None):
+        """Multi-GPU, one process per GPU: exchange the gradients through CUDA-IPC-mapped peer buffers and one fused
+        wait + sum + clip + Adam kernel per rank (qs_ppo_adam_peer) instead of reduce -> NCCL all-reduce -> Adam.  The
+        64-byte IPC handles travel through one torch.distributed all_gather at set-up; nothing else uses NCCL."""
+        import torch.distributed as dist
+        torch, C = self.torch, self.C
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.qs_ppo_comm_create(C.byref(self.desc), int(world), int(rank), C.byref(h)), "qs_ppo_comm_create")
+            buf = (C.c_ubyte * 64)()
+            self._check(self.lib.qs_ppo_comm_export(h, buf), "qs_ppo_comm_export")
+            mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=self.device)
+            handles = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(handles, mine, group=group)
+            for p in range(world):
+                if p != rank:
+                    raw = (C.c_ubyte * 64).from_buffer_copy(bytes(handles[p].cpu().tolist()))
+                    self._check(self.lib.qs_ppo_comm_import(h, p, raw), "qs_ppo_comm_import")
+            dist.barrier(group=group)
+        self.comm, self.world, self.rank = h, int(world), int(rank)
+
+    def close(self):
+        if self.comm is not None:
+            self.lib.qs_ppo_comm_destroy(self.comm)
+            self.comm = None
 
     def _stream(self):
         return self.C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
@@ -150,12 +178,26 @@ class FusedUpdater:
             raise ValueError("idx: expected a contiguous 1-D int32 CUDA tensor")
         n = N if idx is None else idx.numel()
         p = lambda t: None if t is None else self.C.c_void_p(t.data_ptr())
+        # peer mode: the gradient goes straight into this rank's exported slot of the NEXT update
+        out = p(self.grad_buf) if self.comm is None else self.C.c_void_p(self.lib.qs_ppo_comm_slot(self.comm, self.epoch + 1))
         with torch.cuda.device(self.device):
             self._check(self.lib.qs_ppo_grad(self.C.byref(self.desc), p(params), p(obs), p(act), p(old_logp), p(adv), p(ret),
                                              p(idx), int(n), float(clip_range), float(vf_coef), float(ent_coef),
-                                             int(bool(normalize_adv)), p(self.workspace), p(self.grad_buf), self._stream()),
+                                             int(bool(normalize_adv)), p(self.workspace), out, self._stream()),
                         "qs_ppo_grad")
-        return self.grad_buf
+        return self.grad_buf if self.comm is None else None
+
+    def adam_peer(self, params, lr, max_grad_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-5, stats_acc=None):
+        """Peer mode: wait for every rank's slot of this update, sum them over NVLink, clip, Adam -- one kernel."""
+        self.step += 1
+        self.epoch += 1
+        p = lambda t: None if t is None else self.C.c_void_p(t.data_ptr())
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.qs_ppo_adam_peer(self.C.byref(self.desc), self.comm, int(self.epoch), p(params), p(self.m),
+                                                  p(self.v), int(self.step), float(lr), float(beta1), float(beta2), float(eps),
+                                                  float(max_grad_norm), p(self.norm), p(stats_acc), self._stream()),
+                        "qs_ppo_adam_peer")
+        return self.norm
 
     def permutation(self, n: int, seed: int, epoch: int, out=None):
         """int32 [n] pseudo-random permutation of 0..n-1 keyed by (seed, epoch) (qs_ppo_permutation): the per-epoch shuffle
@@ -187,7 +229,7 @@ class PPOTrainer:
     vector ``self.params``; fused=False: torch autograd on ``self.policy``."""
 
     def __init__(self, engine, cfg: PPOConfig | None = None, ctx: DistContext | None = None, seed: int = 0,
-                 fused: bool | None = None, tensor_cores: bool | None = None):
+                 fused: bool | None = None, tensor_cores: bool | None = None, peer: bool = False):
         import torch
         self.torch = torch
         self.engine = engine
@@ -198,6 +240,20 @@ class PPOTrainer:
         self.tensor_cores = self.fused if tensor_cores is None else bool(tensor_cores)
         self.params = self.policy.pack() if self.fused else None                 # fused: THE master copy of the weights
         self.updater = FusedUpdater(engine.device, engine.obs_dim) if self.fused else None
+        if peer and self.fused and self.ctx.world > 1:
+            # Set-up (CUDA IPC) is the only part that can fail for environmental reasons; the decision to use the peer
+            # path must be unanimous, otherwise every rank stays on the NCCL all-reduce.
+            import torch.distributed as dist
+            ok = 1
+            try:
+                self.updater.enable_peer(self.ctx.world, self.ctx.rank, self.ctx.group)
+            except Exception as e:           # noqa: BLE001 -- reported, then decided collectively
+                ok = 0
+                print(f"[rank {self.ctx.rank}] peer-memory gradient exchange unavailable ({e}); using NCCL", flush=True)
+            flag = torch.tensor([ok], dtype=torch.int32, device=engine.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.ctx.group)
+            if int(flag.item()) == 0:
+                self.updater.close()
         self.shuffle_seed = (int(seed) << 20) ^ (0x5EED + 7919 * self.ctx.rank)     # every rank shuffles its own rows
         self._epochs_done = 0
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
@@ -239,6 +295,10 @@ class PPOTrainer:
                 g = up.grad(self.params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb],
                             clip_range=c.clip_range, vf_coef=c.vf_coef, ent_coef=c.ent_coef,
                             normalize_adv=c.normalize_advantage)
+                if up.comm is not None:
+                    # gradients meet in NVLink peer memory inside the optimiser kernel: no collective call at all
+                    up.adam_peer(self.params, c.learning_rate, max_grad_norm=c.max_grad_norm, stats_acc=acc)
+                    continue
                 if world > 1:
                     import torch.distributed as dist
                     dist.all_reduce(g, group=self.ctx.group)       # the ONLY collective: P + 8 floats, sum

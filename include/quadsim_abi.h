@@ -293,6 +293,8 @@ int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* gra
  *                         the same count on every rank; slots alternate by parity)
  *   qs_ppo_adam_peer    : the fused wait + sum + clip + Adam for that `epoch`; stats_acc (optional, device, 8 floats)
  *                         += the world-summed loss statistics.  A peer that never arrives traps the kernel (bounded wait).
+ *   tear-down           : every rank qs_ppo_comm_close_peers, a host-side barrier, then qs_ppo_comm_destroy (an exported
+ *                         buffer must not be freed while a peer still maps it)
  */
 typedef struct QsPpoComm QsPpoComm;
 int qs_ppo_comm_create(const QsPolicyDesc* desc, int32_t world, int32_t rank, QsPpoComm** out);
@@ -302,6 +304,7 @@ void* qs_ppo_comm_slot(QsPpoComm* comm, uint32_t epoch);
 int qs_ppo_adam_peer(const QsPolicyDesc* desc, QsPpoComm* comm, uint32_t epoch, float* policy_params, float* m, float* v,
                      int32_t step, float lr, float beta1, float beta2, float eps, float max_grad_norm, float* norm_out,
                      float* stats_acc, void* stream);
+int qs_ppo_comm_close_peers(QsPpoComm* comm);   /* unmap the peers' buffers; call on every rank (then synchronise the ranks) before any rank destroys */
 int qs_ppo_comm_destroy(QsPpoComm* comm);
 
 /*

@@ -576,12 +576,18 @@ int qs_ppo_adam_peer(const QsPolicyDesc* desc, QsPpoComm* c, uint32_t epoch, flo
     return check_launch("ppo_peer_adam_kernel");
 }
 
-int qs_ppo_comm_destroy(QsPpoComm* c) {
+int qs_ppo_comm_close_peers(QsPpoComm* c) {
     if (!c) return QS_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (int p = 0; p < c->world; ++p)
-        if (c->opened[p]) cudaIpcCloseMemHandle(c->peers.base[p]);
+        if (c->opened[p]) { cudaIpcCloseMemHandle(c->peers.base[p]); c->opened[p] = false; c->peers.base[p] = nullptr; }
+    return QS_OK;
+}
+
+int qs_ppo_comm_destroy(QsPpoComm* c) {
+    if (!c) return QS_OK;
+    qs_ppo_comm_close_peers(c);
     cudaFree(c->local);
     delete c;
     return QS_OK;

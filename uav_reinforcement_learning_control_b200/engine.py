@@ -55,6 +55,7 @@ _EXPORTS = {
     "qs_ppo_comm_slot": (C.c_void_p, [C.c_void_p, C.c_uint32]),
     "qs_ppo_adam_peer": (C.c_int, [C.POINTER(Q.QsPolicyDesc), C.c_void_p, C.c_uint32] + [C.c_void_p] * 3 + [C.c_int32]
                          + [C.c_float] * 5 + [C.c_void_p] * 3),
+    "qs_ppo_comm_close_peers": (C.c_int, [C.c_void_p]),
     "qs_ppo_comm_destroy": (C.c_int, [C.c_void_p]),
     "qs_ppo_adam": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_float] * 6
                     + [C.c_void_p] * 2),

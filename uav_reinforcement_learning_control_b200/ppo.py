@@ -154,12 +154,21 @@ class FusedUpdater:
                     raw = (C.c_ubyte * 64).from_buffer_copy(bytes(handles[p].cpu().tolist()))
                     self._check(self.lib.qs_ppo_comm_import(h, p, raw), "qs_ppo_comm_import")
             dist.barrier(group=group)
-        self.comm, self.world, self.rank = h, int(world), int(rank)
+        self.comm, self.world, self.rank, self._group = h, int(world), int(rank), group
 
-    def close(self):
-        if self.comm is not None:
-            self.lib.qs_ppo_comm_destroy(self.comm)
-            self.comm = None
+    def close(self, collective: bool = True):
+        """Tear the peer exchange down.  collective=True (every rank calls it): unmap the peers, barrier, then free -- an
+        exported buffer must not be freed while a peer still maps it."""
+        if self.comm is None:
+            return
+        if collective:
+            import torch.distributed as dist
+            self.torch.cuda.synchronize(self.device)
+            dist.barrier(group=self._group)                  # nobody is still reading a slot
+            self.lib.qs_ppo_comm_close_peers(self.comm)
+            dist.barrier(group=self._group)                  # nobody still maps this rank's buffer
+        self.lib.qs_ppo_comm_destroy(self.comm)
+        self.comm = None
 
     def _stream(self):
         return self.C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
@@ -253,7 +262,7 @@ class PPOTrainer:
             flag = torch.tensor([ok], dtype=torch.int32, device=engine.device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.ctx.group)
             if int(flag.item()) == 0:
-                self.updater.close()
+                self.updater.close(collective=False)     # some ranks have nothing to close: no barriers here
         self.shuffle_seed = (int(seed) << 20) ^ (0x5EED + 7919 * self.ctx.rank)     # every rank shuffles its own rows
         self._epochs_done = 0
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)

@@ -334,3 +334,27 @@ def test_trainer_fused_on_trajectory_follow_env_and_unsupported_policies():
         FusedUpdater("cuda:0", obs_dim=21)
     eng21 = Engine(Q.EnvConfig.mjx_brax(), 256, device=0)
     assert not PPOTrainer(eng21, PPOConfig(n_steps=8), seed=0).fused          # falls back to the torch-autograd learner by design
+
+
+@pytest.mark.gpu
+def test_peer_memory_update_two_gpus():
+    """qs_ppo_adam_peer (gradient exchange over NVLink peer memory inside the optimiser kernel) against the NCCL form, two
+    ranks under torchrun: same parameters as reduce + all-reduce + Adam (bitwise at world 2, where the sum is commutative)
+    and bitwise identical across the ranks.  Needs two GPUs on the box."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PPO_N="262144")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "peer_update_check.py")],
+                         env=env, capture_output=True, text=True, timeout=240)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert out.returncode == 0 and lines, out.stderr[-2000:]
+    d = json.loads(lines[-1])
+    assert d["world"] == 2 and d["peer_params_bitwise_in_sync_across_ranks"]
+    assert d["max_abs_diff_peer_vs_nccl"] == 0.0 and d["max_abs_param_change"] > 1e-4

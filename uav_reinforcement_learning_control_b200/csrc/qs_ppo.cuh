@@ -5,6 +5,14 @@
 // vf=[128,128] ReLU, clip_range, ent_coef, vf_coef, max_grad_norm, normalize_advantage, Adam eps 1e-5), i.e. per
 // minibatch   loss = -mean(min(r A, clip(r, 1-e, 1+e) A)) + vf_coef * mean((ret - V)^2) - ent_coef * H(pi).
 //
+// Kernels in this file:
+//   ppo_grad_tc2_kernel     the production gradient kernel (one network per CTA, two tiles in flight, issuer + gather warps)
+//   ppo_grad_tc_kernel      the first, single-tile schedule, kept as the A/B reference (QS_PPO_V1=1); its description below
+//                           introduces the GEMM formulation both share
+//   ppo_adv_stats_kernel    advantage mean / std of a minibatch         ppo_reduce_kernel   fixed-order sum of the per-CTA rows
+//   ppo_adam_kernel         global-norm clip + Adam (single GPU / NCCL)  ppo_peer_adam_kernel  the same fused with the gradient
+//   ppo_permutation_kernel  per-epoch shuffle as a keyed bijection                             exchange over NVLink peer memory
+//
 // ppo_grad_tc_kernel: persistent CTAs (one per SM), each walking over 128-sample tiles of the minibatch.  Thread i owns
 // sample i of the tile and TMEM lane i.  All seven GEMM families of the forward AND backward pass run on tcgen05:
 //

@@ -86,3 +86,77 @@ def test_joint_damping_and_armature_are_parsed():
     c = M.derive_constants(t)
     assert c.rotor_damping[0] == 1e-6 and c.rotor_Js[0] == pytest.approx(3.75335e-6 + 2e-6 + 0.01 * 1e-6)
     os.unlink(f.name)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# contact guard (drone.xml:51,56,61,66,71 geoms with default contype / conaffinity, scene.xml:22 floor)
+# ---------------------------------------------------------------------------------------------------------------
+from uav_reinforcement_learning_control_b200 import config as Q  # noqa: E402
+
+ALL_CFGS = [Q.EnvConfig.north_star(), Q.EnvConfig.hover_gym(), Q.EnvConfig.traj_gym(), Q.EnvConfig.mjx_brax(),
+            Q.EnvConfig.hover_brax(), Q.EnvConfig.mjx_playground()]
+
+
+def _report(tree, cfg):
+    return M.contact_report(tree, *cfg.position_bounds(), overshoot=cfg.position_overshoot(tree.timestep))
+
+
+def test_contact_guard_passes_the_shipped_model():
+    t = M.load_mjcf(M.default_model_path())
+    assert len(t.geom_name) == 5 and all(c == 1 for c in t.geom_contype + t.geom_conaffinity)
+    for cfg in ALL_CFGS:
+        assert _report(t, cfg) == []
+        M.check_contacts(t, *cfg.position_bounds())
+    # the tightest pair: neighbouring propeller discs, 0.0796 m apart, radius 0.0329 m each -> 13.8 mm clearance
+    # (the conservative bounding spheres add the half thickness, so a little less here)
+    c1 = np.asarray(t.body_pos[2]) + t.geom_center[1]; c2 = np.asarray(t.body_pos[3]) + t.geom_center[2]
+    gap = np.linalg.norm(c1 - c2) - t.geom_rbound[1] - t.geom_rbound[2]
+    assert 0.0130 < gap < 0.0139
+
+
+@pytest.mark.skipif(not os.path.exists(REF_XML), reason="reference tree not present (GPU box)")
+def test_contact_guard_passes_reference_xml_and_shipped_bounds_enclose_its_meshes():
+    ref = M.load_mjcf(REF_XML)                     # bounding radii measured from assets/drone/*.STL
+    ours = M.load_mjcf(M.default_model_path())
+    assert ref.geom_type == ["mesh"] * 5 and all(np.isfinite(ref.geom_rbound))
+    for cfg in ALL_CFGS:
+        assert _report(ref, cfg) == []
+    for g in range(5):
+        # every mesh's bounding sphere lies inside the shipped primitive's bounding sphere
+        d = np.linalg.norm(np.asarray(ref.geom_center[g]) - np.asarray(ours.geom_center[g]))
+        assert d + ref.geom_rbound[g] <= ours.geom_rbound[g] + 1e-4, (g, d, ref.geom_rbound[g], ours.geom_rbound[g])
+
+
+def test_contact_guard_rejects_a_floor_and_touching_geoms(tmp_path):
+    src = open(M.default_model_path()).read()
+    floor = src.replace("<worldbody>", '<worldbody>\n    <geom name="floor" size="0 0 0.05" type="plane"/>')   # scene.xml:22
+    p = tmp_path / "floor.xml"; p.write_text(floor)
+    t = M.load_mjcf(str(p))
+    for cfg in ALL_CFGS:
+        rep = _report(t, cfg)
+        assert rep and all("floor" in r for r in rep)
+        with pytest.raises(M.ModelError, match="reachable contacts"):
+            M.check_contacts(t, *cfg.position_bounds())
+        M.check_contacts(t, *cfg.position_bounds(), assume_no_contact=True)        # explicit override only
+    # a floor far below the termination box is unreachable for the bounded envs, still reachable for the unbounded one
+    p.write_text(floor.replace('type="plane"', 'type="plane" pos="0 0 -1"'))
+    t = M.load_mjcf(str(p))
+    assert _report(t, Q.EnvConfig.north_star()) == [] and _report(t, Q.EnvConfig.mjx_brax()) == []
+    assert _report(t, Q.EnvConfig.mjx_playground())
+    # a static obstacle inside the box
+    p.write_text(src.replace("<worldbody>", '<worldbody>\n    <geom name="pole" type="capsule" fromto="1 1 0 1 1 2" size="0.05"/>'))
+    assert any("pole" in r for r in _report(M.load_mjcf(str(p)), Q.EnvConfig.north_star()))
+    # propeller discs grown until neighbours overlap
+    p.write_text(src.replace('size="0.0329 0.001"', 'size="0.0400 0.001"'))
+    rep = _report(M.load_mjcf(str(p)), Q.EnvConfig.north_star())
+    assert len(rep) == 4 and all("overlap" in r for r in rep)                      # the 4 neighbouring pairs, not the diagonals
+    # the same discs with collisions switched off are fine; parent-child (base <-> prop) is always filtered
+    p.write_text(src.replace('size="0.0329 0.001"', 'size="0.0400 0.001" contype="0" conaffinity="0"'))
+    assert _report(M.load_mjcf(str(p)), Q.EnvConfig.north_star()) == []
+    # a mesh whose file is missing has an unknown extent
+    p.write_text(src.replace("<worldbody>", '<asset><mesh name="m" file="nope.stl"/></asset>\n  <worldbody>').replace(
+        '<geom name="prop1_bound" type="cylinder" pos="0 0 -0.001" size="0.0329 0.001" mass="0"/>', '<geom name="prop1_bound" type="mesh" mesh="m"/>'))
+    assert any("extent unknown" in r for r in _report(M.load_mjcf(str(p)), Q.EnvConfig.north_star()))
+    # <contact> sections are not interpreted -> reported
+    p.write_text(src.replace("<actuator>", "<contact><exclude body1='prop1' body2='prop2'/></contact>\n  <actuator>"))
+    assert any("<contact>" in r for r in _report(M.load_mjcf(str(p)), Q.EnvConfig.north_star()))

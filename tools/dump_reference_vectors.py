@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Emit golden vectors from the REAL reference stack (MuJoCo C engine + MJX + the reference's own env classes).
+
+    JAX_PLATFORMS=cpu python tools/dump_reference_vectors.py --reference-root /path/to/uav_reinforcement_learning_control \
+        --out tests/golden/mujoco_vectors.json
+
+This is the hook SURVEY.md 8c(iii) / VERDICT r1 item 1a asks for: it can only run where ``mujoco`` and ``jax`` (and,
+for the episode sections, ``gymnasium`` / ``brax``) are installed -- none of them exists in the build image, which is
+why the physics parity of this repo is "unpinned".  Run it anywhere those packages exist, commit the JSON it writes,
+and ``tests/test_reference_vectors.py`` consumes it automatically (CPU suite: oracle + float32 host build of the
+kernels' per-env source; GPU suite: the sm_100a kernels through the C ABI).  Without the file that test XFAILS loudly.
+
+Sections written (arrays are exact little-endian bytes, see tests/golden/vector_io.py):
+  single_step : n >= 4096 random (qpos[11], qvel[10], ctrl[4]) -- float32-representable, incl. saturated and
+                out-of-range motor commands, |v| up to 20 m/s, |omega| up to 20 rad/s, rotor spin -- and the state after
+                ONE step of ``mujoco.mj_step`` (float64; hover_env.py:180) and of ``mjx.step`` (float32;
+                train_brax_ppo.py:317) for model/drone/drone.xml.
+  hover_env   : 512 transitions of the real ``HoverEnv`` (envs/hover_env.py:159-198): state before / action / state
+                after / obs / reward / terminated / truncated / voltage, episodes re-seeded on termination.
+  mjx_brax    : 512 transitions of the real ``JaxMJXQuadBraxEnv`` (train_brax_ppo.py:307-356) from ``reset(rng)``.
+
+``--self-test`` writes the same layout with this repo's own oracle standing in for the reference (meta.source =
+"self-test"); it exists only so the consumer's plumbing can be exercised where MuJoCo is absent and is never
+accepted as evidence (the test refuses any file whose source is not "mujoco").
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests.golden import vector_io  # noqa: E402
+
+
+def synth_inputs(n: int, seed: int = 0):
+    """Random single-step inputs, all exactly representable in float32 (so C-fp64 and MJX-fp32 start from identical
+    numbers).  Covers: saturated / zero / out-of-range motors, translational speed up to 20 m/s, body rates up to
+    20 rad/s, rotor spin up to 100 rad/s, rotor angles up to +-50 rad, arbitrary attitude."""
+    rng = np.random.default_rng(seed)
+    qpos = np.zeros((n, 11)); qvel = np.zeros((n, 10))
+    qpos[:, 0:2] = rng.uniform(-3, 3, (n, 2)); qpos[:, 2] = rng.uniform(0.0, 4.0, n)
+    q = rng.normal(size=(n, 4)); qpos[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    qpos[:, 7:11] = rng.uniform(-50, 50, (n, 4))
+    speed = rng.choice([0.0, 0.5, 5.0, 20.0], size=(n, 1))
+    qvel[:, 0:3] = rng.uniform(-1, 1, (n, 3)) * speed
+    qvel[:, 3:6] = rng.uniform(-1, 1, (n, 3)) * rng.choice([0.0, 1.0, 20.0], size=(n, 1))
+    qvel[:, 6:10] = rng.uniform(-1, 1, (n, 4)) * rng.choice([0.0, 10.0, 100.0], size=(n, 1))
+    ctrl = rng.uniform(0, 13, (n, 4))
+    kind = rng.integers(0, 6, n)
+    ctrl[kind == 0] = 13.0                      # saturated
+    ctrl[kind == 1] = 0.0                       # idle
+    ctrl[kind == 2] = rng.uniform(-2, 16, (int((kind == 2).sum()), 4))     # beyond ctrlrange: the engine must clamp
+    ctrl[kind == 3] = 0.5462804                 # hover
+    # a few structured cases first: rest at identity under hover / yaw / roll torque patterns
+    qpos[:8] = 0; qpos[:8, 2] = 1; qpos[:8, 3] = 1; qvel[:8] = 0
+    ctrl[0] = 0.5462804; ctrl[1] = 0.0; ctrl[2] = [1, 0, 1, 0]; ctrl[3] = [0, 1, 0, 1]
+    ctrl[4] = [1, 1, 0, 0]; ctrl[5] = [0, 1, 1, 0]; ctrl[6] = 13.0; ctrl[7] = [13, 0, 0, 0]
+    f = lambda a: a.astype(np.float32)
+    return f(qpos), f(qvel), f(ctrl)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the real reference stack
+# ------------------------------------------------------------------------------------------------------------------
+def dump_mujoco(ref_root: str, n: int, seed: int, steps: int):
+    import mujoco                                    # noqa: F401  (fails loudly where the reference stack is absent)
+    import jax
+    import jax.numpy as jp
+    from mujoco import mjx
+    xml = os.path.join(ref_root, "model", "drone", "drone.xml")
+    model = mujoco.MjModel.from_xml_path(xml)
+    data = mujoco.MjData(model)
+    assert (model.nq, model.nv, model.nu) == (11, 10, 4), (model.nq, model.nv, model.nu)
+    qpos, qvel, ctrl = synth_inputs(n, seed)
+
+    # --- C engine, float64 (what hover_env.py:180 / trajectory_follow_env.py:154 call)
+    c_qpos = np.zeros((n, 11)); c_qvel = np.zeros((n, 10))
+    for i in range(n):
+        mujoco.mj_resetData(model, data)
+        data.qpos[:] = qpos[i].astype(np.float64); data.qvel[:] = qvel[i].astype(np.float64)
+        data.ctrl[:] = ctrl[i].astype(np.float64)
+        mujoco.mj_step(model, data)
+        c_qpos[i] = data.qpos; c_qvel[i] = data.qvel
+
+    # --- MJX, float32 (what train_brax_ppo.py:317 / jax_mjx_quad_env.py:144 call)
+    mx = mjx.put_model(model)
+    dx = mjx.make_data(mx)
+
+    def one(qp, qv, c):
+        d = mjx.step(mx, dx.replace(qpos=qp, qvel=qv, ctrl=c))
+        return d.qpos, d.qvel
+    step = jax.jit(jax.vmap(one))
+    x_qpos, x_qvel = [], []
+    for lo in range(0, n, 1024):
+        a, b = step(jp.asarray(qpos[lo:lo + 1024]), jp.asarray(qvel[lo:lo + 1024]), jp.asarray(ctrl[lo:lo + 1024]))
+        x_qpos.append(np.asarray(a)); x_qvel.append(np.asarray(b))
+    out = {
+        "meta": {"source": "mujoco", "mujoco_version": mujoco.__version__, "jax_version": jax.__version__,
+                 "jax_backend": jax.default_backend(), "xml": "model/drone/drone.xml", "seed": seed, "n": n},
+        "single_step": {"qpos": qpos, "qvel": qvel, "ctrl": ctrl, "c_qpos": c_qpos, "c_qvel": c_qvel,
+                        "mjx_qpos": np.concatenate(x_qpos).astype(np.float32),
+                        "mjx_qvel": np.concatenate(x_qvel).astype(np.float32)},
+    }
+
+    # --- the reference's own env classes
+    sys.path.insert(0, ref_root)
+    try:
+        out["hover_env"] = dump_hover_env(steps, seed)
+    except Exception as e:                               # noqa: BLE001 -- gymnasium may be absent where mujoco exists
+        out["meta"]["hover_env_skipped"] = repr(e)
+    try:
+        out["mjx_brax"] = dump_mjx_brax(xml, steps, seed)
+    except Exception as e:                               # noqa: BLE001 -- brax may be absent
+        out["meta"]["mjx_brax_skipped"] = repr(e)
+    return out
+
+
+def _actions(steps, seed):
+    """Half gentle (hover thrust + small noise: long episodes), half uniform random (terminations)."""
+    rng = np.random.default_rng(seed + 17)
+    a = rng.uniform(-1, 1, (steps, 4)).astype(np.float32)
+    gentle = np.arange(steps) < steps // 2
+    a[gentle] = (np.array([-0.958, 0, 0, 0]) + 0.02 * rng.normal(size=(int(gentle.sum()), 4))).astype(np.float32)
+    return a
+
+
+def dump_hover_env(steps: int, seed: int):
+    """Real HoverEnv (envs/hover_env.py:159-238)."""
+    from envs.hover_env import HoverEnv
+    env = HoverEnv()
+    acts = _actions(steps, seed)
+    rec = {k: [] for k in ("qpos0", "qvel0", "target", "voltage0", "step_count0", "action", "qpos1", "qvel1", "obs",
+                           "reward", "terminated", "truncated", "voltage1", "reset_obs_next")}
+    episode_seed = seed
+    obs, _ = env.reset(seed=episode_seed)
+    for t in range(steps):
+        rec["qpos0"].append(env.data.qpos.copy()); rec["qvel0"].append(env.data.qvel.copy())
+        rec["target"].append(np.asarray(env.target_state.position, dtype=np.float32).copy())
+        rec["voltage0"].append(float(env.voltage)); rec["step_count0"].append(int(env._step_count))
+        obs, reward, terminated, truncated, info = env.step(acts[t])
+        rec["action"].append(acts[t])
+        rec["qpos1"].append(env.data.qpos.copy()); rec["qvel1"].append(env.data.qvel.copy())
+        rec["obs"].append(np.asarray(obs, dtype=np.float32)); rec["reward"].append(float(reward))
+        rec["terminated"].append(bool(terminated)); rec["truncated"].append(bool(truncated))
+        rec["voltage1"].append(float(env.voltage))
+        if terminated or truncated:
+            episode_seed += 1
+            obs, _ = env.reset(seed=episode_seed)
+            rec["reset_obs_next"].append(np.asarray(obs, dtype=np.float32))
+        else:
+            rec["reset_obs_next"].append(np.full(12, np.nan, np.float32))
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out["max_episode_steps"] = int(env.max_episode_steps)
+    return out
+
+
+def dump_mjx_brax(xml: str, steps: int, seed: int):
+    """Real JaxMJXQuadBraxEnv (train_brax_ppo.py:179-368), un-wrapped: reset(rng) then `steps` env.step calls."""
+    import jax
+    import jax.numpy as jp
+    from train_brax_ppo import JaxMJXQuadBraxEnv
+    env = JaxMJXQuadBraxEnv(xml_path=xml)
+    reset, step = jax.jit(env.reset), jax.jit(env.step)
+    acts = _actions(steps, seed + 1)
+    state = reset(jax.random.PRNGKey(seed))
+    rec = {k: [] for k in ("qpos0", "qvel0", "step_count0", "action", "qpos1", "qvel1", "obs", "reward", "done")}
+    reset_state = {"qpos": np.asarray(state.pipeline_state.qpos), "qvel": np.asarray(state.pipeline_state.qvel),
+                   "obs": np.asarray(state.obs)}
+    for t in range(steps):
+        rec["qpos0"].append(np.asarray(state.pipeline_state.qpos)); rec["qvel0"].append(np.asarray(state.pipeline_state.qvel))
+        rec["step_count0"].append(int(state.info["step_count"]))
+        state = step(state, jp.asarray(acts[t]))
+        rec["action"].append(acts[t])
+        rec["qpos1"].append(np.asarray(state.pipeline_state.qpos)); rec["qvel1"].append(np.asarray(state.pipeline_state.qvel))
+        rec["obs"].append(np.asarray(state.obs)); rec["reward"].append(float(state.reward)); rec["done"].append(float(state.done))
+        if float(state.done) != 0.0:
+            state = reset(jax.random.PRNGKey(seed + 1000 + t))
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out["reset"] = reset_state
+    out["traj_pos"] = np.asarray(env._sample_trajectory(env._max_episode_steps, env._traj_duration_seconds))
+    out["max_episode_steps"] = int(env._max_episode_steps)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# --self-test: this repo's oracle in the reference's place (plumbing check only, never evidence)
+# ------------------------------------------------------------------------------------------------------------------
+def dump_self_test(n: int, seed: int, steps: int):
+    from oracle.envs import OracleEnv
+    from oracle.mujoco_pipeline import TreePipeline
+    from uav_reinforcement_learning_control_b200 import config as Q
+    from uav_reinforcement_learning_control_b200 import model as M
+    tree = M.load_mjcf(M.default_model_path())
+    pipe = TreePipeline(tree)
+    qpos, qvel, ctrl = synth_inputs(n, seed)
+    cq, cv = pipe.step(qpos.astype(np.float64), qvel.astype(np.float64), ctrl.astype(np.float64))
+    out = {"meta": {"source": "self-test", "n": n, "seed": seed, "note": "oracle stands in for MuJoCo: plumbing check only"},
+           "single_step": {"qpos": qpos, "qvel": qvel, "ctrl": ctrl, "c_qpos": cq, "c_qvel": cv,
+                           "mjx_qpos": cq.astype(np.float32), "mjx_qvel": cv.astype(np.float32)}}
+    # HoverEnv-shaped episode record
+    cfg = Q.EnvConfig.hover_gym(auto_reset=Q.RESET_RESAMPLE, seed=seed)
+    orc = OracleEnv(tree, cfg)
+    s = OracleEnv.blank(1); orc.reset(s)
+    acts = _actions(steps, seed)
+    rec = {k: [] for k in ("qpos0", "qvel0", "target", "voltage0", "step_count0", "action", "qpos1", "qvel1", "obs",
+                           "reward", "terminated", "truncated", "voltage1", "reset_obs_next")}
+    for t in range(steps):
+        rec["qpos0"].append(s["qpos"][0].copy()); rec["qvel0"].append(s["qvel"][0].copy())
+        rec["target"].append(s["target"][0].copy()); rec["voltage0"].append(float(s["voltage"][0]))
+        rec["step_count0"].append(int(s["step_count"][0]))
+        s1 = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in s.items()}
+        cfg_nr = Q.EnvConfig.hover_gym(seed=seed)
+        o = OracleEnv(tree, cfg_nr).step(s1, acts[t:t + 1])
+        rec["action"].append(acts[t]); rec["qpos1"].append(s1["qpos"][0].copy()); rec["qvel1"].append(s1["qvel"][0].copy())
+        rec["obs"].append(o["obs"][0]); rec["reward"].append(float(o["reward"][0]))
+        rec["terminated"].append(bool(o["done"][0])); rec["truncated"].append(bool(o["truncated"][0]))
+        rec["voltage1"].append(float(s1["voltage"][0]))
+        o2 = orc.step(s, acts[t:t + 1])
+        rec["reset_obs_next"].append(o2["obs"][0] if o2["finished"][0] else np.full(12, np.nan, np.float32))
+    out["hover_env"] = {k: np.asarray(v) for k, v in rec.items()}
+    out["hover_env"]["max_episode_steps"] = cfg.max_episode_steps
+    # JaxMJXQuadBraxEnv-shaped record
+    cfgb = Q.EnvConfig.mjx_brax(seed=seed)
+    orb = OracleEnv(tree, cfgb)
+    s = OracleEnv.blank(1); orb.reset(s)
+    actb = _actions(steps, seed + 1)
+    rec = {k: [] for k in ("qpos0", "qvel0", "step_count0", "action", "qpos1", "qvel1", "obs", "reward", "done")}
+    reset_state = {"qpos": s["qpos"][0].astype(np.float32), "qvel": s["qvel"][0].astype(np.float32),
+                   "obs": orb.evaluate(s, None)["obs"][0]}
+    for t in range(steps):
+        rec["qpos0"].append(s["qpos"][0].astype(np.float32)); rec["qvel0"].append(s["qvel"][0].astype(np.float32))
+        rec["step_count0"].append(int(s["step_count"][0]))
+        o = orb.step(s, actb[t:t + 1])
+        rec["action"].append(actb[t]); rec["qpos1"].append(s["qpos"][0].astype(np.float32)); rec["qvel1"].append(s["qvel"][0].astype(np.float32))
+        rec["obs"].append(o["obs"][0]); rec["reward"].append(float(o["reward"][0])); rec["done"].append(float(o["done"][0]))
+        if o["done"][0] != 0:
+            s = OracleEnv.blank(1); s["episode"][:] = t + 1; orb.reset(s)
+        else:
+            s["qpos"] = s["qpos"].astype(np.float32).astype(np.float64); s["qvel"] = s["qvel"].astype(np.float32).astype(np.float64)
+    out["mjx_brax"] = {k: np.asarray(v) for k, v in rec.items()}
+    out["mjx_brax"]["reset"] = reset_state
+    out["mjx_brax"]["traj_pos"] = cfgb.target_table()
+    out["mjx_brax"]["max_episode_steps"] = cfgb.max_episode_steps
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("--reference-root", default=os.environ.get("QS_REFERENCE_ROOT", "/root/reference"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "mujoco_vectors.json"))
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=512)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--self-test", action="store_true", help="oracle in MuJoCo's place: plumbing check only, never evidence")
+    args = ap.parse_args()
+    os.environ.setdefault("JAX_PLATFORMS", "cpu")
+    if args.self_test:
+        out = dump_self_test(args.n, args.seed, args.steps)
+    else:
+        try:
+            out = dump_mujoco(args.reference_root, args.n, args.seed, args.steps)
+        except ImportError as e:
+            raise SystemExit(f"the reference stack is not installed here ({e}); run this script where `mujoco` and `jax` "
+                             "exist, or pass --self-test for the plumbing check")
+    vector_io.save(args.out, out)
+    print(f"wrote {args.out}: source={out['meta']['source']}, single_step n={args.n}, sections={sorted(k for k in out if k != 'meta')}")
+
+
+if __name__ == "__main__":
+    main()

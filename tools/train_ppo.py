@@ -61,6 +61,8 @@ def main():
                           "env_steps_per_s_incl_update": args.total_envs * args.n_steps * args.iters / dt,
                           "mean_reward_first": log[0]["mean_reward"], "mean_reward_last": log[-1]["mean_reward"],
                           "episodes_last": log[-1]["episodes"], "params_in_sync_across_ranks": in_sync}), flush=True)
+    if tr.updater is not None:
+        tr.updater.close()                     # collective tear-down of the peer buffers (unmap, barrier, free)
     if ctx.world > 1:
         import torch.distributed as dist
         dist.barrier(); dist.destroy_process_group()

@@ -191,6 +191,23 @@ class EnvConfig:
     def obs_dim(self):
         return 12 if self.mode in (MODE_HOVER_GYM, MODE_TRAJ_GYM) else 21
 
+    def position_bounds(self):
+        """(lo, hi) of the base position while an episode is alive -- what the loader's contact guard
+        (model.check_contacts) needs: the gym modes' termination box (hover_env.py:54-57), the Brax modes' limits
+        (train_brax_ppo.py:184-191), (None, None) for JaxMJXQuadEnv, which never terminates."""
+        if self.mode in (MODE_HOVER_GYM, MODE_TRAJ_GYM):
+            return tuple(self.term_lo[:3]), tuple(self.term_hi[:3])
+        if self.mode in (MODE_MJX_BRAX, MODE_HOVER_BRAX):
+            return (-self.pos_limit_xy, -self.pos_limit_xy, self.z_low), (self.pos_limit_xy, self.pos_limit_xy, self.z_high)
+        return None, None
+
+    def position_overshoot(self, dt: float) -> float:
+        """How far the base can travel in the one step that ends an episode: (v_max + a_max dt) dt with v_max the
+        velocity bound of the mode (hover_brax has none: 20 m/s is assumed) and a_max = full thrust / mass + g."""
+        v = max(abs(float(self.term_lo[6])), abs(float(self.term_hi[6]))) if self.mode in (MODE_HOVER_GYM, MODE_TRAJ_GYM) else self.vel_limit
+        a = 4.0 * self.max_motor_thrust / 0.2227 + 9.81
+        return (v + a * dt) * dt
+
     def mixer(self):
         """A and A^-1 (hover_env.py:94-100), float64."""
         l, k = self.arm_length, self.yaw_coeff

@@ -8,11 +8,6 @@
 #include <atomic>
 #include <new>
 
-// The cp.async-prefetching persistent step kernel (qs_kernels.cuh: step_kernel_pf) is kept as a build option: on B200 it
-// measured 75.8 us per 2^20-env step against 73.0 us for the plain kernel (profiles/README.md), so it is off by default.
-#ifndef QS_USE_PREFETCH_STEP
-#define QS_USE_PREFETCH_STEP 0
-#endif
 #include "qs_kernels.cuh"
 #include "qs_rollout.cuh"
 #include "qs_rollout_tc.cuh"
@@ -38,6 +33,19 @@ int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
 
 inline int nblocks(int n, int block) { return (n + block - 1) / block; }
 
+// Every handle-taking entry point runs on the handle's device and leaves the caller's current device as it found it
+// (two engines on different GPUs in one process, or an Engine(device=1) used after another cudaSetDevice).
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 }  // namespace
 
 #ifndef QS_HOST_STREAMS
@@ -51,8 +59,6 @@ struct QsEngine {
     float* target_table;    // device, [max_episode_steps][3] or null
     double* waypoints;      // device, [shapes][QS_MAX_WP][3] or null
     float* scratch;         // device staging for qs_step_host: action | obs | reward | done
-    int pf_grid;            // persistent grid of the prefetching step kernel (SMs x resident CTAs)
-    int pp_grid;            // persistent grid of the TMA-pipelined step kernel (SMs x resident CTAs)
     cudaStream_t hs[QS_HOST_STREAMS];     // qs_step_host: copy/compute streams (H2D + kernel of later chunks under the D2H of earlier ones)
     cudaEvent_t hev[QS_HOST_STREAMS + 1];
     qs::Tables tables() const { return qs::Tables{target_table, waypoints}; }
@@ -102,7 +108,7 @@ int qs_create(const QsParams* params, int32_t num_envs, int32_t device, const fl
     int ndev = 0;
     QS_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(QS_EINVAL, "qs_create: no such device");
-    QS_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);              // the caller's current device is restored on return
     cudaDeviceProp prop;
     QS_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(QS_EUNSUPPORTED, "qs_create: libquadsim is built for sm_100a (B200) only");
@@ -121,23 +127,6 @@ int qs_create(const QsParams* params, int32_t num_envs, int32_t device, const fl
         if (cudaMalloc(&e->waypoints, bytes) != cudaSuccess) { cudaFree(e->target_table); delete e; return fail(QS_ENOMEM, "cudaMalloc waypoints"); }
         cudaMemcpy(e->waypoints, waypoints_host, bytes, cudaMemcpyHostToDevice);
     }
-    e->pf_grid = prop.multiProcessorCount;
-    {
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qs::step_kernel_pp<QS_MODE_HOVER_GYM>, qs::kBlock, 0);
-        e->pp_grid = prop.multiProcessorCount * (per_sm < 1 ? 1 : per_sm);
-    }
-#if QS_USE_PREFETCH_STEP
-    {
-        const int smem = (int)qs::step_pf_smem_bytes();
-        int per_sm = 1;
-        cudaFuncSetAttribute(qs::step_kernel_pf<QS_MODE_HOVER_GYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(qs::step_kernel_pf<QS_MODE_TRAJ_GYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qs::step_kernel_pf<QS_MODE_HOVER_GYM>, qs::kBlock, smem);
-        if (per_sm < 1) per_sm = 1;
-        e->pf_grid = prop.multiProcessorCount * per_sm;
-    }
-#endif
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { cudaFree(e->target_table); cudaFree(e->waypoints); delete e; return fail(QS_ECUDA, "qs_create", ce); }
     *out = e;
@@ -146,7 +135,7 @@ int qs_create(const QsParams* params, int32_t num_envs, int32_t device, const fl
 
 int qs_destroy(QsHandle h) {
     if (!h) return QS_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaFree(h->target_table); cudaFree(h->waypoints); cudaFree(h->scratch);
     for (int k = 0; k < QS_HOST_STREAMS; ++k) if (h->hs[k]) cudaStreamDestroy(h->hs[k]);
     for (int k = 0; k <= QS_HOST_STREAMS; ++k) if (h->hev[k]) cudaEventDestroy(h->hev[k]);
@@ -164,6 +153,7 @@ int qs_get_params(QsHandle h, QsParams* out) {
 
 int qs_reset(QsHandle h, float* state, const uint8_t* mask, float* obs, float* first_state, void* stream) {
     if (!h || !state) return fail(QS_EINVAL, "qs_reset: null");
+    DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     QS_DISPATCH_MODE(h->P.mode, (qs::reset_kernel<M_><<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, s>>>(
         h->P, h->tables(), h->n, state, mask, obs, first_state)));
@@ -173,21 +163,6 @@ int qs_reset(QsHandle h, float* state, const uint8_t* mask, float* obs, float* f
 static int launch_step(QsHandle h, int lo, int count, float* state, const float* action, float* obs, float* reward,
                        float* done, float* truncated, float* metrics, float* terminal_obs, const float* first_state,
                        cudaStream_t s) {
-#if QS_USE_PREFETCH_STEP
-    if (h->P.mode == QS_MODE_HOVER_GYM || h->P.mode == QS_MODE_TRAJ_GYM) {
-        // persistent, cp.async-prefetching variant: one wave of CTAs walks over all tiles
-        const size_t smem = qs::step_pf_smem_bytes();
-        const int tiles = nblocks(count, qs::kBlock);
-        const int grid = tiles < h->pf_grid ? tiles : h->pf_grid;
-        if (h->P.mode == QS_MODE_HOVER_GYM)
-            qs::step_kernel_pf<QS_MODE_HOVER_GYM><<<grid, qs::kBlock, smem, s>>>(h->P, h->tables(), h->n, lo, count, state,
-                (const float4*)action, obs, reward, done, truncated, metrics, terminal_obs);
-        else
-            qs::step_kernel_pf<QS_MODE_TRAJ_GYM><<<grid, qs::kBlock, smem, s>>>(h->P, h->tables(), h->n, lo, count, state,
-                (const float4*)action, obs, reward, done, truncated, metrics, terminal_obs);
-        return check_launch("step_kernel_pf");
-    }
-#endif
     // Programmatic dependent launch (QS_USE_PDL): the step kernel signals launch_dependents at its top and waits for
     // its predecessors (griddepcontrol.wait) before its first global access, so the launch latency, CTA ramp-up and
     // parameter set-up of step k+1 overlap the drain of whatever ran before it on the stream.
@@ -203,22 +178,6 @@ static int launch_step(QsHandle h, int lo, int count, float* state, const float*
     if (Pq.mode == QS_MODE_HOVER_GYM && !Pq.battery && !Pq.rate_wrapper && !Pq.waypoint_mode && !Pq.pre_clip_action &&
         !metrics && !terminal_obs) {
         // plain north-star configuration: feature-folded instantiation (qs_env.cuh: FeatLean)
-#if QS_USE_PIPELINED_STEP
-        // full, 16-byte aligned tiles go through the persistent TMA-pipelined kernel; a ragged tail (if any) through
-        // the plain one
-        const int ntiles = count / qs::kBlock;
-        if (ntiles >= h->pp_grid && (h->n & 3) == 0 && (lo & 3) == 0 && ((uintptr_t)state & 15u) == 0) {
-            cudaLaunchConfig_t lp = lc;
-            lp.gridDim = dim3((unsigned)h->pp_grid);
-            cudaLaunchKernelEx(&lp, qs::step_kernel_pp<QS_MODE_HOVER_GYM>, h->P, h->tables(), (int)h->n, lo, ntiles, state, a4,
-                               obs, reward, done, truncated);
-            const int rem = count - ntiles * qs::kBlock;
-            if (rem == 0) return check_launch("step_kernel_pp");
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            lc.gridDim = dim3(1u);
-            lo += ntiles * qs::kBlock; count = rem;
-        }
-#endif
         cudaLaunchKernelEx(&lc, qs::step_kernel<QS_MODE_HOVER_GYM, qs::FeatLean>, h->P, h->tables(), (int)h->n, lo, count, state, a4,
                            obs, reward, done, truncated, metrics, terminal_obs, first_state);
         return check_launch("step_kernel<lean>");
@@ -231,6 +190,7 @@ static int launch_step(QsHandle h, int lo, int count, float* state, const float*
 int qs_step(QsHandle h, float* state, const float* action, float* obs, float* reward, float* done,
             float* truncated, float* metrics, float* terminal_obs, const float* first_state, void* stream) {
     if (!h || !state || !action || !obs || !reward || !done) return fail(QS_EINVAL, "qs_step: null");
+    DeviceGuard guard(h->device);
     if (h->P.auto_reset == QS_RESET_RESTORE_FIRST && !first_state)
         return fail(QS_EINVAL, "qs_step: auto_reset=restore_first needs first_state");
     if (((uintptr_t)action & 15u) != 0) return fail(QS_EINVAL, "qs_step: action must be 16-byte aligned");
@@ -259,6 +219,7 @@ int qs_traj_info(QsHandle h, const float* state, const uint32_t* episode, const 
                  void* stream) {
     if (!h || !state || !out9) return fail(QS_EINVAL, "qs_traj_info: null");
     if (h->P.mode != QS_MODE_TRAJ_GYM) return fail(QS_EINVAL, "qs_traj_info: the spline reference exists in QS_MODE_TRAJ_GYM only");
+    DeviceGuard guard(h->device);
     qs::traj_info_kernel<<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, (cudaStream_t)stream>>>(h->P, h->n, state, episode,
                                                                                              sample_index, out9);
     return check_launch("traj_info_kernel");
@@ -267,6 +228,7 @@ int qs_traj_info(QsHandle h, const float* state, const uint32_t* episode, const 
 int qs_observe(QsHandle h, const float* state, const float* action, float* obs, float* reward, float* done,
                void* stream) {
     if (!h || !state) return fail(QS_EINVAL, "qs_observe: null");
+    DeviceGuard guard(h->device);
     if (action && ((uintptr_t)action & 15u) != 0) return fail(QS_EINVAL, "qs_observe: action must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     QS_DISPATCH_MODE(h->P.mode, (qs::observe_kernel<M_><<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, s>>>(
@@ -276,6 +238,7 @@ int qs_observe(QsHandle h, const float* state, const float* action, float* obs, 
 
 int qs_physics_step(QsHandle h, float* state, const float* ctrl, void* stream) {
     if (!h || !state || !ctrl) return fail(QS_EINVAL, "qs_physics_step: null");
+    DeviceGuard guard(h->device);
     if (((uintptr_t)ctrl & 15u) != 0) return fail(QS_EINVAL, "qs_physics_step: ctrl must be 16-byte aligned");
     qs::physics_kernel<<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, (cudaStream_t)stream>>>(
         h->P, h->n, state, (const float4*)ctrl);
@@ -285,6 +248,7 @@ int qs_physics_step(QsHandle h, float* state, const float* ctrl, void* stream) {
 int qs_rollout_random(QsHandle h, float* state, int32_t T, uint32_t t0, float* stats, const float* first_state,
                       void* stream) {
     if (!h || !state || T < 0) return fail(QS_EINVAL, "qs_rollout_random: bad argument");
+    DeviceGuard guard(h->device);
     if (h->P.auto_reset == QS_RESET_RESTORE_FIRST && !first_state)
         return fail(QS_EINVAL, "qs_rollout_random: auto_reset=restore_first needs first_state");
     cudaStream_t s = (cudaStream_t)stream;
@@ -298,6 +262,17 @@ int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_
     if (!h || !state || !action_host || !obs_host || !reward_host || !done_host)
         return fail(QS_EINVAL, "qs_step_host: null");
     if (h->P.auto_reset == QS_RESET_RESTORE_FIRST) return fail(QS_EUNSUPPORTED, "qs_step_host: use qs_step for brax auto-reset");
+    DeviceGuard guard(h->device);
+    {
+        // the schedule below relies on truly asynchronous copies: pageable buffers would silently serialise it
+        const void* hb[4] = {action_host, obs_host, reward_host, done_host};
+        for (int k = 0; k < 4; ++k) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, hb[k]) != cudaSuccess) { cudaGetLastError(); return fail(QS_EINVAL, "qs_step_host: cannot query a host buffer"); }
+            if (at.type != cudaMemoryTypeHost)
+                return fail(QS_EINVAL, "qs_step_host: host buffers must be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)");
+        }
+    }
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)h->n, D = (size_t)h->P.obs_dim;
     if (!h->scratch) {
@@ -365,6 +340,7 @@ int qs_rollout_policy(QsHandle h, float* state, const QsPolicyDesc* desc, const 
                       float* traj_value, float* traj_reward, float* traj_done, float* traj_trunc,
                       float* last_value, const float* first_state, void* stream) {
     if (!h || !state || !desc || !policy_params || T <= 0) return fail(QS_EINVAL, "qs_rollout_policy: bad argument");
+    DeviceGuard guard(h->device);
     if (desc->obs_dim != h->P.obs_dim || desc->hidden != 128 || desc->act_dim != 4 || desc->dist < 0 || desc->dist > 1)
         return fail(QS_EUNSUPPORTED, "qs_rollout_policy: policy must be obs_dim->128->128->4 (dist 0|1)");
     if (h->P.auto_reset == QS_RESET_RESTORE_FIRST && !first_state)
@@ -532,6 +508,7 @@ int qs_ppo_comm_create(const QsPolicyDesc* desc, int32_t world, int32_t rank, Qs
 
 int qs_ppo_comm_export(QsPpoComm* c, void* handle64) {
     if (!c || !handle64) return fail(QS_EINVAL, "qs_ppo_comm_export: null");
+    DeviceGuard guard(c->device);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t h;
     QS_CUDA(cudaIpcGetMemHandle(&h, c->local));
@@ -542,6 +519,7 @@ int qs_ppo_comm_export(QsPpoComm* c, void* handle64) {
 int qs_ppo_comm_import(QsPpoComm* c, int32_t peer, const void* handle64) {
     if (!c || !handle64 || peer < 0 || peer >= c->world) return fail(QS_EINVAL, "qs_ppo_comm_import: bad argument");
     if (peer == c->rank) return QS_OK;
+    DeviceGuard guard(c->device);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, sizeof(h));
     void* ptr = nullptr;
@@ -563,6 +541,7 @@ int qs_ppo_adam_peer(const QsPolicyDesc* desc, QsPpoComm* c, uint32_t epoch, flo
         return fail(QS_EINVAL, "qs_ppo_adam_peer: bad argument (epoch counts from 1)");
     for (int p = 0; p < c->world; ++p)
         if (!c->peers.base[p]) return fail(QS_EINVAL, "qs_ppo_adam_peer: a peer buffer has not been imported");
+    DeviceGuard guard(c->device);
     const qs::PolicyLayout L = qs::policy_layout(desc->obs_dim, desc->dist);
     qs::ppo::AdamArgs a;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_grad_norm = max_grad_norm; a.grad_scale = 1.0f / (float)c->world;
@@ -578,7 +557,7 @@ int qs_ppo_adam_peer(const QsPolicyDesc* desc, QsPpoComm* c, uint32_t epoch, flo
 
 int qs_ppo_comm_close_peers(QsPpoComm* c) {
     if (!c) return QS_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (int p = 0; p < c->world; ++p)
         if (c->opened[p]) { cudaIpcCloseMemHandle(c->peers.base[p]); c->opened[p] = false; c->peers.base[p] = nullptr; }
@@ -588,6 +567,7 @@ int qs_ppo_comm_close_peers(QsPpoComm* c) {
 int qs_ppo_comm_destroy(QsPpoComm* c) {
     if (!c) return QS_OK;
     qs_ppo_comm_close_peers(c);
+    DeviceGuard guard(c->device);
     cudaFree(c->local);
     delete c;
     return QS_OK;

@@ -98,7 +98,8 @@ def _ptr(t):
 class Engine:
     """One handle = one shard of envs on one device (qs_create ... qs_destroy)."""
 
-    def __init__(self, cfg: Q.EnvConfig, num_envs: int, device=0, xml_path: str | None = None):
+    def __init__(self, cfg: Q.EnvConfig, num_envs: int, device=0, xml_path: str | None = None,
+                 assume_no_contact: bool = False):
         import torch
         if not torch.cuda.is_available():
             raise QuadSimError("no CUDA device: the quadsim engine has no CPU fallback")
@@ -108,6 +109,9 @@ class Engine:
         tree = M.load_mjcf(xml_path or M.default_model_path())
         self.tree = tree
         self.constants = M.derive_constants(tree)
+        # the kernels have no collision stage: refuse a model whose geoms could touch inside the termination bounds
+        M.check_contacts(tree, *cfg.position_bounds(), overshoot=cfg.position_overshoot(self.constants.dt),
+                         assume_no_contact=assume_no_contact)
         self.cfg = cfg
         self.num_envs = int(num_envs)
         self.obs_dim = cfg.obs_dim
@@ -137,8 +141,9 @@ class Engine:
         torch = self.torch
         if t is None:
             return
-        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
-            raise QuadSimError(f"{name}: expected contiguous float32 CUDA tensor of shape {tuple(shape)}, "
+        if (t.dtype != torch.float32 or not t.is_cuda or t.device != self.device or not t.is_contiguous()
+                or tuple(t.shape) != tuple(shape)):
+            raise QuadSimError(f"{name}: expected contiguous float32 tensor of shape {tuple(shape)} on {self.device}, "
                                f"got {t.dtype} {tuple(t.shape)} on {t.device}")
 
     def new_state(self):
@@ -164,8 +169,8 @@ class Engine:
         if obs is None:
             obs = self._f32(n, D)
         self._chk(obs, (n, D), "obs"); self._chk(first_state, (21, n), "first_state")
-        if mask is not None and (mask.dtype != self.torch.uint8 or tuple(mask.shape) != (n,)):
-            raise QuadSimError("mask must be a uint8 CUDA tensor of shape (num_envs,)")
+        if mask is not None and (mask.dtype != self.torch.uint8 or tuple(mask.shape) != (n,) or mask.device != self.device):
+            raise QuadSimError(f"mask must be a uint8 tensor of shape (num_envs,) on {self.device}")
         self._check(self.lib.qs_reset(self.handle, _ptr(state), _ptr(mask), _ptr(obs), _ptr(first_state), self._stream()))
         return obs
 

@@ -29,7 +29,7 @@ import numpy as np
 
 __all__ = [
     "ModelError", "TreeModel", "QuadConstants", "load_mjcf", "derive_constants",
-    "default_model_path", "load_default",
+    "default_model_path", "load_default", "contact_report", "check_contacts",
 ]
 
 JNT_FREE, JNT_HINGE = 0, 3   # MuJoCo's mjtJoint values for the two types we accept
@@ -94,6 +94,16 @@ class TreeModel:
     act_site: list = field(default_factory=list)
     act_gear: list = field(default_factory=list)      # 6
     act_ctrlrange: list = field(default_factory=list)  # (lo, hi) or None
+    # collision geometry (never simulated: it only feeds the contact guard, ``contact_report``)
+    geom_name: list = field(default_factory=list)
+    geom_body: list = field(default_factory=list)
+    geom_type: list = field(default_factory=list)      # plane | sphere | capsule | cylinder | ellipsoid | box | mesh
+    geom_center: list = field(default_factory=list)    # centre of the bounding sphere, body frame (3)
+    geom_rbound: list = field(default_factory=list)    # its radius (inf for a plane)
+    geom_normal: list = field(default_factory=list)    # planes: unit normal in the body frame, else None
+    geom_contype: list = field(default_factory=list)
+    geom_conaffinity: list = field(default_factory=list)
+    has_contact_section: bool = False                  # <contact> pairs / excludes are not interpreted
     # options
     timestep: float = 0.002
     gravity: np.ndarray = field(default_factory=lambda: np.array([0.0, 0.0, -9.81]))
@@ -174,8 +184,11 @@ def load_mjcf(path: str) -> TreeModel:
     viscosity/integrator>, nested <default> classes for <motor>/<joint>, <body>
     (pos/quat), <inertial> (pos/quat/mass/diaginertia), <joint> (free|hinge; pos/
     axis/damping/armature), <site> (pos/quat), <actuator><motor site= gear=
-    ctrlrange=>.  Geoms, meshes, sensors, visuals and <keyframe> are ignored
-    (the reference's keyframe has the wrong length for nq and no code reads it).
+    ctrlrange=>.  <geom> elements (incl. default classes, contype / conaffinity and the bounding radius of <mesh>
+    assets read from their STL files) are parsed into bounding spheres for the contact guard (``contact_report``) --
+    the engine has no collision stage, so a model whose geoms could touch must be rejected, not silently
+    mis-simulated.  Sensors, visuals and <keyframe> are ignored (the reference's keyframe has the wrong length for
+    nq and no code reads it).
     """
     try:
         root = ET.parse(path).getroot()
@@ -188,10 +201,22 @@ def load_mjcf(path: str) -> TreeModel:
 
     comp = root.find("compiler")
     autolimits = True   # MuJoCo >= 2.3 default
+    meshdir = ""
     if comp is not None:
         if comp.get("angle", "degree") not in ("degree", "radian"):
             raise ModelError("bad compiler angle")
         autolimits = comp.get("autolimits", "true") == "true"
+        meshdir = comp.get("meshdir", comp.get("assetdir", ""))
+    m.has_contact_section = root.find("contact") is not None
+    meshes = {}
+    for asset in root.findall("asset"):
+        for me in asset.findall("mesh"):
+            cls = me.get("class") or "main"
+            d = defaults.get(cls, {}).get("mesh", {})
+            fname = me.get("file")
+            name = me.get("name") or (os.path.splitext(os.path.basename(fname))[0] if fname else None)
+            meshes[name] = (None if fname is None else os.path.join(os.path.dirname(os.path.abspath(path)), meshdir, fname),
+                            _floats(me.get("scale", d.get("scale")), 3, [1, 1, 1]))
     opt = root.find("option")
     if opt is not None:
         m.timestep = float(opt.get("timestep", m.timestep))
@@ -212,6 +237,48 @@ def load_mjcf(path: str) -> TreeModel:
     m.body_pos.append(np.zeros(3)); m.body_quat.append(np.array([1.0, 0, 0, 0]))
     m.body_ipos.append(np.zeros(3)); m.body_iquat.append(np.array([1.0, 0, 0, 0]))
     m.body_mass.append(0.0); m.body_inertia.append(np.zeros(3))
+
+    def add_geoms(elem, bid, childclass):
+        for g in elem.findall("geom"):
+            d = dflt("geom", g, childclass)
+            get = lambda k, dv=None: g.get(k, d.get(k, dv))
+            gtype = get("type", "mesh" if get("mesh") is not None else "sphere")
+            pos = _floats(get("pos"), 3, [0, 0, 0])
+            R = quat_to_mat(_floats(get("quat"), 4, [1, 0, 0, 0]))
+            if get("fromto") is not None:
+                ft = _floats(get("fromto"), 6)
+                pos = 0.5 * (ft[:3] + ft[3:])
+            size = _floats(get("size"), None, [0.0])
+            normal = None
+            if gtype == "plane":
+                centre, rb, normal = pos, math.inf, R[:, 2]
+            elif gtype == "sphere":
+                centre, rb = pos, float(size[0])
+            elif gtype in ("capsule", "cylinder"):
+                half = 0.5 * float(np.linalg.norm(ft[3:] - ft[:3])) if get("fromto") is not None else float(size[1])
+                centre, rb = pos, (float(size[0]) + half if gtype == "capsule" else math.hypot(float(size[0]), half))
+            elif gtype == "ellipsoid":
+                centre, rb = pos, float(np.max(size))
+            elif gtype == "box":
+                centre, rb = pos, float(np.linalg.norm(size[:3]))
+            elif gtype == "mesh":
+                mname = get("mesh")
+                if mname not in meshes:
+                    raise ModelError(f"geom references unknown mesh {mname!r}")
+                v = _stl_vertices(*meshes[mname])
+                if v is None:
+                    centre, rb = pos, math.nan          # extent unknown: the contact guard refuses to clear it
+                else:
+                    w = v @ R.T + pos
+                    centre = 0.5 * (w.min(axis=0) + w.max(axis=0))
+                    rb = float(np.linalg.norm(w - centre, axis=1).max())
+            else:
+                raise ModelError(f"geom type {gtype!r} not supported")
+            m.geom_name.append(g.get("name", f"geom{len(m.geom_name)}"))
+            m.geom_body.append(bid); m.geom_type.append(gtype)
+            m.geom_center.append(np.asarray(centre, dtype=np.float64)); m.geom_rbound.append(rb)
+            m.geom_normal.append(normal)
+            m.geom_contype.append(int(get("contype", 1))); m.geom_conaffinity.append(int(get("conaffinity", 1)))
 
     def add_sites(elem, bid, childclass):
         for s in elem.findall("site"):
@@ -261,12 +328,14 @@ def load_mjcf(path: str) -> TreeModel:
                         j.get("limited", d.get("limited", "auto")) != "false"):
                     raise ModelError("joint limits not supported")
             add_sites(b, bid, cc)
+            add_geoms(b, bid, cc)
             walk(b, bid, cc)
 
     wb = root.find("worldbody")
     if wb is None:
         raise ModelError("no <worldbody>")
     add_sites(wb, 0, None)
+    add_geoms(wb, 0, None)
     walk(wb, 0, None)
 
     act = root.find("actuator")
@@ -290,6 +359,134 @@ def load_mjcf(path: str) -> TreeModel:
             else:
                 m.act_ctrlrange.append(None)
     return m
+
+
+def _stl_vertices(path, scale):
+    """Vertices [n, 3] (float64, scaled) of a binary or ASCII STL file, or None when it cannot be read."""
+    if path is None:
+        return None
+    try:
+        with open(path, "rb") as f:
+            raw = f.read()
+    except OSError:
+        return None
+    v = None
+    if len(raw) >= 84:
+        ntri = int.from_bytes(raw[80:84], "little")
+        if 84 + 50 * ntri == len(raw) and ntri > 0:
+            tri = np.frombuffer(raw, dtype=np.uint8, offset=84).reshape(ntri, 50)
+            v = tri[:, 12:48].copy().view("<f4").reshape(-1, 3).astype(np.float64)
+    if v is None:
+        pts = [ln.split()[1:4] for ln in raw.decode("ascii", "ignore").splitlines() if ln.strip().startswith("vertex")]
+        if not pts:
+            return None
+        v = np.array(pts, dtype=np.float64)
+    return v * np.asarray(scale, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------
+# contact guard
+# --------------------------------------------------------------------------
+def contact_report(tree: TreeModel, pos_lo=None, pos_hi=None, overshoot: float = 0.0):
+    """Geom pairs of ``tree`` that MuJoCo's collision phase could ever find in contact while the base origin stays in
+    the box [pos_lo, pos_hi] (the env's termination bounds; None = unbounded), as a list of human-readable strings.
+
+    The sm_100a step kernel has no collision / constraint stage, so it is only valid for models
+    where this list is empty.  Filtering follows MuJoCo's broad phase: a pair is a candidate when
+    ``(contype1 & conaffinity2) | (contype2 & conaffinity1)`` is non-zero, the geoms sit on different bodies, and the
+    bodies are not parent and child (``filterparent``; the world body never counts as a parent).  The geometric test is
+    conservative: every geom is replaced by a bounding sphere, a geom on a hinge body by the sphere swept about the
+    hinge axis (valid for every joint angle), and the whole vehicle by one sphere about the base origin when tested
+    against world geoms; ``overshoot`` inflates the box by the distance the base can travel in the one step that ends
+    the episode.  A mesh whose file could not be read has an unknown extent and is reported.
+    """
+    out = []
+    if tree.has_contact_section:
+        out.append("<contact> section present: explicit pairs / excludes are not interpreted")
+    ng = len(tree.geom_name)
+    if ng == 0:
+        return out
+    free = [b for t, b in zip(tree.jnt_type, tree.jnt_body) if t == JNT_FREE]
+    base = free[0] if free else None
+
+    def to_base(b, x):
+        """point x of body b's frame -> base frame (bodies are the base or its direct children, checked elsewhere)."""
+        while b != base and b != 0:
+            x = quat_to_mat(tree.body_quat[b]) @ x + tree.body_pos[b]
+            b = tree.body_parent[b]
+        return x, b
+
+    # bounding spheres in the base frame (vehicle geoms) or the world frame (static geoms), valid for every hinge angle
+    centre, radius, frame = [], [], []
+    for g in range(ng):
+        b = tree.geom_body[g]
+        c = np.asarray(tree.geom_center[g], dtype=np.float64); r = tree.geom_rbound[g]
+        hinge = [k for k, (t, jb) in enumerate(zip(tree.jnt_type, tree.jnt_body)) if t == JNT_HINGE and jb == b]
+        if hinge and math.isfinite(r):
+            k = hinge[0]
+            ax = np.asarray(tree.jnt_axis[k], dtype=np.float64); ax = ax / np.linalg.norm(ax)
+            rel = c - tree.jnt_pos[k]
+            on_axis = tree.jnt_pos[k] + ax * float(rel @ ax)
+            r = r + float(np.linalg.norm(c - on_axis))
+            c = on_axis
+        cb, root = to_base(b, c)
+        centre.append(cb); radius.append(r); frame.append("world" if root == 0 and b == 0 else "vehicle")
+
+    def candidates(i, j):
+        bi, bj = tree.geom_body[i], tree.geom_body[j]
+        if bi == bj:
+            return False
+        if not ((tree.geom_contype[i] & tree.geom_conaffinity[j]) or (tree.geom_contype[j] & tree.geom_conaffinity[i])):
+            return False
+        if bi != 0 and bj != 0 and (tree.body_parent[bi] == bj or tree.body_parent[bj] == bi):
+            return False                                   # filterparent
+        return True
+
+    veh = [g for g in range(ng) if frame[g] == "vehicle"]
+    R_vehicle = max([float(np.linalg.norm(centre[g])) + radius[g] for g in veh], default=0.0)
+    lo = None if pos_lo is None else np.asarray(pos_lo, dtype=np.float64) - overshoot
+    hi = None if pos_hi is None else np.asarray(pos_hi, dtype=np.float64) + overshoot
+    for i in range(ng):
+        for j in range(i + 1, ng):
+            if not candidates(i, j):
+                continue
+            name = f"{tree.geom_name[i]} ({tree.body_name[tree.geom_body[i]]}) <-> {tree.geom_name[j]} ({tree.body_name[tree.geom_body[j]]})"
+            if math.isnan(radius[i]) or math.isnan(radius[j]):
+                out.append(name + ": mesh extent unknown (file not readable)")
+                continue
+            if frame[i] == frame[j] == "vehicle":
+                gap = float(np.linalg.norm(centre[i] - centre[j])) - radius[i] - radius[j]
+                if gap <= 0.0:
+                    out.append(name + f": bounding spheres overlap by {-gap:.4f} m")
+                continue
+            if frame[i] == frame[j]:
+                continue                                   # two static geoms
+            w = i if frame[i] == "world" else j            # static geom vs the vehicle anywhere in the box
+            if lo is None or hi is None or not (np.isfinite(lo).all() and np.isfinite(hi).all()):
+                out.append(name + ": the env has no position bounds, a static geom is always reachable")
+                continue
+            if tree.geom_type[w] == "plane":
+                n = np.asarray(tree.geom_normal[w], dtype=np.float64)
+                dmin = float(np.minimum(n * lo, n * hi).sum() - n @ centre[w])    # lowest height of the base origin above the plane
+                if dmin - R_vehicle <= 0.0:
+                    out.append(name + f": plane reachable inside the termination box (clearance {dmin - R_vehicle:.4f} m)")
+            else:
+                d = np.maximum(np.maximum(lo - centre[w], centre[w] - hi), 0.0)
+                gap = float(np.linalg.norm(d)) - radius[w] - R_vehicle
+                if gap <= 0.0:
+                    out.append(name + f": static geom reachable inside the termination box (clearance {gap:.4f} m)")
+    return out
+
+
+def check_contacts(tree: TreeModel, pos_lo=None, pos_hi=None, overshoot: float = 0.0, assume_no_contact: bool = False):
+    """Raise ``ModelError`` when ``contact_report`` is non-empty, unless the caller explicitly takes responsibility
+    with ``assume_no_contact=True``."""
+    if assume_no_contact:
+        return
+    rep = contact_report(tree, pos_lo, pos_hi, overshoot)
+    if rep:
+        raise ModelError("the model has reachable contacts, which the engine does not simulate (pass "
+                         "assume_no_contact=True to override):\n  " + "\n  ".join(rep))
 
 
 # --------------------------------------------------------------------------

@@ -135,39 +135,72 @@ class FusedUpdater:
             from .engine import QuadSimError
             raise QuadSimError(f"{what}: libquadsim error {rc}: {self.lib.qs_last_error_string().decode()}")
 
-    def enable_peer(self, world: int, rank: int, group=None):
+    def enable_peer(self, world: int, rank: int, group=None) -> bool:
         """Multi-GPU, one process per GPU: exchange the gradients through CUDA-IPC-mapped peer buffers and one fused
         wait + sum + clip + Adam kernel per rank (qs_ppo_adam_peer) instead of reduce -> NCCL all-reduce -> Adam.  The
-        64-byte IPC handles travel through one torch.distributed all_gather at set-up; nothing else uses NCCL."""
+        64-byte IPC handles travel through one torch.distributed all_gather at set-up; nothing else uses NCCL.
+
+        Set-up is split into phases that contain only LOCAL work, each followed by a MIN all-reduce of the status, so every
+        rank issues the same sequence of collectives whatever fails where.  Returns True when every rank mapped every peer;
+        otherwise every rank has torn its part down (collectively: unmap, barrier, free) and the caller stays on NCCL."""
         import torch.distributed as dist
         torch, C = self.torch, self.C
-        h = C.c_void_p()
-        with torch.cuda.device(self.device):
-            self._check(self.lib.qs_ppo_comm_create(C.byref(self.desc), int(world), int(rank), C.byref(h)), "qs_ppo_comm_create")
-            buf = (C.c_ubyte * 64)()
-            self._check(self.lib.qs_ppo_comm_export(h, buf), "qs_ppo_comm_export")
-            mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=self.device)
-            handles = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(handles, mine, group=group)
-            for p in range(world):
-                if p != rank:
-                    raw = (C.c_ubyte * 64).from_buffer_copy(bytes(handles[p].cpu().tolist()))
-                    self._check(self.lib.qs_ppo_comm_import(h, p, raw), "qs_ppo_comm_import")
-            dist.barrier(group=group)
-        self.comm, self.world, self.rank, self._group = h, int(world), int(rank), group
+
+        def unanimous(ok):
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            return int(flag.item()) == 1
+
+        def report(e):
+            print(f"[rank {rank}] peer-memory gradient exchange unavailable ({e}); using NCCL", flush=True)
+
+        self.world, self.rank, self._group = int(world), int(rank), group
+        # phase 1 (local): create this rank's buffer and export its handle
+        buf, ok = (C.c_ubyte * 64)(), True
+        try:
+            h = C.c_void_p()
+            with torch.cuda.device(self.device):
+                self._check(self.lib.qs_ppo_comm_create(C.byref(self.desc), int(world), int(rank), C.byref(h)), "qs_ppo_comm_create")
+                self.comm = h                      # from here on close() frees it
+                self._check(self.lib.qs_ppo_comm_export(h, buf), "qs_ppo_comm_export")
+        except Exception as e:                     # noqa: BLE001 -- reported, then decided collectively
+            ok = False
+            report(e)
+        if not unanimous(ok):
+            self.close(collective=False)           # nobody has mapped anything yet
+            return False
+        # phase 2 (collective, unconditional): exchange the handles
+        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=self.device)
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine, group=group)
+        # phase 3 (local): map the peers
+        try:
+            with torch.cuda.device(self.device):
+                for p in range(world):
+                    if p != rank:
+                        raw = (C.c_ubyte * 64).from_buffer_copy(bytes(handles[p].cpu().tolist()))
+                        self._check(self.lib.qs_ppo_comm_import(self.comm, p, raw), "qs_ppo_comm_import")
+        except Exception as e:                     # noqa: BLE001
+            ok = False
+            report(e)
+        if not unanimous(ok):
+            self.close(collective=True)            # some ranks map this rank's buffer: unmap, barrier, then free
+            return False
+        dist.barrier(group=group)
+        return True
 
     def close(self, collective: bool = True):
         """Tear the peer exchange down.  collective=True (every rank calls it): unmap the peers, barrier, then free -- an
-        exported buffer must not be freed while a peer still maps it."""
-        if self.comm is None:
-            return
-        if collective:
+        exported buffer must not be freed while a peer still maps it.  Safe to call on a rank whose set-up failed."""
+        if collective and getattr(self, "_group", "unset") != "unset" and getattr(self, "world", 1) > 1:
             import torch.distributed as dist
             self.torch.cuda.synchronize(self.device)
             dist.barrier(group=self._group)                  # nobody is still reading a slot
-            self.lib.qs_ppo_comm_close_peers(self.comm)
+            if self.comm is not None:
+                self.lib.qs_ppo_comm_close_peers(self.comm)
             dist.barrier(group=self._group)                  # nobody still maps this rank's buffer
-        self.lib.qs_ppo_comm_destroy(self.comm)
+        if self.comm is not None:
+            self.lib.qs_ppo_comm_destroy(self.comm)
         self.comm = None
 
     def _stream(self):
@@ -250,19 +283,9 @@ class PPOTrainer:
         self.params = self.policy.pack() if self.fused else None                 # fused: THE master copy of the weights
         self.updater = FusedUpdater(engine.device, engine.obs_dim) if self.fused else None
         if peer and self.fused and self.ctx.world > 1:
-            # Set-up (CUDA IPC) is the only part that can fail for environmental reasons; the decision to use the peer
-            # path must be unanimous, otherwise every rank stays on the NCCL all-reduce.
-            import torch.distributed as dist
-            ok = 1
-            try:
-                self.updater.enable_peer(self.ctx.world, self.ctx.rank, self.ctx.group)
-            except Exception as e:           # noqa: BLE001 -- reported, then decided collectively
-                ok = 0
-                print(f"[rank {self.ctx.rank}] peer-memory gradient exchange unavailable ({e}); using NCCL", flush=True)
-            flag = torch.tensor([ok], dtype=torch.int32, device=engine.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.ctx.group)
-            if int(flag.item()) == 0:
-                self.updater.close(collective=False)     # some ranks have nothing to close: no barriers here
+            # Set-up (CUDA IPC) is the only part that can fail for environmental reasons; enable_peer decides
+            # unanimously (every rank uses the peer path or every rank stays on the NCCL all-reduce).
+            self.updater.enable_peer(self.ctx.world, self.ctx.rank, self.ctx.group)
         self.shuffle_seed = (int(seed) << 20) ^ (0x5EED + 7919 * self.ctx.rank)     # every rank shuffles its own rows
         self._epochs_done = 0
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)

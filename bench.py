@@ -35,15 +35,47 @@ NUM_ENVS = 1 << 20
 
 
 def measured_peaks():
+    """(HBM GB/s, bf16 TFLOP/s sustained, source): MEASURED_PEAKS.json (driver-written), else B200_PROFILING.md's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             with open(p) as f:
                 d = json.load(f)
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", 1400.0)), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+LAUNCHES_PER_STEP = 16      # one bench "step" = 16 env-step launches: 4 independent state sets x 4 action batches
+STATE_SETS = 4              # 4 x 294 MB of state/obs/action traffic rotate, so every launch reads lines the 126 MB L2 no longer holds
+
+
+def source_fingerprint():
+    """sha256 over the kernel sources: ties a committed ncu traffic measurement to the code that was measured."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "uav_reinforcement_learning_control_b200", "csrc")
+    for f in sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")) +
+                    [os.path.join(ROOT, "include", "quadsim_abi.h")]):
+        with open(f, "rb") as fh:
+            h.update(os.path.basename(f).encode()); h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic():
+    """DRAM bytes per step-kernel launch from the ncu capture of THIS source tree (tools/measure_traffic.py writes it in
+    the same gpurun call as the ncu summary); None when the committed measurement belongs to other sources."""
+    tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    try:
+        with open(tp) as f:
+            d = json.load(f)
+        if d.get("source_fingerprint") == source_fingerprint():
+            return float(d["dram_bytes_per_launch"]), d
+    except Exception:
+        pass
+    return None, None
 
 
 class ClockSampler:
@@ -120,6 +152,29 @@ def cpu_baseline(cfg, n_envs=1 << 16, target_seconds=12.0, threads=0):
                       f"MuJoCo-pipeline restatement (oracle/cpu_ref.c), {el:.1f} s"}, el, steps_done
 
 
+def cpu_baseline_c1(cfg):
+    """the reference's own CPU-runnable case, 16 envs x 512 steps, random actions -- single thread and
+    all host threads (oracle/cpu_ref.c stands in for the uninstallable MuJoCo / MJX stack)."""
+    from oracle import cpu_ref
+    from uav_reinforcement_learning_control_b200 import model as M
+    tree = M.load_mjcf(M.default_model_path())
+    out = {"workload": "16 hover envs x 512 steps, random actions, auto-reset (BASELINE.json configs[0]); float64 CPU port",
+           "unit": UNIT, "kind": "port"}
+    for key, thr in (("single_thread", 1), ("all_threads", 0)):
+        hr = cpu_ref.HoverRollout(tree, cfg, 16)
+        cores = thr or min(hr.max_threads(), 16)
+        hr.run(8, seed=0, threads=cores)
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            hr.run(512, seed=reps + 1, threads=cores)
+            reps += 1
+            if time.perf_counter() - t0 > 1.0 or reps >= 64:
+                break
+        el = time.perf_counter() - t0
+        out[key] = {"value": 16 * 512 * reps / el, "cores": cores, "episodes_of_512_steps": reps}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the CPU port of the reference path, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -154,6 +209,16 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def roofline_policy(tflops_bf16, traj_gbs):
+    """Where a tcgen05 policy rollout stands against both rooflines that bound it."""
+    hbm, tc, src = measured_peaks()
+    return {"tensor": {"achieved": tflops_bf16, "peak": tc, "unit": "TFLOP/s", "frac": tflops_bf16 / tc,
+                       "note": "73 984 FLOP of actor + critic forward per env-step / bf16_tflops_sustained"},
+            "hbm": {"achieved": traj_gbs, "peak": hbm, "unit": "GB/s", "frac": traj_gbs / hbm,
+                    "note": "80 B of trajectory written per env-step / hbm_gbs"},
+            "peak_source": src}
 
 
 def main():
@@ -210,17 +275,31 @@ def main():
     # global env ids: rank r owns [r*n, (r+1)*n) -> results identical for any sharding
     cfg = Q.EnvConfig.north_star(seed=0, env_id_offset=rank * n)
     eng = Engine(cfg, n, device=local)
-    state = eng.new_state()
-    obs = torch.empty(n, 12, device=dev); rew = torch.empty(n, device=dev); done = torch.empty(n, device=dev)
-    eng.reset(state, obs=obs)
+    # STATE_SETS independent copies of the whole per-launch working set (state planes, obs, reward, done) and as many action
+    # batches: consecutive launches never touch the same lines, so every launch streams from / to HBM (cold L2)
+    states = [eng.new_state() for _ in range(STATE_SETS)]
+    obss = [torch.empty(n, 12, device=dev) for _ in range(STATE_SETS)]
+    rews = [torch.empty(n, device=dev) for _ in range(STATE_SETS)]
+    dones = [torch.empty(n, device=dev) for _ in range(STATE_SETS)]
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
-    # a ring of pre-generated random action batches (synthetic uniformly randomised policies)
-    acts = [torch.rand(n, 4, device=dev, generator=gen) * 2 - 1 for _ in range(4)]
+    acts = [torch.rand(n, 4, device=dev, generator=gen) * 2 - 1 for _ in range(STATE_SETS)]
+    for j in range(STATE_SETS):
+        eng.reset(states[j], obs=obss[j])
+        if j:
+            states[j][26] = torch.full((n,), j * 1000, dtype=torch.int32, device=dev).view(torch.float32)   # distinct episode streams
+            eng.reset(states[j], obs=obss[j])
+    state, obs, rew, done = states[0], obss[0], rews[0], dones[0]
     stream = torch.cuda.current_stream(dev)
+
+    def bench_step(i):
+        """one bench step = LAUNCHES_PER_STEP launches rotating over the state sets (every env advances 4 steps)"""
+        for l in range(LAUNCHES_PER_STEP):
+            j = l % STATE_SETS
+            eng.step(states[j], acts[(j + l // STATE_SETS + i) % STATE_SETS], obs=obss[j], reward=rews[j], done=dones[j])
 
     # ---------------------------------------------------------------- value: HBM-resident API-mode step
     for i in range(W):
-        eng.step(state, acts[i % 4], obs=obs, reward=rew, done=done)
+        bench_step(i)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -232,7 +311,7 @@ def main():
     wall0 = time.time()
     e0.record(stream)
     for i in range(K):
-        eng.step(state, acts[i % 4], obs=obs, reward=rew, done=done)
+        bench_step(i)
     e1.record(stream)
     barrier()
     wall1 = time.time()
@@ -244,30 +323,28 @@ def main():
         if wall1 - wall0 < 0.5:
             tl0 = time.time()
             while time.time() - tl0 < 0.6:
-                for i in range(50):
-                    eng.step(state, acts[i % 4], obs=obs, reward=rew, done=done)
+                for i in range(4):
+                    bench_step(i)
                 torch.cuda.synchronize()
             wall1 = time.time()
         clocks = sampler.stop(wall0, wall1)
-    value = world * n * K / (ms * 1e-3)
-    finite = bool(torch.isfinite(obs).all().item())
+    value = world * n * LAUNCHES_PER_STEP * K / (ms * 1e-3)
+    finite = bool(all(torch.isfinite(o).all().item() for o in obss))
 
     # bytes per env-step actually required by the algorithm for this config (DESIGN.md "Traffic"):
     # state words in/out (21 qpos/qvel + 3 target + step_count + episode [+ voltage]) + action 16 + obs 48 + reward 4 + done 4
     words = 21 + 3 + 1 + 1 + (1 if cfg.battery else 0)
     bytes_per = 2 * 4 * words + 16 + 48 + 8
-    peak, peak_src = measured_peaks()
-    achieved = bytes_per * n * K / (ms * 1e-3) / 1e9          # per GPU (max-over-ranks time)
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-    if os.path.exists(tp):
-        try:
-            with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    peak, peak_tc, peak_src = measured_peaks()
+    us_per_launch = ms * 1e3 / (K * LAUNCHES_PER_STEP)
+    achieved = bytes_per * n / (us_per_launch * 1e-6) / 1e9       # per GPU (max-over-ranks time)
+    traffic, traffic_rec = measured_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "qs::step_kernel<QS_MODE_HOVER_GYM>", "bytes_per_env_step": bytes_per,
+                "traffic": traffic,
+                "frac_dram": None if traffic is None else (traffic / (us_per_launch * 1e-6) / 1e9) / peak,
+                "kernel": "qs::step_kernel<QS_MODE_HOVER_GYM, FeatLean>", "bytes_per_env_step": bytes_per,
+                "bytes_per_launch": bytes_per * n, "us_per_launch": us_per_launch,
+                "traffic_source": None if traffic_rec is None else traffic_rec.get("how"),
                 "peak_source": peak_src}
 
     # ---------------------------------------------------------------- e2e: host buffers through the C ABI
@@ -313,7 +390,13 @@ def main():
         "config": {"workload": "hover env dynamics-only step, 1M envs on 1xB200 (BASELINE.json configs[1]): "
                                "HoverEnv semantics, random actions, Philox auto-reset, one fused launch per step",
                    "num_envs_per_gpu": n, "global_envs": world * n, "mode": "hover_gym/north_star",
-                   "l2": f"working set {bytes_per * n / 1e6:.0f} MB per launch > 126 MB L2 (no flush needed)",
+                   "step": f"one bench step = {LAUNCHES_PER_STEP} env-step launches ({STATE_SETS} independent state sets x "
+                           f"{LAUNCHES_PER_STEP // STATE_SETS} action batches) = {LAUNCHES_PER_STEP} x {n} env-steps per GPU",
+                   "launches_per_step": LAUNCHES_PER_STEP,
+                   "l2": f"{STATE_SETS} independent working sets of {bytes_per * n / 1e6:.0f} MB rotate between launches "
+                         f"({STATE_SETS * bytes_per * n / 1e6:.0f} MB >> 126 MB L2): every launch reads and writes cold lines",
+                   "bytes_per_env_step": f"{bytes_per} B = SURVEY 8d's 288 B minus the voltage plane (2 x 4 B), which the "
+                                         "north-star config (battery sag off) neither reads nor writes",
                    "parallelism": f"env-shard x{world}, no per-step communication"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "outputs_finite": finite,
@@ -376,7 +459,8 @@ def main():
             "value": world * nb * Tp / (ms_p * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb, "T": Tp,
             "ms_rollout": ms_roll, "ms_gae": ms_p - ms_roll, "traj_hbm_gbs": (80.0 * nb * Tp) / (ms_roll * 1e-3) / 1e9,
             "policy_tflops_bf16": flop * nb * Tp / (ms_roll * 1e-3) / 1e12,
-            "note": "tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), 128-env M tiles, 64 of 148 SMs busy at 8192 envs"}
+            "roofline_policy": roofline_policy(flop * nb * Tp / (ms_roll * 1e-3) / 1e12, (80.0 * nb * Tp) / (ms_roll * 1e-3) / 1e9),
+            "note": "tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM)"}
         # one full PPO iteration of configs[2] on the device -- tcgen05 rollout (8192 x 1024) -> GAE ->
         # 4 epochs x 8 minibatches of 2^20 samples through qs_ppo_grad / qs_ppo_adam (one flat NCCL all-reduce of the
         # 37 033-float gradient + statistics per minibatch when N > 1 -- or, by default, no collective at all: the gradients meet in
@@ -450,25 +534,35 @@ def main():
             line[key] = {"value": world * nb2 * T2 / (ms_q * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb2, "T": T2,
                          ("policy_tflops_bf16" if tcf else "policy_tflops_fp32"): flop * nb2 * T2 / (ms_q * 1e-3) / 1e12,
                          "traj_hbm_gbs": (80.0 * nb2 * T2) / (ms_q * 1e-3) / 1e9}
+            if tcf:
+                line[key]["roofline_policy"] = roofline_policy(flop * nb2 * T2 / (ms_q * 1e-3) / 1e12, (80.0 * nb2 * T2) / (ms_q * 1e-3) / 1e9)
         del eng_q, bufq
         # BASELINE.json configs[3]: circle / figure-8 / square waypoint tracking (utils/trajectories.py tables, evaluate.py's
         # advance rule and lap reset fused in the step), 262 144 envs, policy rollout on tcgen05
-        from uav_reinforcement_learning_control_b200 import trajectories as TJ
+        from uav_reinforcement_learning_control_b200 import policies, trajectories as TJ
         cfg_w = Q.EnvConfig.waypoint_eval(TJ.default_tables(0.5), auto_reset=Q.RESET_RESAMPLE, seed=4, env_id_offset=rank * nb2)
         eng_w = Engine(cfg_w, nb2, device=local)
         st_w = eng_w.new_state()
         eng_w.reset(st_w)
-        bufw = eng_w.rollout_policy(st_w, params, T=T2, t0=0, dist=0, tensor_cores=True)
+        # flown by a scripted cascaded-PD policy written into the 2x128 ReLU network's weights (policies.pd_waypoint_policy):
+        # the timed leg really advances waypoints (a random-init policy leaves the bounds before reaching the first one)
+        params_w = torch.from_numpy(policies.pd_waypoint_policy(log_std=-3.5)).to(dev)
+        Tw = 128
+        bufw = eng_w.rollout_policy(st_w, params_w, T=Tw, t0=0, dist=0, tensor_cores=True)
         barrier()
+        reached0 = sum_over_ranks(st_w[29].view(torch.int32).sum().item())
         e0.record(stream)
-        eng_w.rollout_policy(st_w, params, T=T2, t0=T2, dist=0, buffers=bufw, tensor_cores=True)
+        eng_w.rollout_policy(st_w, params_w, T=Tw, t0=Tw, dist=0, buffers=bufw, tensor_cores=True)
         e1.record(stream)
         barrier()
         ms_w = max_over_ranks(e0.elapsed_time(e1))
-        line["rollout_waypoint_tc"] = {"value": world * nb2 * T2 / (ms_w * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb2, "T": T2,
-                                       "waypoints_reached": sum_over_ranks(st_w[29].view(torch.int32).sum().item()),
-                                       "note": "waypoint tables circle / eight / square (13 / 13 / 12 points), reach radius 0.25, battery sag on; random-init "
-                                               "policy here (it leaves the bounds before reaching a waypoint) -- tools/waypoint_demo.py flies a trained one"}
+        reached1 = sum_over_ranks(st_w[29].view(torch.int32).sum().item())
+        line["rollout_waypoint_tc"] = {"value": world * nb2 * Tw / (ms_w * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb2, "T": Tw,
+                                       "waypoints_reached": reached1, "waypoints_reached_in_timed_launch": reached1 - reached0,
+                                       "envs_out_of_bounds_in_timed_launch": sum_over_ranks(bufw["done"].sum().item()),
+                                       "policy_tflops_bf16": flop * nb2 * Tw / (ms_w * 1e-3) / 1e12,
+                                       "note": "waypoint tables circle / eight / square (13 / 13 / 12 points), reach radius 0.25, battery sag on; "
+                                               "scripted PD policy in the network weights, sigma = exp(-3.5) exploration noise"}
         del eng_w, bufw
         # BASELINE.json configs[4], this GPU's shard: 2^20 envs x 128 steps per PPO iteration (8 M envs across 8 GPUs), the
         # 37 033-float gradient all-reduce per minibatch being the only NCCL traffic
@@ -493,12 +587,23 @@ def main():
                                "gradient_exchange": "none (1 GPU)" if world == 1 else (
                                    "NVLink peer memory inside the optimiser kernel (qs_ppo_adam_peer)" if trs.updater.comm is not None
                                    else "NCCL all-reduce")}
+        # do the ranks really hold the same policy after the timed update?  (all-gather AFTER the timed region)
+        pbits = trs.params.view(torch.int32)
+        if world > 1:
+            gathered = [torch.empty_like(pbits) for _ in range(world)]
+            dist.all_gather(gathered, pbits)
+            in_sync = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+        else:
+            in_sync = True
+        line["sharded_ppo"]["params_bitwise_in_sync"] = in_sync
+        line["sharded_ppo"]["params_finite"] = bool(torch.isfinite(trs.params).all().item())
         trs.updater.close()
         del trs, eng_s
         torch.cuda.empty_cache()
         if rank == 0:
             cb, _, _ = cpu_baseline(Q.EnvConfig.north_star(seed=0), target_seconds=args.cpu_seconds)
             line["cpu_baseline"] = cb
+            line["cpu_baseline_c1"] = cpu_baseline_c1(Q.EnvConfig.north_star(seed=0))
     if rank == 0 and "cpu_baseline" not in line:
         cb, _, _ = cpu_baseline(Q.EnvConfig.north_star(seed=0), n_envs=1 << 14, target_seconds=3.0)
         line["cpu_baseline"] = cb

@@ -269,3 +269,121 @@ def test_rollout_tensor_core_path_21d(mode, B, T):
     # and the FMA path's own numbers against the exact fp32 oracle forward
     head32, value32 = ppo_ref.forward(pp, b["obs"][0])
     assert_close(buf2["value"][0].cpu().numpy(), value32, rtol=2e-4, atol=2e-4, what="value (fp32 FMA, 21-D)")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Chunked lock-step parity of the rollout kernels against the oracle env.
+#
+# The 12-D observation does not carry the whole state (no quaternion, no rotor angles / rates), so a transition cannot be
+# re-derived from the recorded observation alone.  Instead the rollout is launched in chunks of T steps: at every chunk
+# boundary the oracle is re-seeded from the kernel's own state planes, then steps T times with the actions the kernel
+# RECORDED, and everything the kernel wrote for those steps -- observations, done / truncated flags, rewards (incl. the
+# SB3 timeout bootstrap), and at the end of the chunk the state planes with their step / episode / waypoint counters --
+# is compared.  Inside a chunk the env state lives in the kernel's registers across steps, auto-resets, waypoint
+# advances and lap resets happen in-kernel: exactly the code paths a per-step qs_step test never reaches.
+# ---------------------------------------------------------------------------------------------------------------------
+def _lockstep(cfg, B, T, chunks, params, dist, tensor_cores, bootstrap_gamma=0.0, t0=5, obs_tol=1e-4, what=""):
+    import torch
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    eng = Engine(cfg, B, device=0)
+    st = eng.new_state(); eng.reset(st)
+    d_params = torch.from_numpy(params).cuda()
+    pp = ppo_ref.unpack(params, 12, dist)
+    orc = OracleEnv(_tree(), cfg)
+    ids = np.arange(B, dtype=np.uint32) + np.uint32(cfg.env_id_offset)
+    tol_pi = (2e-3, 2e-3, 5e-3) if tensor_cores else (1e-3, 1e-3, 1e-3)
+    buf = None
+    tot = dict(done=0, trunc=0, boot=0, finished=0)
+    for c in range(chunks):
+        torch.cuda.synchronize()
+        s = OracleEnv.from_planes(st.cpu().numpy())
+        obs = orc.evaluate(s, None)["obs"]
+        buf = eng.rollout_policy(st, d_params, T=T, t0=t0 + c * T, dist=dist, bootstrap_gamma=bootstrap_gamma,
+                                 tensor_cores=tensor_cores, buffers=buf)
+        torch.cuda.synchronize()
+        b = {k: v.cpu().numpy() for k, v in buf.items()}
+        for t in range(T):
+            w = f"{what} chunk {c} t={t}"
+            tol = obs_tol * (1 + t)
+            assert_close(b["obs"][t], obs, rtol=tol, atol=tol, what=f"{w} obs")
+            head, value = ppo_ref.forward(pp, b["obs"][t], bf16=tensor_cores)
+            raw, act, logp = ppo_ref.sample(pp, head, ppo_ref.policy_noise(cfg.seed, ids, t0 + c * T + t), dist)
+            assert_close(b["act"][t], raw, rtol=tol_pi[0], atol=tol_pi[0], what=f"{w} raw action")
+            assert_close(b["value"][t], value, rtol=tol_pi[1], atol=tol_pi[1], what=f"{w} value")
+            assert_close(b["logp"][t], logp, rtol=tol_pi[2], atol=tol_pi[2], what=f"{w} logp")
+            # the action the kernel applied = its recorded raw sample through the env-side squashing
+            a_gpu = np.clip(b["act"][t], -1.0, 1.0) if dist == 0 else np.tanh(b["act"][t].astype(np.float64)).astype(np.float32)
+            o = orc.step(s, a_gpu.astype(np.float32))
+            np.testing.assert_array_equal(b["done"][t], o["done"], err_msg=f"{w} done")
+            np.testing.assert_array_equal(b["trunc"][t], o["truncated"], err_msg=f"{w} trunc")
+            rew = np.asarray(o["reward"], dtype=np.float64).copy()
+            boot = (o["truncated"] != 0) & (o["done"] == 0) & o["finished"]
+            if bootstrap_gamma > 0 and boot.any():
+                _, vt = ppo_ref.forward(pp, o["terminal_obs"][boot], bf16=tensor_cores)
+                rew[boot] += bootstrap_gamma * vt
+            assert_close(b["reward"][t], rew, rtol=max(tol, tol_pi[1]), atol=max(tol, tol_pi[1]), what=f"{w} reward")
+            tot["done"] += int(o["done"].sum()); tot["trunc"] += int(o["truncated"].sum()); tot["boot"] += int(boot.sum())
+            tot["finished"] += int(o["finished"].sum())
+            obs = o["obs"]
+        tol = obs_tol * (1 + T)
+        assert_close(b["last_obs"], obs, rtol=tol, atol=tol, what=f"{what} chunk {c} last_obs")
+        _, v_last = ppo_ref.forward(pp, b["last_obs"], bf16=tensor_cores)
+        assert_close(b["last_value"], v_last, rtol=tol_pi[1], atol=tol_pi[1], what=f"{what} chunk {c} last value")
+        pv = planes_view(st.cpu().numpy())
+        for k in ("step_count", "episode", "wp_idx", "wp_reached", "laps"):
+            np.testing.assert_array_equal(pv[k], s[k], err_msg=f"{what} chunk {c}: {k} plane")
+        np.testing.assert_array_equal(pv["target"], s["target"], err_msg=f"{what} chunk {c}: target plane")
+        assert_close(pv["qpos"], s["qpos"], rtol=20 * tol, atol=20 * tol, what=f"{what} chunk {c} qpos plane")
+        if cfg.battery:
+            assert_close(pv["voltage"], s["voltage"], rtol=1e-5, atol=1e-5, what=f"{what} chunk {c} voltage plane")
+    tot["state"] = planes_view(st.cpu().numpy())
+    return tot
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True], ids=["fma", "tcgen05"])
+def test_rollout_waypoint_mode_lockstep(tensor_cores):
+    """BASELINE configs[3] through BOTH rollout kernels: circle / figure-8 / square waypoint tables flown by the scripted PD
+    policy (policies.pd_waypoint_policy) with exploration noise; waypoint index / reached / laps / episode counters
+    bit-exact against evaluate.py's advance rule in the oracle, incl. lap completion -> in-kernel reset to waypoint 0."""
+    from uav_reinforcement_learning_control_b200 import policies, trajectories as TJ
+    cfg = Q.EnvConfig.waypoint_eval(TJ.default_tables(0.5), auto_reset=Q.RESET_RESAMPLE, seed=4, env_id_offset=7)
+    params = policies.pd_waypoint_policy(log_std=-3.5)
+    tot = _lockstep(cfg, B=99, T=32, chunks=27, params=params, dist=0, tensor_cores=tensor_cores, what="waypoint")
+    pv = tot["state"]
+    assert (pv["laps"] >= 1).all(), "every env must have closed a lap (13 / 13 / 12 waypoints) within 864 steps"
+    assert (pv["episode"] >= 1).all() and tot["finished"] >= 99      # the lap ended the episode, the kernel reset it inline
+    assert tot["done"] == 0                                           # nobody left the bounds
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True], ids=["fma", "tcgen05"])
+def test_rollout_waypoint_mode_with_terminations(tensor_cores):
+    """Same kernels, waypoint mode, but a random policy: envs leave the bounds within ~10 steps, so the in-kernel
+    (draw-free) waypoint reset, done flags and episode counters are exercised on every step."""
+    from uav_reinforcement_learning_control_b200 import trajectories as TJ
+    cfg = Q.EnvConfig.waypoint_eval(TJ.default_tables(0.5), auto_reset=Q.RESET_RESAMPLE, seed=9, env_id_offset=3, max_episode_steps=7)
+    params = _random_policy(12, 0, seed=23, scale=0.8)
+    tot = _lockstep(cfg, B=333, T=12, chunks=3, params=params, dist=0, tensor_cores=tensor_cores, bootstrap_gamma=0.95,
+                    what="waypoint/random")
+    assert tot["done"] > 50 and tot["trunc"] > 50 and tot["boot"] > 10
+
+
+@pytest.mark.parametrize("dist,B,T", [(0, 128, 8), (0, 300, 6), (1, 517, 5)])
+def test_rollout_tensor_core_transitions_12d(dist, B, T):
+    """The 12-D tcgen05 rollout's TRANSITIONS (not only its policy heads): observations, rewards incl. the timeout bootstrap,
+    done / truncated flags and the final state planes against the oracle, north-star hover mode with Philox auto-reset
+    (speculative partner-warpgroup resets at these batch sizes)."""
+    cfg = Q.EnvConfig.north_star(seed=21, env_id_offset=64, max_episode_steps=4)
+    params = _random_policy(12, dist, seed=17, scale=0.6)
+    tot = _lockstep(cfg, B=B, T=T, chunks=3, params=params, dist=dist, tensor_cores=True, bootstrap_gamma=0.9, what=f"tc12 dist{dist}")
+    assert tot["trunc"] > 0 and tot["finished"] > B
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True], ids=["fma", "tcgen05"])
+def test_rollout_traj_gym_lockstep(tensor_cores):
+    """TrajectoryFollowEnv semantics (x, y +-3 / z 0..3 bounds, 16.8 V battery, target pinned at the start position: Q7)
+    through both rollout kernels."""
+    cfg = Q.EnvConfig.traj_gym(auto_reset=Q.RESET_RESAMPLE, seed=13, env_id_offset=11, max_episode_steps=9)
+    params = _random_policy(12, 0, seed=31, scale=0.5)
+    tot = _lockstep(cfg, B=200, T=10, chunks=3, params=params, dist=0, tensor_cores=tensor_cores, bootstrap_gamma=0.97,
+                    what="traj_gym")
+    assert tot["trunc"] > 0 and tot["finished"] > 100

@@ -387,3 +387,29 @@ def test_rollout_traj_gym_lockstep(tensor_cores):
     tot = _lockstep(cfg, B=200, T=10, chunks=3, params=params, dist=0, tensor_cores=tensor_cores, bootstrap_gamma=0.97,
                     what="traj_gym")
     assert tot["trunc"] > 0 and tot["finished"] > 100
+
+
+@pytest.mark.parametrize("B", [300, 8192])
+def test_rollout_tensor_core_tile_spreading_is_bitwise_neutral(B, monkeypatch):
+    """QS_TC_EPT spreads a batch over more CTAs (ept < 128 live rows per 128-row UMMA tile; a tuning knob that measured
+    neutral, profiles/README.md).  Which rows of which tile an env occupies must not change a single bit of what the
+    kernel records."""
+    import torch
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    cfg = Q.EnvConfig.north_star(seed=5, env_id_offset=17, max_episode_steps=6)
+    params = torch.from_numpy(_random_policy(12, 0, seed=2, scale=0.6)).cuda()
+    outs = []
+    for ept in (None, "56", "37"):
+        if ept is None:
+            monkeypatch.delenv("QS_TC_EPT", raising=False)
+        else:
+            monkeypatch.setenv("QS_TC_EPT", ept)
+        eng = Engine(cfg, B, device=0)
+        st = eng.new_state(); eng.reset(st)
+        buf = eng.rollout_policy(st, params, T=9, t0=2, dist=0, tensor_cores=True, bootstrap_gamma=0.9)
+        torch.cuda.synchronize()
+        outs.append(({k: v.cpu().numpy() for k, v in buf.items()}, st.cpu().numpy()))
+    for b, stn in outs[1:]:
+        for k in outs[0][0]:
+            np.testing.assert_array_equal(b[k].view(np.uint32), outs[0][0][k].view(np.uint32), err_msg=k)
+        np.testing.assert_array_equal(stn.view(np.uint32), outs[0][1].view(np.uint32))

@@ -181,11 +181,12 @@ def random_states(n, seed=0, pos=1.5, vel=5.0, omega=10.0, spin=30.0, theta=50.0
 class GpuBackend:
     """Same interface as HostHarness, but through the real library: torch tensors -> C ABI -> sm_100a kernels."""
 
-    def __init__(self, cfg, num_envs=None):
+    def __init__(self, cfg, num_envs=None, lean=False):
         self.cfg = cfg
         self.D = cfg.obs_dim
         self._eng = None
         self._n = None
+        self.lean = lean          # True: request neither metrics nor terminal_obs, so that qs_step picks its lean kernels
 
     def _engine(self, n):
         from uav_reinforcement_learning_control_b200.engine import Engine
@@ -203,13 +204,13 @@ class GpuBackend:
         n = st.shape[1]
         eng = self._engine(n)
         d_st = self._up(st); d_act = self._up(np.asarray(action, dtype=np.float32)); d_first = self._up(first)
-        trunc = torch.zeros(n, device="cuda"); met = torch.zeros(4, n, device="cuda")
-        term = torch.full((n, self.D), float("nan"), device="cuda") if want_term else None
+        trunc = torch.zeros(n, device="cuda"); met = None if self.lean else torch.zeros(4, n, device="cuda")
+        term = torch.full((n, self.D), float("nan"), device="cuda") if (want_term and not self.lean) else None
         obs, rew, done = eng.step(d_st, d_act, truncated=trunc, metrics=met, terminal_obs=term, first_state=d_first)
         torch.cuda.synchronize()
         st[:] = d_st.cpu().numpy()
         return dict(obs=obs.cpu().numpy(), reward=rew.cpu().numpy(), done=done.cpu().numpy(),
-                    truncated=trunc.cpu().numpy(), metrics=met.cpu().numpy(),
+                    truncated=trunc.cpu().numpy(), metrics=None if met is None else met.cpu().numpy(),
                     terminal_obs=None if term is None else term.cpu().numpy())
 
     def reset(self, st, mask=None, want_first=False):

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(CSRC, "libquadsim.so")
 
 SOURCES = ["quadsim.cu"]
-HEADERS = ["qs_math.cuh", "qs_philox.cuh", "qs_dynamics.cuh", "qs_env.cuh", "qs_kernels.cuh", "qs_rollout.cuh",
+HEADERS = ["qs_math.cuh", "qs_pack2.cuh", "qs_step2.cuh", "qs_philox.cuh", "qs_dynamics.cuh", "qs_env.cuh", "qs_kernels.cuh", "qs_rollout.cuh",
            "qs_rollout_tc.cuh", "qs_ppo.cuh", "qs_traj.cuh"]
 
 NVCC_FLAGS = [

@@ -68,7 +68,9 @@ struct WarpResetScratch {
     float4 val[32];
 };
 
-template <int MODE>
+// The env of lane L has global id gid_warp_first + L * LANE_STRIDE (LANE_STRIDE = 2 in the packed step kernel, where a
+// lane owns two adjacent envs and the routine runs once per half with gid_warp_first advanced by the half).
+template <int MODE, int LANE_STRIDE = 1>
 __device__ __forceinline__ void warp_autoreset_smem(const QsParams& P, uint32_t gid_warp_first, Env& e, float* obs,
                                                     bool need, WarpResetScratch& S) {
     static_assert(ModeTraits<MODE>::kGym, "Philox re-sampling exists in the gym modes only");
@@ -83,7 +85,7 @@ __device__ __forceinline__ void warp_autoreset_smem(const QsParams& P, uint32_t 
         const int r = lane >> 2, blk = lane & 3;
         constexpr int kBlocks = (MODE == QS_MODE_HOVER_GYM) ? 4 : 3;
         if (r < npass && blk < kBlocks) {
-            const U4 rnd = philox4x32_10(U4{gid_warp_first + S.src[r], S.epi[r], (uint32_t)blk, STREAM_RESET}, P.philox_key);
+            const U4 rnd = philox4x32_10(U4{gid_warp_first + S.src[r] * (uint32_t)LANE_STRIDE, S.epi[r], (uint32_t)blk, STREAM_RESET}, P.philox_key);
             // words 0..11 -> state12 ranges, 12..14 -> target ranges: both live in one table of 16 (lo, hi) pairs
             const float* lo = blk < 3 ? &P.init_lo[4 * blk] : &P.target_lo[0];
             const float* hi = blk < 3 ? &P.init_hi[4 * blk] : &P.target_hi[0];

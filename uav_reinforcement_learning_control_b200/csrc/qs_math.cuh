@@ -27,6 +27,12 @@ QS_HD float fma_(float a, float b, float c) {
 #endif
 }
 
+// a constant in the lane type R (float here; the two-lane f2 specialisation lives in qs_pack2.cuh)
+template <class R> QS_HD R splat_(float c);
+template <> QS_HD float splat_<float>(float c) { return c; }
+
+QS_HD float abs_(float x) { return fabsf(x); }
+
 QS_HD float rsqrt_(float x) {
 #if defined(__CUDA_ARCH__)
     float r;                                // one MUFU.RSQ (<= 2 ulp); callers pass normal-range arguments
@@ -95,9 +101,11 @@ QS_HD float rcp_(float x) {
 
 // odd minimax polynomial of degree 15 for atan(t) on [-1, 1] (max error 3.1e-7 rad over float32 inputs, measured against
 // float64)
-QS_HD float atan_unit_(float t) {
-    const float s = t * t;
-    float p = -0.004054448804439777f;
+// (R = float, or the two-lane f2 of qs_pack2.cuh: the same polynomial on both lanes with packed FP32 instructions)
+template <class R>
+QS_HD R atan_unit_(R t) {
+    const R s = t * t;
+    R p = splat_<R>(-0.004054448804439777f);
     p = fma_(p, s, 0.021862509027492236f);
     p = fma_(p, s, -0.05591164661595514f);
     p = fma_(p, s, 0.09642144994501779f);
@@ -144,3 +152,5 @@ QS_HD bool finite_(float x) {
 }
 
 }  // namespace qs
+
+#include "qs_pack2.cuh"

@@ -237,7 +237,13 @@ template <int MODE, int DIST, int TILES, bool PARTNER = false>
 __global__ void __launch_bounds__(kM * TILES * (PARTNER ? 2 : 1), 1)
 rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, float* __restrict__ state,
                          const float* __restrict__ params, int steps, uint32_t t0, int deterministic,
-                         float bootstrap_gamma, RolloutBuffers rb, const float* __restrict__ first) {
+                         float bootstrap_gamma, RolloutBuffers rb, const float* __restrict__ first, int ept) {
+    // ept = envs per tile (<= 128): the first `ept` rows of the 128-row UMMA tile carry envs, the rest are padding.
+    // Spreading a small batch over more SMs this way (8192 envs: 147 CTAs x 56 envs instead of 64 CTAs x 128) was
+    // MEASURED NOT TO HELP (profiles/README.md, round 2: 4.52 / 4.41 / 4.50 / 4.60 ms for ept 128 / 96 / 64 / 56 at
+    // 8192 x 1024): a rollout is T sequential steps per CTA and the per-step latency chain of a CTA does not depend on
+    // how many of its rows are live, so the launch takes T x chain whatever the grid.  The knob stays as a test /
+    // tuning override (QS_TC_EPT); results are bitwise independent of it.
     constexpr int D = ModeTraits<MODE>::kObsDim;
     constexpr bool kGym = ModeTraits<MODE>::kGym;
     constexpr int K1 = (D + 2 <= 16) ? 16 : 32;            // observation + two bias slots
@@ -261,7 +267,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES)) + tile;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::bar_off(TILES) + 8 * TILES);
     unsigned char* tsm = smem + Smem::TILE0 + tile * Smem::TILE_BYTES;   // this tile's A operands
-    const int b0 = (blockIdx.x * TILES + tile) * kM;
+    const int b0 = (blockIdx.x * TILES + tile) * ept;
 
     // ---- one-time setup: weights fp32 -> bf16 UMMA layout, constants, barrier, TMEM -------------------
     for (int idx = gtid; idx < (Smem::WEND) / 4; idx += NT) reinterpret_cast<uint32_t*>(smem)[idx] = 0u;   // zero all B operands
@@ -330,7 +336,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     const uint64_t dA1b = make_desc(tbase + Smem::A1 + kBiasStep * 4096, 16 * 128, 128);   // the K step with the constant-1 slots
     uint32_t phase = 0;
 
-    const bool owner = half == 0 && (b0 + tid) < n;
+    const bool owner = half == 0 && tid < ept && (b0 + tid) < n;
     const uint32_t gid = P.env_id_offset + (uint32_t)(b0 + tid);
     float4* sEps = reinterpret_cast<float4*>(tsm + Smem::EPS);           // PARTNER only
     // standard-normal noise of (env gid, step index ts): Philox stream 1 + Box-Muller (fast intrinsics: the noise only
@@ -506,7 +512,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
 #pragma unroll
             for (int k = 0; k < D; ++k) stage[tid * D + k] = obs_[k];
             tile_sync<kTT>(tile);
-            const int rows = min(kM, n - b0);
+            const int rows = min(ept, n - b0);
             for (int idx = tid; idx < rows * D; idx += kM) dst_tile[idx] = stage[idx];
             tile_sync<kTT>(tile);                           // the staging tile is rewritten next step
         }
@@ -660,8 +666,14 @@ inline int launch_rollout_tc_tt(const QsParams& P, const Tables& T, int n, float
     using Smem = SmemT<(ModeTraits<MODE>::kObsDim + 2 <= 16) ? 16 : 32, PARTNER>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total(TILES));
     if (ce != cudaSuccess) return (int)ce;
-    kern<<<(n + kM * TILES - 1) / (kM * TILES), kM * TILES * (PARTNER ? 2 : 1), Smem::total(TILES), s>>>(
-        P, T, n, state, params, steps, t0, opt.deterministic, opt.bootstrap_gamma, rb, first);
+    int ept = kM;                                    // envs per tile; QS_TC_EPT: test / tuning override (see the kernel)
+    if (TILES == 1) {
+        const char* ov = getenv("QS_TC_EPT");
+        const int ept_env = ov ? atoi(ov) : 0;
+        if (ept_env > 0 && ept_env <= kM) ept = ept_env;
+    }
+    kern<<<(n + ept * TILES - 1) / (ept * TILES), kM * TILES * (PARTNER ? 2 : 1), Smem::total(TILES), s>>>(
+        P, T, n, state, params, steps, t0, opt.deterministic, opt.bootstrap_gamma, rb, first, ept);
     return 0;
 }
 

@@ -9,6 +9,7 @@
 #include <new>
 
 #include "qs_kernels.cuh"
+#include "qs_step2.cuh"
 #include "qs_rollout.cuh"
 #include "qs_rollout_tc.cuh"
 #include "qs_ppo.cuh"
@@ -178,6 +179,20 @@ static int launch_step(QsHandle h, int lo, int count, float* state, const float*
     if (Pq.mode == QS_MODE_HOVER_GYM && !Pq.battery && !Pq.rate_wrapper && !Pq.waypoint_mode && !Pq.pre_clip_action &&
         !metrics && !terminal_obs) {
         // plain north-star configuration: feature-folded instantiation (qs_env.cuh: FeatLean)
+        // two adjacent envs per thread on the packed FP32 pipe (qs_step2.cuh) whenever the pairs are 8-byte aligned; an
+        // odd last env (and any unaligned call) goes through the one-env-per-thread kernel
+        static const int use_step2 = getenv("QS_STEP2") ? atoi(getenv("QS_STEP2")) : 1;      // A/B knob
+        if (use_step2 && (h->n & 1) == 0 && (lo & 1) == 0 && count >= 2 &&
+            (((uintptr_t)state | (uintptr_t)reward | (uintptr_t)done | (uintptr_t)truncated) & 7u) == 0) {
+            const int npairs = count / 2;
+            cudaLaunchConfig_t l2 = lc;
+            l2.gridDim = dim3((unsigned)nblocks(npairs, qs::kBlock2)); l2.blockDim = dim3(qs::kBlock2);
+            cudaLaunchKernelEx(&l2, qs::step2_kernel, h->P, (int)h->n, lo / 2, npairs, state, a4, obs, reward, done, truncated);
+            if ((count & 1) == 0) return check_launch("step2_kernel");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            lc.gridDim = dim3(1u);
+            lo += 2 * npairs; count = 1;
+        }
         cudaLaunchKernelEx(&lc, qs::step_kernel<QS_MODE_HOVER_GYM, qs::FeatLean>, h->P, h->tables(), (int)h->n, lo, count, state, a4,
                            obs, reward, done, truncated, metrics, terminal_obs, first_state);
         return check_launch("step_kernel<lean>");

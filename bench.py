@@ -341,7 +341,14 @@ def main():
     traffic, traffic_rec = measured_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
+                "traffic_steady_state": None if traffic_rec is None else traffic_rec.get("steady_state", {}).get("dram_bytes_per_launch"),
                 "frac_dram": None if traffic is None else (traffic / (us_per_launch * 1e-6) / 1e9) / peak,
+                "frac_dram_steady_state": None if (traffic_rec is None or "steady_state" not in traffic_rec) else
+                (traffic_rec["steady_state"]["dram_bytes_per_launch"] / (us_per_launch * 1e-6) / 1e9) / peak,
+                "traffic_note": "traffic = dram__bytes of ONE cold launch (ncu flushes caches first): reads match the algorithmic "
+                                "126 MB, writes are short of the algorithmic 168 MB because dirty lines still sit in the 126 MB L2 "
+                                "when the kernel ends; traffic_steady_state = the same launches without cache flushes, where every "
+                                "launch also absorbs its predecessor's write-backs",
                 "kernel": "qs::step_kernel<QS_MODE_HOVER_GYM, FeatLean>", "bytes_per_env_step": bytes_per,
                 "bytes_per_launch": bytes_per * n, "us_per_launch": us_per_launch,
                 "traffic_source": None if traffic_rec is None else traffic_rec.get("how"),

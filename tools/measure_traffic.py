@@ -56,27 +56,42 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     cmd = [sys.executable, os.path.abspath(__file__), "--driver"]
     subprocess.check_call(cmd)                                   # must exit 0 without ncu first
-    raw = os.path.join(OUT, "step_kernel_traffic_ncu.csv")
-    subprocess.check_call(["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum",
-                           "--clock-control", "none", "-k", "regex:step_kernel", "-s", str(WARM), "-c", str(COUNT),
-                           "--csv", "--log-file", raw] + cmd)
-    rd, wr, dur = [], [], []
-    with open(raw) as f:
-        rows = [r for r in csv.reader(l for l in f if l.startswith('"'))]
-    hdr = rows[0]
-    iname, ival, iunit = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3,
              "nsecond": 1e-3}
-    for r in rows[1:]:
-        v = float(r[ival].replace(",", "")) * scale.get(r[iunit], 1.0)
-        {"dram__bytes_read.sum": rd, "dram__bytes_write.sum": wr, "gpu__time_duration.sum": dur}.get(r[iname], []).append(v)
+
+    def capture(tag, extra):
+        raw = os.path.join(OUT, f"step_kernel_traffic_ncu{tag}.csv")
+        subprocess.check_call(["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum",
+                               "--clock-control", "none"] + extra + ["-k", "regex:step2?_kernel", "-s", str(WARM), "-c", str(COUNT),
+                               "--csv", "--log-file", raw] + cmd)
+        rd, wr, dur = [], [], []
+        with open(raw) as f:
+            rows = [r for r in csv.reader(l for l in f if l.startswith('"'))]
+        hdr = rows[0]
+        iname, ival, iunit = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        for r in rows[1:]:
+            v = float(r[ival].replace(",", "")) * scale.get(r[iunit], 1.0)
+            {"dram__bytes_read.sum": rd, "dram__bytes_write.sum": wr, "gpu__time_duration.sum": dur}.get(r[iname], []).append(v)
+        return rd, wr, dur
+
+    # (1) ncu's default cache control: caches flushed before every profiled launch -> what ONE cold launch moves while it
+    #     runs (dirty lines still in the 126 MB L2 when the kernel ends are NOT counted: they are written back later)
+    rd, wr, dur = capture("", [])
+    # (2) no cache control: every launch also absorbs the write-backs the previous launch left behind, i.e. the steady
+    #     state of back-to-back launches over rotating state sets (bench.py's loop)
+    rd2, wr2, dur2 = capture("_steady", ["--cache-control", "none"])
     import bench
     n = bench.NUM_ENVS
     rec = {"dram_bytes_per_launch": (sum(rd) + sum(wr)) / max(len(rd), 1),
            "dram_read_bytes_per_launch": sum(rd) / max(len(rd), 1), "dram_write_bytes_per_launch": sum(wr) / max(len(wr), 1),
            "algorithmic_bytes_per_launch": 280 * n, "launches": len(rd), "us_per_launch_under_ncu": sum(dur) / max(len(dur), 1),
+           "steady_state": {"dram_bytes_per_launch": (sum(rd2) + sum(wr2)) / max(len(rd2), 1),
+                            "dram_read_bytes_per_launch": sum(rd2) / max(len(rd2), 1),
+                            "dram_write_bytes_per_launch": sum(wr2) / max(len(wr2), 1),
+                            "us_per_launch_under_ncu": sum(dur2) / max(len(dur2), 1),
+                            "how": "same capture with --cache-control none: each launch also takes the previous launch's write-backs"},
            "source_fingerprint": bench.source_fingerprint(),
-           "how": "tools/measure_traffic.py: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on "
+           "how": "tools/measure_traffic.py (cold launch, ncu flushes caches before each): ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on "
                   f"{COUNT} step_kernel launches of bench.py's loop (2^20 envs, {bench.STATE_SETS} rotating state sets), shipped libquadsim.so"}
     with open(os.path.join(OUT, "step_kernel_traffic.json"), "w") as f:
         json.dump(rec, f, indent=1)

@@ -217,7 +217,8 @@ typedef struct QsPolicyDesc {
     float bootstrap_gamma;  /* > 0: SB3 timeout bootstrap, reward += gamma * V(terminal_obs) on truncation */
     int32_t tensor_cores;   /* 0: fp32 FMA path; 1: tcgen05/TMEM path (bf16 operands, fp32 accumulate): hover_gym dist 0|1,
                                traj_gym dist 0, mjx_brax / hover_brax dist 1 */
-    int32_t reserved[1];
+    int32_t sample_seed;    /* qs_ppo_grad, dist 1 only: key of the entropy-term noise (brax draws a fresh action sample per loss
+                               evaluation); the caller advances it every update.  Ignored elsewhere. */
 } QsPolicyDesc;
 
 /* number of float32 in the packed parameter vector for a policy description:
@@ -252,8 +253,12 @@ int qs_gae(int32_t T, int32_t B, const float* reward, const float* value, const 
 /*
  * PPO update on device.  Replaces the caller of the rollout, SB3 ``PPO.train`` as configured by
  * train.py:50-68 (MlpPolicy pi=[128,128] vf=[128,128] ReLU, Adam eps 1e-5, clip_range, ent_coef, vf_coef, max_grad_norm,
- * per-minibatch advantage normalisation).  Covers the SB3 policy (obs_dim 12, dist 0); handle-free like qs_gae, runs on
- * the current device.  All pointers are device memory except the scalars.
+ * per-minibatch advantage normalisation), and the loss of brax ``ppo_train.train`` (train_brax_ppo.py:589-620: tanh-normal
+ * policy, 21-D observation) on precomputed advantages.  Covers obs_dim 12 | 21 with dist 0 | 1; handle-free like qs_gae,
+ * runs on the current device.  All pointers are device memory except the scalars.
+ * normalize_adv: 0 off, 1 (adv - mean) / (unbiased std + 1e-8) as SB3 / torch, 2 the same with the population std as brax / jnp.
+ * dist 1: loss = -mean(min(rho A, clip(rho) A)) + vf_coef mean((ret - V)^2) - ent_coef mean(H) with H the tanh-normal entropy
+ * estimate brax uses (one fresh sample per row, keyed by desc->sample_seed); brax's value loss is vf_coef = 0.25.
  *
  * qs_ppo_grad: gradient of   -mean(min(r A, clip(r, 1-c, 1+c) A)) + vf_coef mean((ret - V)^2) - ent_coef H(pi)
  * over the minibatch rows idx[0..n) (idx == NULL: rows 0..n-1) of the rollout buffers obs [N][12], act [N][4] (raw
@@ -279,6 +284,17 @@ int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const floa
 int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* grad, float* m, float* v, int32_t step,
                 float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, float* norm_out,
                 void* stream);
+
+/*
+ * Running observation normaliser of the Brax trainer (normalize_observations=True, train_brax_ppo.py:611;
+ * brax.training.acme.running_statistics): merges obs [n][obs_dim] into running = {count, mean[obs_dim], M2[obs_dim]}
+ * (device doubles, zero before the first call) with the parallel Welford update and writes mean_out / inv_std_out
+ * (normally pointers INTO the packed parameter vector: its obs_mean / obs_inv_std entries), inv_std = 1 / clip(sqrt(M2 /
+ * count), std_min, std_max).  workspace: qs_obs_stats_workspace_bytes(obs_dim) bytes of device scratch.
+ */
+int64_t qs_obs_stats_workspace_bytes(int32_t obs_dim);
+int qs_obs_stats_update(const float* obs, int64_t n, int32_t obs_dim, double* running, float* mean_out, float* inv_std_out,
+                        float std_min, float std_max, void* workspace, void* stream);
 
 /*
  * Multi-GPU form of the update's gradient exchange (one process per GPU; what brax's ``lax.pmean`` of the gradients does

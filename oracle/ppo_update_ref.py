@@ -14,6 +14,15 @@ published source:
 The backward pass is written out by hand (no autograd here); tests/test_ppo_update.py additionally checks it against
 torch autograd of uav_reinforcement_learning_control_b200.ppo.ActorCritic.evaluate.
 
+``dist=1`` is the loss of brax ``ppo_train.train`` as the reference configures it (train_brax_ppo.py:589-620: tanh-normal
+policy over the 21-D raw observation; brax.training.agents.ppo.losses.compute_ppo_loss, third party, restated from its
+published source) on precomputed advantages / value targets:
+
+    scale  = softplus(raw_scale) + 0.001,   logp = sum_k [N(a_raw; loc, scale) - ldj(a_raw)],  ldj(x) = 2 (log 2 - x - softplus(-2x))
+    A      = (adv - mean(adv)) / (std(adv) + 1e-8)                      (population std, jnp.std)
+    loss   = -mean(min(rho A, clip(rho, 1-c, 1+c) A)) + vf_coef mean((ret - V)^2) - ent_coef mean(H)     (brax: vf_coef = 0.25)
+    H_i    = sum_k [1/2 + log sqrt(2 pi) + log scale_k + ldj(loc_k + scale_k eps_ik)]      eps: one fresh N(0,1) draw per row
+
 ``bf16=True`` models the rounding points of the tcgen05 kernel (csrc/qs_ppo.cuh): every MMA operand -- normalised
 observation, weights, relu(H1), relu(H2), the head gradient, the masked hidden gradients -- is rounded to bfloat16,
 products and sums are exact-ish (float64 here, fp32 in TMEM), hidden biases enter as bf16 hi + lo pairs.
@@ -27,11 +36,27 @@ from .ppo_ref import A, H, LOG_SQRT_2PI, bf16_round, bias_hilo, unpack
 PARAM_ORDER = ["aW1", "ab1", "aW2", "ab2", "aW3", "ab3", "cW1", "cb1", "cW2", "cb2", "cW3", "cb3", "log_std", "mean", "inv_std"]
 
 
-def adv_normalise(adv):
+def adv_normalise(adv, ddof=1):
     adv = np.asarray(adv, dtype=np.float64)
     n = adv.size
-    std = np.sqrt(np.sum((adv - adv.mean()) ** 2) / (n - 1)) if n > 1 else 0.0
+    std = np.sqrt(np.sum((adv - adv.mean()) ** 2) / (n - ddof)) if n > ddof else 0.0
     return (adv - adv.mean()) / (std + 1e-8)
+
+
+def softplus(x):
+    return np.logaddexp(0.0, x)
+
+
+def entropy_noise(sample_seed, rows):
+    """The four standard normals the kernel draws for the entropy term of row j: Philox4x32-10 with key
+    (sample_seed, 0x5eed0ea7), counter (j, 0, 0, 3), Box-Muller pairs (csrc/qs_ppo_generic.cuh)."""
+    from . import philox
+    rows = np.asarray(rows, dtype=np.uint32)
+    ctr = np.stack([rows, np.zeros_like(rows), np.zeros_like(rows), np.full_like(rows, 3)], axis=1)
+    raw = philox.philox4x32_10(ctr, np.array([int(sample_seed) & 0xFFFFFFFF, 0x5eed0ea7], dtype=np.uint32))
+    e0, e1 = philox.normal_pair(raw[:, 0], raw[:, 1])
+    e2, e3 = philox.normal_pair(raw[:, 2], raw[:, 3])
+    return np.stack([e0, e1, e2, e3], axis=1)
 
 
 def _mlp_fwd_bwd(x, W1, b1, W2, b2, W3, dout_fn, q, qb):
@@ -49,10 +74,13 @@ def _mlp_fwd_bwd(x, W1, b1, W2, b2, W3, dout_fn, q, qb):
     return out, g
 
 
-def grad(params, obs, act, old_logp, adv, ret, clip_range, vf_coef, ent_coef, normalize_adv=True, bf16=False):
-    """-> (flat gradient in the packed layout, stats dict).  obs [n,12], act [n,4] raw samples, old_logp/adv/ret [n]."""
+def grad(params, obs, act, old_logp, adv, ret, clip_range, vf_coef, ent_coef, normalize_adv=True, bf16=False, dist=0,
+         ddof=None, eps_entropy=None):
+    """-> (flat gradient in the packed layout, stats dict).  obs [n, D], act [n,4] raw samples, old_logp/adv/ret [n].
+    dist 1: eps_entropy [n, 4] is the noise of the entropy sample (entropy_noise(sample_seed, rows) for the kernel's)."""
     obs_dim = np.asarray(obs).shape[1]
-    pp = unpack(params, obs_dim, 0)
+    pp = unpack(params, obs_dim, dist)
+    ddof = (1 if dist == 0 else 0) if ddof is None else ddof
     n = len(obs)
     q = bf16_round if bf16 else (lambda a: np.asarray(a, dtype=np.float64))
     qb = bias_hilo if bf16 else (lambda a: np.asarray(a, dtype=np.float64))
@@ -60,14 +88,45 @@ def grad(params, obs, act, old_logp, adv, ret, clip_range, vf_coef, ent_coef, no
         x = q((np.asarray(obs, dtype=np.float32) - pp["mean"].astype(np.float32)) * pp["inv_std"].astype(np.float32))
     else:
         x = (np.asarray(obs, dtype=np.float64) - pp["mean"]) * pp["inv_std"]
-    Ahat = adv_normalise(adv) if normalize_adv else np.asarray(adv, dtype=np.float64)
+    Ahat = adv_normalise(adv, ddof) if normalize_adv else np.asarray(adv, dtype=np.float64)
     act = np.asarray(act, dtype=np.float64)
     old_logp = np.asarray(old_logp, dtype=np.float64)
     ret = np.asarray(ret, dtype=np.float64)
-    ls = pp["log_std"]
-    inv_sig = np.exp(-ls)
+    ls = pp["log_std"] if dist == 0 else None
+    inv_sig = np.exp(-ls) if dist == 0 else None
     st = {}
     extra = {}
+    Ao = A if dist == 0 else 2 * A
+
+    def surrogate(logp):
+        lr = logp - old_logp
+        ratio = np.exp(lr)
+        lo, hi = 1.0 - clip_range, 1.0 + clip_range
+        unclipped, clipped = Ahat * ratio, Ahat * np.clip(ratio, lo, hi)
+        inside = (ratio >= lo) & (ratio <= hi)
+        active = inside | (unclipped < clipped)
+        st["pg_loss"] = float(np.mean(-np.minimum(unclipped, clipped)))
+        st["clip_frac"] = float(np.mean(~inside))
+        st["approx_kl"] = float(np.mean((ratio - 1.0) - lr))
+        return np.where(active, -Ahat * ratio, 0.0)          # d loss_i / d logp_i (before the 1/n)
+
+    def actor_dout_tanh(out):
+        loc = out[:, :A] + pp["ab3"][:A]
+        rs = out[:, A:2 * A] + pp["ab3"][A:]
+        scale = softplus(rs) + 0.001
+        sig = 1.0 / (1.0 + np.exp(-rs))
+        z = (act - loc) / scale
+        ldj_a = 2.0 * (np.log(2.0) - act - softplus(-2.0 * act))
+        logp = np.sum(-0.5 * z * z - np.log(scale) - LOG_SQRT_2PI - ldj_a, axis=1)
+        g = surrogate(logp)
+        xs = loc + scale * eps_entropy
+        th = np.tanh(xs)
+        ent = np.sum(0.5 + LOG_SQRT_2PI + np.log(scale) + 2.0 * (np.log(2.0) - xs - softplus(-2.0 * xs)), axis=1)
+        st["entropy"] = float(np.mean(ent))
+        d = np.zeros_like(out)
+        d[:, :A] = g[:, None] * z / scale + (-ent_coef) * (-2.0 * th)
+        d[:, A:2 * A] = (g[:, None] * (z * z - 1.0) / scale + (-ent_coef) * (1.0 / scale - 2.0 * th * eps_entropy)) * sig
+        return d
 
     def actor_dout(out):
         mean = out[:, :A] + pp["ab3"]
@@ -96,26 +155,43 @@ def grad(params, obs, act, old_logp, adv, ret, clip_range, vf_coef, ent_coef, no
         d[:, 0] = 2.0 * vf_coef * err
         return d
 
-    W3a = np.zeros((H, 16)); W3a[:, :A] = pp["aW3"]
+    W3a = np.zeros((H, 16)); W3a[:, :Ao] = pp["aW3"]
     W3c = np.zeros((H, 16)); W3c[:, 0] = pp["cW3"]
-    _, ga = _mlp_fwd_bwd(x, pp["aW1"], pp["ab1"], pp["aW2"], pp["ab2"], W3a, actor_dout, q, qb)
+    if dist == 1 and eps_entropy is None:
+        eps_entropy = np.zeros((n, A))
+    _, ga = _mlp_fwd_bwd(x, pp["aW1"], pp["ab1"], pp["aW2"], pp["ab2"], W3a, actor_dout if dist == 0 else actor_dout_tanh, q, qb)
     _, gc = _mlp_fwd_bwd(x, pp["cW1"], pp["cb1"], pp["cW2"], pp["cb2"], W3c, critic_dout, q, qb)
     s = 1.0 / n
     parts = {
         "aW1": ga["W1"] * s, "ab1": ga["b1"] * s, "aW2": ga["W2"] * s, "ab2": ga["b2"] * s,
-        "aW3": ga["W3"][:, :A] * s, "ab3": ga["b3"][:A] * s,
+        "aW3": ga["W3"][:, :Ao] * s, "ab3": ga["b3"][:Ao] * s,
         "cW1": gc["W1"] * s, "cb1": gc["b1"] * s, "cW2": gc["W2"] * s, "cb2": gc["b2"] * s,
         "cW3": gc["W3"][:, 0] * s, "cb3": gc["b3"][:1] * s,
-        "log_std": extra["dls"] * s - ent_coef,
+        "log_std": (extra["dls"] * s - ent_coef) if dist == 0 else np.zeros(0),
         "mean": np.zeros(obs_dim), "inv_std": np.zeros(obs_dim),
     }
     flat = np.concatenate([np.asarray(parts[k], dtype=np.float64).reshape(-1) for k in PARAM_ORDER])
     return flat, st
 
 
-def split(flat, obs_dim=12):
+def split(flat, obs_dim=12, dist=0):
     """Packed vector -> dict of named views (for per-tensor error reports)."""
-    return unpack(flat, obs_dim, 0)
+    return unpack(flat, obs_dim, dist)
+
+
+def running_obs_stats(state, obs, std_min=1e-6, std_max=1e6):
+    """brax.training.acme.running_statistics.update + the normaliser it implies (third party, restated): merge the batch
+    into state = (count, mean[D], summed_variance[D]); returns (state', mean, inv_std) with
+    std = clip(sqrt(max(summed_variance / count, 0)), std_min, std_max)."""
+    count, mean, m2 = state
+    obs = np.asarray(obs, dtype=np.float64)
+    n = obs.shape[0]
+    tot = count + n
+    diff0 = obs - mean
+    mean_new = mean + diff0.sum(axis=0) / tot
+    m2_new = m2 + (diff0 * (obs - mean_new)).sum(axis=0)
+    std = np.clip(np.sqrt(np.maximum(m2_new / tot, 0.0)), std_min, std_max)
+    return (tot, mean_new, m2_new), mean_new, 1.0 / std
 
 
 def adam_step(params, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-5, max_grad_norm=0.5, grad_scale=1.0, n_train=None):

@@ -358,3 +358,182 @@ def test_peer_memory_update_two_gpus():
     d = json.loads(lines[-1])
     assert d["world"] == 2 and d["peer_params_bitwise_in_sync_across_ranks"]
     assert d["max_abs_diff_peer_vs_nccl"] == 0.0 and d["max_abs_param_change"] > 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Brax side of N4: 21-D observation, tanh-normal policy, brax's PPO loss and running observation
+# normaliser.  The oracle extension is pinned to torch autograd on the CPU exactly like the SB3 one above.
+# ---------------------------------------------------------------------------------------------------------------------
+B_CLIP, B_VF, B_ENT = 0.3, 0.25, 1e-2            # brax ppo defaults: clipping_epsilon 0.3, v_loss 0.5 * 0.5, entropy_cost (train_brax_ppo.py:440-455)
+
+
+def _policy_brax(seed, obs_dim=21):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for out in (8, 1):
+        for (i, o) in ((obs_dim, 128), (128, 128), (128, out)):
+            lim = (3.0 / i) ** 0.5
+            parts += [rng.uniform(-lim, lim, i * o), rng.uniform(-0.1, 0.1, o)]
+    parts += [rng.uniform(-0.2, 0.2, obs_dim), rng.uniform(0.5, 1.5, obs_dim)]
+    p = np.concatenate(parts).astype(np.float32)
+    assert p.size == ppo_ref.param_count(obs_dim, 1)
+    return p
+
+
+def _batch_brax(params, N, seed, obs_dim=21):
+    rng = np.random.default_rng(seed)
+    obs = rng.uniform(-1, 1, (N, obs_dim)).astype(np.float32)
+    pp = ppo_ref.unpack(params, obs_dim, 1)
+    head, value = ppo_ref.forward(pp, obs)
+    eps = rng.normal(size=(N, 4))
+    raw, _, logp = ppo_ref.sample(pp, head, eps, 1)
+    act = raw.astype(np.float32)
+    old_logp = (logp + rng.normal(scale=0.2, size=N)).astype(np.float32)
+    adv = (2.0 * (eps @ np.array([1.0, -1.0, 0.5, 0.2])) + 0.5 * rng.normal(size=N) + 0.3).astype(np.float32)
+    ret = (value + 0.5 + 0.5 * np.sin(3.0 * obs[:, 0]) + 0.3 * obs[:, 5] + 0.1 * rng.normal(size=N)).astype(np.float32)
+    return obs, act, old_logp, adv, ret
+
+
+def _autograd_grad_brax(params, batch, eps_ent, obs_dim=21, normalize=True):
+    """brax compute_ppo_loss on precomputed advantages, written with torch ops (float64) and differentiated by autograd."""
+    import torch
+    pp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=k not in ("mean", "inv_std")) for k, v in ppo_ref.unpack(params, obs_dim, 1).items()}
+    obs, act, old_logp, adv, ret = [torch.from_numpy(np.asarray(b, dtype=np.float64)) for b in batch]
+    eps_ent = torch.from_numpy(np.asarray(eps_ent, dtype=np.float64))
+    x = (obs - pp["mean"]) * pp["inv_std"]
+    h = torch.relu(x @ pp["aW1"] + pp["ab1"]); h = torch.relu(h @ pp["aW2"] + pp["ab2"]); head = h @ pp["aW3"] + pp["ab3"]
+    c = torch.relu(x @ pp["cW1"] + pp["cb1"]); c = torch.relu(c @ pp["cW2"] + pp["cb2"]); value = c @ pp["cW3"] + pp["cb3"][0]
+    loc, scale = head[:, :4], torch.nn.functional.softplus(head[:, 4:]) + 0.001
+    dist = torch.distributions.Normal(loc, scale)
+    ldj = lambda t: 2.0 * (np.log(2.0) - t - torch.nn.functional.softplus(-2.0 * t))
+    logp = (dist.log_prob(act) - ldj(act)).sum(-1)
+    a = adv
+    if normalize:
+        a = (a - a.mean()) / (a.std(unbiased=False) + 1e-8)
+    rho = torch.exp(logp - old_logp)
+    pg = -torch.min(rho * a, torch.clamp(rho, 1 - B_CLIP, 1 + B_CLIP) * a).mean()
+    vl = ((ret - value) ** 2).mean()
+    ent = (dist.entropy() + ldj(loc + scale * eps_ent)).sum(-1).mean()
+    (pg + B_VF * vl - B_ENT * ent).backward()
+    order = ["aW1", "ab1", "aW2", "ab2", "aW3", "ab3", "cW1", "cb1", "cW2", "cb2", "cW3", "cb3"]
+    g = np.concatenate([pp[k].grad.reshape(-1).numpy() for k in order] + [np.zeros(2 * obs_dim)])
+    return g, float(pg.detach()), float(vl.detach()), float(ent.detach())
+
+
+@pytest.mark.parametrize("obs_dim", [21, 12])
+def test_oracle_brax_gradient_matches_torch_autograd(obs_dim):
+    params = _policy_brax(11, obs_dim)
+    batch = _batch_brax(params, 600, 12, obs_dim)
+    eps_ent = U.entropy_noise(77, np.arange(600))
+    assert abs(eps_ent.mean()) < 0.1 and abs(eps_ent.std() - 1.0) < 0.1
+    g_ref, pg, vl, ent = _autograd_grad_brax(params, batch, eps_ent, obs_dim)
+    g, st = U.grad(params, *batch, B_CLIP, B_VF, B_ENT, dist=1, eps_entropy=eps_ent)
+    assert 0.05 < st["clip_frac"] < 0.95, st
+    np.testing.assert_allclose(g, g_ref, rtol=1e-9, atol=1e-12)
+    assert abs(st["pg_loss"] - pg) < 1e-12 and abs(st["v_loss"] - vl) < 1e-12 and abs(st["entropy"] - ent) < 1e-12
+
+
+def test_oracle_running_obs_stats_match_direct_moments():
+    rng = np.random.default_rng(5)
+    state = (0.0, np.zeros(21), np.zeros(21))
+    chunks = [rng.normal(loc=3.0, scale=[0.1 + 0.2 * k for k in range(21)], size=(n, 21)) for n in (1000, 37, 5000)]
+    for c in chunks:
+        state, mean, inv_std = U.running_obs_stats(state, c)
+    allx = np.concatenate(chunks)
+    np.testing.assert_allclose(mean, allx.mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(1.0 / inv_std, allx.std(axis=0), rtol=1e-10)
+    # a constant feature clips at std_min instead of dividing by zero
+    st2, m2, i2 = U.running_obs_stats((0.0, np.zeros(2), np.zeros(2)), np.ones((10, 2)))
+    assert np.all(i2 == 1e6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("obs_dim,dist,n", [(21, 1, 4096), (21, 1, 1000), (12, 1, 2048), (21, 0, 2048)])
+def test_fused_gradient_generic_policies_match_oracle(obs_dim, dist, n):
+    """qs_ppo_grad for the Brax policy family (21-D obs, tanh-normal head) and the mixed variants, through
+    ppo_grad_tc_kernel<D, DIST> (qs_ppo_generic.cuh), against the bf16-operand oracle: 2e-3 per tensor."""
+    import torch
+    from uav_reinforcement_learning_control_b200.ppo import FusedUpdater
+    params = _policy_brax(21, obs_dim) if dist == 1 else _policy(21, obs_dim)
+    if dist == 1:
+        batch = _batch_brax(params, n, 22, obs_dim)
+    else:
+        rng = np.random.default_rng(22)
+        obs = rng.uniform(-1, 1, (n, obs_dim)).astype(np.float32)
+        pp = ppo_ref.unpack(params, obs_dim, 0)
+        head, value = ppo_ref.forward(pp, obs)
+        eps = rng.normal(size=(n, 4))
+        act = (head + np.exp(pp["log_std"]) * eps).astype(np.float32)
+        logp = np.sum(-0.5 * eps * eps - pp["log_std"] - ppo_ref.LOG_SQRT_2PI, axis=1)
+        batch = (obs, act, (logp + rng.normal(scale=0.15, size=n)).astype(np.float32),
+                 (2.0 * (eps @ np.array([1.0, -1.0, 0.5, 0.2])) + 0.3).astype(np.float32), (value + 0.5).astype(np.float32))
+    up = FusedUpdater("cuda:0", obs_dim=obs_dim, dist=dist)
+    dev = [torch.from_numpy(np.ascontiguousarray(b)).cuda() for b in batch]
+    clip, vf, ent = (B_CLIP, B_VF, B_ENT) if dist == 1 else (CLIP, VF, ENT)
+    g = up.grad(torch.from_numpy(params).cuda(), *dev, clip_range=clip, vf_coef=vf, ent_coef=ent,
+                normalize_adv=2 if dist == 1 else 1, sample_seed=1234)
+    torch.cuda.synchronize()
+    eps_ent = U.entropy_noise(1234, np.arange(n)) if dist == 1 else None
+    g_ref, st = U.grad(params, *batch, clip, vf, ent, bf16=True, dist=dist, eps_entropy=eps_ent)
+    got = g.cpu().numpy().astype(np.float64)
+    a, b = U.split(got[:up.P], obs_dim, dist), U.split(g_ref, obs_dim, dist)
+    for k in U.PARAM_ORDER:
+        if b[k].size == 0:
+            continue
+        tol = (1e-2 if k == "log_std" else 2e-3) * max(np.abs(b[k]).max(), 1e-12) + 1e-9
+        assert np.abs(a[k] - b[k]).max() <= tol, (k, np.abs(a[k] - b[k]).max(), np.abs(b[k]).max())
+    stats = got[up.P:]
+    assert abs(stats[0] / n - st["pg_loss"]) < 2e-3 and abs(stats[1] / n - st["v_loss"]) < 2e-3 * max(1.0, st["v_loss"])
+    assert stats[4] == n and abs(stats[2] / n - st["clip_frac"]) < 5e-3
+    if dist == 1:
+        assert abs(stats[5] / n - st["entropy"]) < 5e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("obs_dim", [21, 12])
+def test_running_obs_normaliser_kernel_matches_oracle(obs_dim):
+    import torch
+    from uav_reinforcement_learning_control_b200.ppo import FusedUpdater
+    up = FusedUpdater("cuda:0", obs_dim=obs_dim, dist=1)
+    params = torch.from_numpy(_policy_brax(3, obs_dim)).cuda()
+    rng = np.random.default_rng(8)
+    state = (0.0, np.zeros(obs_dim), np.zeros(obs_dim))
+    for n in (5000, 777, 200000):
+        x = (rng.normal(loc=np.linspace(-3, 3, obs_dim), scale=np.linspace(0.05, 4.0, obs_dim), size=(n, obs_dim))).astype(np.float32)
+        x[:, 3] = 1.0                                   # a constant feature (the quaternion w of a level drone): std clips at 1e-6
+        up.update_obs_stats(params, torch.from_numpy(x).cuda())
+        state, mean, inv_std = U.running_obs_stats(state, x)
+        torch.cuda.synchronize()
+        got = params.cpu().numpy()
+        L = ppo_ref.param_count(obs_dim, 1)
+        np.testing.assert_allclose(got[L - 2 * obs_dim:L - obs_dim], mean, rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(got[L - obs_dim:], inv_std, rtol=1e-5)
+    assert got[L - obs_dim + 3] == np.float32(1e6)
+
+
+@pytest.mark.gpu
+def test_trainer_runs_fused_on_mjx_brax():
+    """PPOTrainer on the MJX-parity env (JaxMJXQuadBraxEnv semantics, 21-D obs, Episode + AutoReset wrappers) with brax's
+    reference hyper-parameters: tcgen05 rollout -> brax GAE -> running obs normaliser -> fused tanh-normal PPO update.
+    The update must be the fused kernels (no torch autograd), keep everything finite and actually move the policy."""
+    import torch
+    from uav_reinforcement_learning_control_b200 import config as Q
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    from uav_reinforcement_learning_control_b200.ppo import PPOConfig, PPOTrainer
+    eng = Engine(Q.EnvConfig.mjx_brax(episode_length=500, auto_reset=Q.RESET_RESTORE_FIRST, seed=3), 2048, device=0)
+    tr = PPOTrainer(eng, PPOConfig.brax_reference(), seed=0)
+    assert tr.fused and tr.brax and tr.updater.dist == 1 and tr.updater.obs_dim == 21 and tr.policy is None
+    p0 = tr.params.clone()
+    launches0 = eng.launch_count()
+    log = tr.train(3)
+    torch.cuda.synchronize()
+    assert eng.launch_count() - launches0 >= 3 * (1 + 1 + 1 + 4 * 16 * 2)       # rollout, GAE, obs stats, 64 x (grad, adam) per iteration
+    assert torch.isfinite(tr.params).all()
+    L = tr.params.numel()
+    assert (tr.params[:L - 42] != p0[:L - 42]).float().mean() > 0.9               # the weights moved
+    mean, inv_std = tr.params[L - 42:L - 21].cpu().numpy(), tr.params[L - 21:].cpu().numpy()
+    assert abs(mean[2] - 1.0) < 0.2 and abs(mean[3] - 1.0) < 0.05                 # z ~ 1 m, quaternion w ~ 1
+    assert (inv_std > 1.0).all() and np.isfinite(inv_std).all()                   # every feature's std is below 1 in these units
+    assert float(tr.updater.obs_running[0].item()) == 3 * 10 * 2048
+    for s in log:
+        assert np.isfinite(s["pg_loss"]) and np.isfinite(s["v_loss"]) and 0.0 <= s["clip_frac"] <= 1.0

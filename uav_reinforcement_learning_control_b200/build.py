@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(CSRC, "libquadsim.so")
 
 SOURCES = ["quadsim.cu"]
 HEADERS = ["qs_math.cuh", "qs_pack2.cuh", "qs_step2.cuh", "qs_philox.cuh", "qs_dynamics.cuh", "qs_env.cuh", "qs_kernels.cuh", "qs_rollout.cuh",
-           "qs_rollout_tc.cuh", "qs_ppo.cuh", "qs_traj.cuh"]
+           "qs_rollout_tc.cuh", "qs_ppo.cuh", "qs_ppo_generic.cuh", "qs_traj.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -68,7 +68,7 @@ class QsParams(C.Structure):
 class QsPolicyDesc(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("hidden", C.c_int32), ("act_dim", C.c_int32), ("dist", C.c_int32),
                 ("deterministic", C.c_int32), ("bootstrap_gamma", C.c_float), ("tensor_cores", C.c_int32),
-                ("reserved", C.c_int32 * 1)]
+                ("sample_seed", C.c_int32)]
 
 
 _PI32 = float(np.float32(np.pi))

@@ -6,9 +6,13 @@
 // minibatch   loss = -mean(min(r A, clip(r, 1-e, 1+e) A)) + vf_coef * mean((ret - V)^2) - ent_coef * H(pi).
 //
 // Kernels in this file:
-//   ppo_grad_tc2_kernel     the production gradient kernel (one network per CTA, two tiles in flight, issuer + gather warps)
-//   ppo_grad_tc_kernel      the first, single-tile schedule, kept as the A/B reference (QS_PPO_V1=1); its description below
-//                           introduces the GEMM formulation both share
+//   ppo_grad_tc2_kernel     the production gradient kernel of the SB3 policy (12-D obs, Gaussian head): one network per
+//                           CTA, two tiles in flight, issuer + gather warps
+//   ppo_grad_tc_kernel<D, DIST>  (qs_ppo_generic.cuh) the single-tile schedule, templated on observation size and action
+//                           distribution: the product path for the 21-D / tanh-normal (Brax) policies, and for <12, 0> the
+//                           A/B reference of the kernel above (QS_PPO_V1=1); its description below introduces the GEMM
+//                           formulation both share
+//   obs_stats_*_kernel      (qs_ppo_generic.cuh) running observation normaliser (Welford / Chan merge)
 //   ppo_adv_stats_kernel    advantage mean / std of a minibatch         ppo_reduce_kernel   fixed-order sum of the per-CTA rows
 //   ppo_adam_kernel         global-norm clip + Adam (single GPU / NCCL)  ppo_peer_adam_kernel  the same fused with the gradient
 //   ppo_permutation_kernel  per-epoch shuffle as a keyed bijection                             exchange over NVLink peer memory
@@ -66,27 +70,7 @@ struct Hyper {
     int normalize_adv;
 };
 
-struct SmemP {
-    static constexpr int W1A = 0, W1C = 4096;                 // B: [128 x 16]
-    static constexpr int W2A = 8192, W2C = W2A + 32768;       // B: [128 x 128]
-    static constexpr int W3A = W2C + 32768, W3C = W3A + 4096; // B: [16 x 128]
-    static constexpr int B2A = W3C + 4096, B2C = B2A + 4096;  // B: [128 x 16] bias rows (hi / lo in K slots 12 / 13)
-    static constexpr int WEND = B2C + 4096;
-    static constexpr int A0 = WEND;                           // 2 x [128 x 16] (double buffered over tiles)
-    static constexpr int A1 = A0 + 2 * 4096;                  // [128 x 128] bf16 relu(H1)
-    static constexpr int A2 = A1 + 32768;                     // [128 x 128] bf16 relu(H2); later D1
-    static constexpr int D2 = A2 + 32768;                     // [128 x 128] bf16 masked dH2
-    static constexpr int DOUT = D2 + 32768;                   // [128 x 16]
-    static constexpr int F32 = DOUT + 4096;                   // fp32 constants
-    static constexpr int kB3A = 0, kB3C = 4, kLogStd = 8, kInvSig = 12, kMean = 16, kInvStd = 28, kNumF = 40;
-    static constexpr int RED = F32 + kNumF * 4;               // [4 warps][16] block-reduction scratch
-    static constexpr int BAR = RED + 4 * 16 * 4;
-    static constexpr int TOTAL = BAR + 16;
-};
-
-// TMEM columns
-constexpr uint32_t kColW = 0, kColW2A = 128, kColW2C = 256, kColW1A = 384, kColW1C = 400, kColW3A = 416, kColW3C = 432,
-                   kColB2A = 448, kColB2C = 464, kTmemCols = 512;
+constexpr uint32_t kTmemCols = 512;
 
 __device__ __forceinline__ uint32_t idesc_mn(int M, int N, int a_mn, int b_mn) {
     return make_idesc(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
@@ -124,351 +108,11 @@ struct Sample {
     bool valid;
 };
 
-__device__ __forceinline__ void load_sample(const Batch& b, int tile, int tid, Sample& s) {
-    const int r = tile * kM + tid;
-    s.valid = r < b.n;
-    s.o0 = s.o1 = s.o2 = s.a = make_float4(0.f, 0.f, 0.f, 0.f);
-    s.old_logp = 0.f; s.adv = 0.f; s.ret = 0.f;
-    if (s.valid) {
-        const size_t j = b.idx ? (size_t)b.idx[r] : (size_t)r;
-        const float4* o = reinterpret_cast<const float4*>(b.obs + j * kD);
-        s.o0 = __ldg(o); s.o1 = __ldg(o + 1); s.o2 = __ldg(o + 2);
-        s.a = __ldg(reinterpret_cast<const float4*>(b.act) + j);
-        s.old_logp = __ldg(b.old_logp + j); s.adv = __ldg(b.adv + j); s.ret = __ldg(b.ret + j);
-    }
-}
-
-// adv_norm: [mean, 1 / (std + 1e-8)] of the minibatch's advantages (ppo_adv_stats_kernel)
-// partial : [gridDim.x][partial_stride(P)] fp32, row = this CTA's gradient sums (already scaled by 1 / n) and statistics
-// mn_swap : debug knob, swaps LBO / SBO of the MN-major descriptors
-__global__ void __launch_bounds__(kM, 1)
-ppo_grad_tc_kernel(Batch b, Hyper hp, const float* __restrict__ params, const float* __restrict__ adv_norm,
-                   float* __restrict__ partial, int mn_swap) {
-    using S = SmemP;
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const PolicyLayout L = policy_layout(kD, 0);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float* sF = reinterpret_cast<float*>(smem + S::F32);
-    float* sRed = reinterpret_cast<float*>(smem + S::RED);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 8);
-
-    // ---- one-time setup: fp32 weights -> bf16 UMMA operands (same layouts as the rollout kernel) -------------------
-    for (int i = tid; i < S::WEND / 4; i += kM) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
-    __syncthreads();
-    auto put = [&](int base, int rows, int row, int k, float w) {
-        *reinterpret_cast<__nv_bfloat16*>(smem + base + op_offset(rows, row, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(w);
-    };
-    for (int i = tid; i < kD * kH; i += kM) {
-        const int k = i / kH, n = i % kH;
-        put(S::W1A, 128, n, k, params[L.aW1 + i]);
-        put(S::W1C, 128, n, k, params[L.cW1 + i]);
-    }
-    for (int n = tid; n < kH; n += kM) {
-        const float bv[4] = {params[L.ab1 + n], params[L.cb1 + n], params[L.ab2 + n], params[L.cb2 + n]};
-        const int dst[4] = {S::W1A, S::W1C, S::B2A, S::B2C};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const __nv_bfloat16 hi = __float2bfloat16_rn(bv[q]);
-            const float lo = bv[q] - __bfloat162float(hi);
-            *reinterpret_cast<__nv_bfloat16*>(smem + dst[q] + op_offset(128, n, 1) + 4 * 2) = hi;      // K slot 12
-            put(dst[q], 128, n, 13, lo);                                                              // K slot 13
-        }
-    }
-    for (int i = tid; i < kH * kH; i += kM) {
-        const int k = i / kH, n = i % kH;
-        put(S::W2A, 128, n, k, params[L.aW2 + i]);
-        put(S::W2C, 128, n, k, params[L.cW2 + i]);
-    }
-    for (int i = tid; i < kH * kA; i += kM) put(S::W3A, 16, i % kA, i / kA, params[L.aW3 + i]);
-    for (int k = tid; k < kH; k += kM) put(S::W3C, 16, 0, k, params[L.cW3 + k]);
-    if (tid < kA) {
-        sF[S::kB3A + tid] = params[L.ab3 + tid];
-        const float ls = params[L.log_std + tid];
-        sF[S::kLogStd + tid] = ls;
-        sF[S::kInvSig + tid] = expf(-ls);
-    }
-    if (tid == 0) sF[S::kB3C] = params[L.cb3];
-    if (tid < kD) { sF[S::kMean + tid] = params[L.mean + tid]; sF[S::kInvStd + tid] = params[L.inv_std + tid]; }
-    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (tid < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    fence_before();
-    fence_async_smem();
-    __syncthreads();
-    fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const uint32_t sb = smem_u32(smem);
-    // descriptors.  K-major [rows x K]: LBO = rows/8 * 128 between the two 16-byte K chunks, SBO = 128 between 8-row
-    // groups.  MN-major view of a K-major [128 x C] buffer (MN = the buffer's columns, K = its rows): 8-column groups are
-    // 2048 B apart (SBO), 8-row groups 128 B (LBO); a K = 16 step advances the start address by 256 B.
-    auto dk = [&](int off, int rows) { return make_desc(sb + off, (uint32_t)(rows / 8) * 128u, 128u); };
-    auto dmn = [&](int off, uint32_t grp_stride) {
-        return mn_swap ? make_desc(sb + off, grp_stride, 128u) : make_desc(sb + off, 128u, grp_stride);
-    };
-    const uint32_t id_kk128 = idesc_mn(128, 128, 0, 0), id_kk16 = idesc_mn(128, 16, 0, 0);
-    const uint32_t id_kmn128 = idesc_mn(128, 128, 0, 1);
-    const uint32_t id_mm128 = idesc_mn(128, 128, 1, 1), id_mm16 = idesc_mn(128, 16, 1, 1);
-    uint32_t phase = 0;
-
-    const float adv_mean = hp.normalize_adv ? adv_norm[0] : 0.f;
-    const float adv_istd = hp.normalize_adv ? adv_norm[1] : 1.f;
-    float g_b3a[kA] = {0.f, 0.f, 0.f, 0.f}, g_ls[kA] = {0.f, 0.f, 0.f, 0.f}, g_b3c = 0.f;
-    float st_pg = 0.f, st_v = 0.f, st_clip = 0.f, st_kl = 0.f, st_n = 0.f;
-
-    auto handoff = [&]() { fence_async_smem(); fence_before(); __syncthreads(); };
-    auto wait_phase = [&]() { mbar_wait(bar, phase); phase ^= 1; fence_after(); };
-    // relu epilogue: working columns -> bf16 [128 x 128] operand `dst`
-    auto epilogue_relu = [&](int dst) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            tmem_ld32(tmem + lane_off + kColW + (uint32_t)(c * 32), v);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float* h = v + q * 8;
-                *reinterpret_cast<uint4*>(smem + dst + op_offset(128, tid, c * 4 + q)) =
-                    make_uint4(pack_relu_bf16(h[0], h[1]), pack_relu_bf16(h[2], h[3]), pack_relu_bf16(h[4], h[5]),
-                               pack_relu_bf16(h[6], h[7]));
-            }
-        }
-    };
-    // backward epilogue: working columns * [act > 0] -> bf16 operand `dst` (dst may be the buffer `act` lives in:
-    // every thread reads its own 16-byte chunk before it overwrites it)
-    auto epilogue_mask = [&](int act, int dst) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            tmem_ld32(tmem + lane_off + kColW + (uint32_t)(c * 32), v);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float* g = v + q * 8;
-                const uint32_t off = op_offset(128, tid, c * 4 + q);
-                const uint4 h = *reinterpret_cast<const uint4*>(smem + act + off);
-                *reinterpret_cast<uint4*>(smem + dst + off) =
-                    make_uint4(pack_mask_bf16(g[0], g[1], h.x), pack_mask_bf16(g[2], g[3], h.y),
-                               pack_mask_bf16(g[4], g[5], h.z), pack_mask_bf16(g[6], g[7], h.w));
-            }
-        }
-    };
-
-    const int ntiles = (b.n + kM - 1) / kM;
-    Sample cur, nxt;
-    load_sample(b, blockIdx.x, tid, cur);
-    nxt = cur;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        if (tile + (int)gridDim.x < ntiles) load_sample(b, tile + gridDim.x, tid, nxt);    // in flight during this tile
-        const uint32_t first = (it == 0) ? 0u : 1u;          // accumulate flag of the first K step into a gradient accumulator
-        const int a0 = S::A0 + (it & 1) * 4096;
-        {
-            // A0: bf16 normalised observation, constant 1 in K slots 12 / 13 (0 for the padding rows of a ragged tile)
-            const float o[kD] = {cur.o0.x, cur.o0.y, cur.o0.z, cur.o0.w, cur.o1.x, cur.o1.y, cur.o1.z, cur.o1.w,
-                                 cur.o2.x, cur.o2.y, cur.o2.z, cur.o2.w};
-            float x[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                x[k] = !cur.valid ? 0.f : (k < kD ? (o[k] - sF[S::kMean + k]) * sF[S::kInvStd + k] : (k < kD + 2 ? 1.0f : 0.f));
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-                *reinterpret_cast<uint4*>(smem + a0 + op_offset(128, tid, c)) =
-                    make_uint4(pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
-                               pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
-        }
-#pragma unroll 1
-        for (int net = 0; net < 2; ++net) {
-            const int W1 = net ? S::W1C : S::W1A, W2 = net ? S::W2C : S::W2A, W3 = net ? S::W3C : S::W3A;
-            const int B2 = net ? S::B2C : S::B2A;
-            const uint32_t cW2 = net ? kColW2C : kColW2A, cW1 = net ? kColW1C : kColW1A, cW3 = net ? kColW3C : kColW3A;
-            const uint32_t cB2 = net ? kColB2C : kColB2A;
-            // ---- forward -------------------------------------------------------------------------------------------
-            handoff();
-            if (tid == 0) {
-                fence_after();
-                mma_bf16(tmem + kColW, dk(a0, 128), dk(W1, 128), id_kk128, 0u);
-                mma_commit(bar);
-            }
-            wait_phase();
-            epilogue_relu(S::A1);
-            handoff();
-            if (tid == 0) {
-                fence_after();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    mma_bf16(tmem + kColW, dk(S::A1 + j * 4096, 128), dk(W2 + j * 4096, 128), id_kk128, j > 0);
-                mma_bf16(tmem + kColW, dk(a0, 128), dk(B2, 128), id_kk128, 1u);
-                mma_commit(bar);
-            }
-            wait_phase();
-            epilogue_relu(S::A2);
-            handoff();
-            if (tid == 0) {
-                fence_after();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    mma_bf16(tmem + kColW, dk(S::A2 + j * 4096, 128), dk(W3 + j * 512, 16), id_kk16, j > 0);
-                mma_commit(bar);
-            }
-            wait_phase();
-            // ---- loss gradient w.r.t. the head outputs (fp32, this thread's sample) --------------------------------
-            {
-                float out[16];
-                tmem_ld16(tmem + lane_off + kColW, out);
-                float d[4] = {0.f, 0.f, 0.f, 0.f};
-                if (net == 0) {
-                    const float a[4] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w};
-                    float z[4], logp = 0.f;
-#pragma unroll
-                    for (int k = 0; k < kA; ++k) {
-                        z[k] = (a[k] - (out[k] + sF[S::kB3A + k])) * sF[S::kInvSig + k];
-                        logp += -0.5f * z[k] * z[k] - sF[S::kLogStd + k] - 0.9189385332046727f;
-                    }
-                    const float lr = logp - cur.old_logp;
-                    const float ratio = expf(lr);
-                    const float A = (cur.adv - adv_mean) * adv_istd;
-                    const float lo = 1.0f - hp.clip_range, hi = 1.0f + hp.clip_range;
-                    const float unclipped = A * ratio, clipped = A * fminf(fmaxf(ratio, lo), hi);
-                    const bool inside = ratio >= lo && ratio <= hi;
-                    const bool active = inside || (unclipped < clipped);
-                    const float g = (cur.valid && active) ? -A * ratio : 0.f;          // d loss_i / d logp_i (unscaled)
-#pragma unroll
-                    for (int k = 0; k < kA; ++k) {
-                        d[k] = g * z[k] * sF[S::kInvSig + k];
-                        g_b3a[k] += d[k];
-                        g_ls[k] += g * (z[k] * z[k] - 1.0f);
-                    }
-                    if (cur.valid) {
-                        st_pg += -fminf(unclipped, clipped);
-                        st_clip += inside ? 0.f : 1.f;
-                        st_kl += (ratio - 1.0f) - lr;
-                        st_n += 1.f;
-                    }
-                } else {
-                    const float v = out[0] + sF[S::kB3C];
-                    const float err = v - cur.ret;
-                    d[0] = cur.valid ? 2.0f * hp.vf_coef * err : 0.f;
-                    g_b3c += d[0];
-                    if (cur.valid) st_v += err * err;
-                }
-                *reinterpret_cast<uint4*>(smem + S::DOUT + op_offset(128, tid, 0)) =
-                    make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), 0u, 0u);
-                *reinterpret_cast<uint4*>(smem + S::DOUT + op_offset(128, tid, 1)) = make_uint4(0u, 0u, 0u, 0u);
-            }
-            // ---- backward ------------------------------------------------------------------------------------------
-            handoff();
-            if (tid == 0) {
-                fence_after();
-                // dH2 = dOUT . W3^T   (B: forward W3 operand [16 x 128], MN-major: 8-hidden groups 256 B apart)
-                mma_bf16(tmem + kColW, dk(S::DOUT, 128), dmn(W3, 256u), id_kmn128, 0u);
-                mma_commit(bar);
-                // dW3 += A2^T . dOUT  (not waited for here: the next commit covers it)
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    mma_bf16(tmem + cW3, dmn(S::A2 + j * 256, 2048u), dmn(S::DOUT + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
-            }
-            wait_phase();
-            epilogue_mask(S::A2, S::D2);
-            handoff();
-            if (tid == 0) {
-                fence_after();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)     // dH1 = D2 . W2^T
-                    mma_bf16(tmem + kColW, dk(S::D2 + j * 4096, 128), dmn(W2 + j * 256, 2048u), id_kmn128, j > 0);
-                mma_commit(bar);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)     // dW2 += A1^T . D2
-                    mma_bf16(tmem + cW2, dmn(S::A1 + j * 256, 2048u), dmn(S::D2 + j * 256, 2048u), id_mm128, j > 0 ? 1u : first);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)     // db2 (column 12) += D2^T . A0
-                    mma_bf16(tmem + cB2, dmn(S::D2 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
-            }
-            wait_phase();                       // also covers dW3: A2 may be overwritten now
-            epilogue_mask(S::A1, S::A2);        // D1 -> the A2 buffer
-            handoff();
-            if (tid == 0) {
-                fence_after();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)     // dW1^T (columns 0..11), db1 (column 12) += D1^T . A0
-                    mma_bf16(tmem + cW1, dmn(S::A2 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
-            }
-        }
-        cur = nxt;
-    }
-
-    // ---- flush: TMEM accumulators -> this CTA's partial-gradient row --------------------------------------------------
-    handoff();
-    if (tid == 0) { fence_after(); mma_commit(bar); }
-    wait_phase();
-    const int P = L.total;
-    float* out = partial + (size_t)blockIdx.x * partial_stride(P);
-    const float scale = 1.0f / (float)b.n;
-    for (int i = L.mean + tid; i < P; i += kM) out[i] = 0.f;                 // the observation normaliser is not trained
-    const bool any = it > 0;                                                 // a CTA without tiles holds garbage in TMEM
-#pragma unroll 1
-    for (int net = 0; net < 2; ++net) {
-        const uint32_t cW2 = net ? kColW2C : kColW2A, cW1 = net ? kColW1C : kColW1A, cW3 = net ? kColW3C : kColW3A;
-        const uint32_t cB2 = net ? kColB2C : kColB2A;
-        const int oW2 = net ? L.cW2 : L.aW2, oW1 = net ? L.cW1 : L.aW1, ob1 = net ? L.cb1 : L.ab1, ob2 = net ? L.cb2 : L.ab2;
-        // dW2: lane = input feature k, column = output feature n  ->  W2[k][n], 512 contiguous bytes per thread
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            tmem_ld32(tmem + lane_off + cW2 + (uint32_t)(c * 32), v);
-            float4* d4 = reinterpret_cast<float4*>(out + oW2 + tid * kH + c * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                d4[q] = any ? make_float4(v[4 * q] * scale, v[4 * q + 1] * scale, v[4 * q + 2] * scale, v[4 * q + 3] * scale)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float v[16];
-        tmem_ld16(tmem + lane_off + cW1, v);                                  // lane = hidden n, column = obs k | 12: bias
-#pragma unroll
-        for (int k = 0; k < kD; ++k) out[oW1 + k * kH + tid] = any ? v[k] * scale : 0.f;
-        out[ob1 + tid] = any ? v[kD] * scale : 0.f;
-        tmem_ld16(tmem + lane_off + cB2, v);
-        out[ob2 + tid] = any ? v[kD] * scale : 0.f;
-        tmem_ld16(tmem + lane_off + cW3, v);                                  // lane = hidden k, column = head output
-        if (net == 0) {
-#pragma unroll
-            for (int j = 0; j < kA; ++j) out[L.aW3 + tid * kA + j] = any ? v[j] * scale : 0.f;
-        } else {
-            out[L.cW3 + tid] = any ? v[0] * scale : 0.f;
-        }
-    }
-    // head biases, log_std and statistics: per-thread sums over the CTA's tiles -> block reduction
-    {
-        float r[16] = {g_b3a[0], g_b3a[1], g_b3a[2], g_b3a[3], g_b3c, g_ls[0], g_ls[1], g_ls[2], g_ls[3],
-                       st_pg, st_v, st_clip, st_kl, st_n, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < 14; ++k) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) sRed[warp * 16 + k] = r[k];
-        }
-        __syncthreads();
-        if (tid < 14) {
-            const float s = sRed[tid] + sRed[16 + tid] + sRed[32 + tid] + sRed[48 + tid];
-            if (tid < 4) out[L.ab3 + tid] = s * scale;
-            else if (tid == 4) out[L.cb3] = s * scale;
-            // entropy bonus: H = sum_k (0.5 + 0.5 log 2pi + log_std_k) does not depend on the sample; CTA 0 carries it
-            else if (tid < 9) out[L.log_std + tid - 5] = s * scale - (blockIdx.x == 0 ? hp.ent_coef : 0.f);
-            else out[P + tid - 9] = s;                                        // statistics: plain sums
-        }
-        if (tid >= 14 && tid < 9 + kPartialStats) out[P + tid - 9] = 0.f;
-    }
-    fence_before();
-    __syncthreads();
-    if (tid < 32) {
-        fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
-    }
-}
+}  // namespace ppo
+}  // namespace qs
+#include "qs_ppo_generic.cuh"      // ppo_grad_tc_kernel<D, DIST>: the single-tile schedule for every policy variant
+namespace qs {
+namespace ppo {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // ppo_grad_tc2_kernel -- the production schedule.  Same GEMMs, operands and rounding points as ppo_grad_tc_kernel, but
@@ -1114,12 +758,12 @@ ppo_reduce_kernel(const float* __restrict__ partial, int rows_a, int rows_c, int
     grad[e] = (s0 + s1) + (s2 + s3);
 }
 
-// mean and 1 / (std + 1e-8) (unbiased std, as torch.Tensor.std) of the minibatch's advantages.  Double-precision block
+// mean and 1 / (std + 1e-8) of the minibatch's advantages (ddof 1: unbiased std, as torch.Tensor.std; ddof 0: population).  Double-precision block
 // sums, one atomicAdd pair per block; the last block to finish writes the result and re-arms the scratch.
 // scratch: 2 doubles (sums) + 1 unsigned (blocks done), zero before the first call
 __global__ void __launch_bounds__(256)
-ppo_adv_stats_kernel(const float* __restrict__ adv, const int32_t* __restrict__ idx, int n, double* __restrict__ scratch,
-                     float* __restrict__ adv_norm) {
+ppo_adv_stats_kernel(const float* __restrict__ adv, const int32_t* __restrict__ idx, int n, int ddof,
+                     double* __restrict__ scratch, float* __restrict__ adv_norm) {
     __shared__ double sh[2][8];
     __shared__ bool last;
     double s = 0.0, q = 0.0;
@@ -1142,7 +786,8 @@ ppo_adv_stats_kernel(const float* __restrict__ adv, const int32_t* __restrict__ 
             __threadfence();
             const double St = atomicAdd(&scratch[0], 0.0), Qt = atomicAdd(&scratch[1], 0.0);
             const double mean = St / n;
-            const double var = n > 1 ? fmax(Qt - St * mean, 0.0) / (n - 1) : 0.0;
+            // ddof 1: torch.Tensor.std (SB3); ddof 0: jnp.std (brax)
+            const double var = n > ddof ? fmax(Qt - St * mean, 0.0) / (n - ddof) : 0.0;
             adv_norm[0] = (float)mean;
             adv_norm[1] = (float)(1.0 / (sqrt(var) + 1e-8));
             scratch[0] = 0.0; scratch[1] = 0.0; *cnt = 0u;

@@ -397,12 +397,25 @@ int ppo_device_sms(int* sms) {
     return QS_OK;
 }
 bool ppo_desc_ok(const QsPolicyDesc* d) {
-    return d && d->obs_dim == qs::ppo::kD && d->hidden == 128 && d->act_dim == 4 && d->dist == 0;
+    return d && (d->obs_dim == 12 || d->obs_dim == 21) && d->hidden == 128 && d->act_dim == 4 && (d->dist == 0 || d->dist == 1);
 }
+const char* kPpoDescMsg = "the fused update covers obs_dim 12 | 21 -> 128 -> 128 -> 4 with dist 0 (SB3 Gaussian) | 1 (Brax tanh-normal)";
+
+extern "C++" {
+template <int D, int DIST>
+int launch_ppo_grad_generic(const qs::ppo::Batch& b, const qs::ppo::HyperG& hp, const float* params, const float* adv_norm,
+                            float* partial, int grid, int mn_swap, cudaStream_t s) {
+    using S = qs::ppo::SmemPT<(D + 2 <= 16) ? 16 : 32>;
+    auto kern = qs::ppo::ppo_grad_tc_kernel<D, DIST>;
+    QS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    kern<<<grid, qs::tc::kM, S::TOTAL, s>>>(b, hp, params, adv_norm, partial, mn_swap);
+    return QS_OK;
+}
+}  // extern "C++"
 }  // namespace
 
 int64_t qs_ppo_workspace_bytes(const QsPolicyDesc* desc) {
-    if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, "qs_ppo_workspace_bytes: the fused update covers the SB3 policy (12 -> 128 -> 128 -> 4, dist 0)");
+    if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, kPpoDescMsg);
     int sms = 0;
     const int rc = ppo_device_sms(&sms);
     if (rc != QS_OK) return rc;
@@ -414,11 +427,12 @@ int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const floa
                 const float* old_logp, const float* adv, const float* ret, const int32_t* idx, int32_t n,
                 float clip_range, float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad,
                 void* stream) {
-    if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, "qs_ppo_grad: the fused update covers the SB3 policy (12 -> 128 -> 128 -> 4, dist 0)");
+    if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, kPpoDescMsg);
     if (!policy_params || !obs || !act || !old_logp || !adv || !ret || !workspace || !grad || n <= 0)
         return fail(QS_EINVAL, "qs_ppo_grad: bad argument");
-    if ((((uintptr_t)obs | (uintptr_t)act | (uintptr_t)workspace | (uintptr_t)grad) & 15u) != 0)
-        return fail(QS_EINVAL, "qs_ppo_grad: obs, act, workspace and grad must be 16-byte aligned");
+    if (normalize_adv < 0 || normalize_adv > 2) return fail(QS_EINVAL, "qs_ppo_grad: normalize_adv is 0 (off), 1 (unbiased std) or 2 (population std)");
+    if ((((uintptr_t)act | (uintptr_t)workspace | (uintptr_t)grad) & 15u) != 0 || (desc->obs_dim % 4 == 0 && ((uintptr_t)obs & 15u) != 0))
+        return fail(QS_EINVAL, "qs_ppo_grad: obs (12-D), act, workspace and grad must be 16-byte aligned");
     int sms = 0;
     const int rc = ppo_device_sms(&sms);
     if (rc != QS_OK) return rc;
@@ -429,24 +443,30 @@ int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const floa
     float* partial = (float*)(ws + kPpoWsHeader);
     if (normalize_adv) {
         const int blocks = nblocks(n, 256) < 4 * sms ? nblocks(n, 256) : 4 * sms;
-        qs::ppo::ppo_adv_stats_kernel<<<blocks, 256, 0, s>>>(adv, idx, n, adv_scratch, adv_norm);
+        qs::ppo::ppo_adv_stats_kernel<<<blocks, 256, 0, s>>>(adv, idx, n, normalize_adv == 2 ? 0 : 1, adv_scratch, adv_norm);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     const int ntiles = nblocks(n, qs::tc::kM);
     static const int mn_swap = getenv("QS_PPO_MN_SWAP") ? atoi(getenv("QS_PPO_MN_SWAP")) : 0;   // descriptor debug knob
     static const int use_v1 = getenv("QS_PPO_V1") ? atoi(getenv("QS_PPO_V1")) : 0;              // A/B: the single-tile schedule
     qs::ppo::Batch b{obs, act, old_logp, adv, ret, idx, n};
-    qs::ppo::Hyper hp{clip_range, vf_coef, ent_coef, normalize_adv};
     const int P = qs::policy_param_count(*desc);
     const qs::PolicyLayout L = qs::policy_layout(desc->obs_dim, desc->dist);
     const int len = P + qs::ppo::kPartialStats;
     int rows_a, rows_c;
-    if (use_v1) {
+    if (use_v1 || desc->obs_dim != 12 || desc->dist != 0) {
+        // single-tile schedule, templated on observation size / distribution (qs_ppo_generic.cuh)
         const int grid = ntiles < sms ? ntiles : sms;
-        QS_CUDA(cudaFuncSetAttribute(qs::ppo::ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qs::ppo::SmemP::TOTAL));
-        qs::ppo::ppo_grad_tc_kernel<<<grid, qs::tc::kM, qs::ppo::SmemP::TOTAL, s>>>(b, hp, policy_params, adv_norm, partial, mn_swap);
+        qs::ppo::HyperG hg{clip_range, vf_coef, ent_coef, normalize_adv, (uint32_t)desc->sample_seed};
+        int rc2;
+        if (desc->obs_dim == 12) rc2 = desc->dist == 0 ? launch_ppo_grad_generic<12, 0>(b, hg, policy_params, adv_norm, partial, grid, mn_swap, s)
+                                                       : launch_ppo_grad_generic<12, 1>(b, hg, policy_params, adv_norm, partial, grid, mn_swap, s);
+        else rc2 = desc->dist == 0 ? launch_ppo_grad_generic<21, 0>(b, hg, policy_params, adv_norm, partial, grid, mn_swap, s)
+                                   : launch_ppo_grad_generic<21, 1>(b, hg, policy_params, adv_norm, partial, grid, mn_swap, s);
+        if (rc2 != QS_OK) return rc2;
         rows_a = rows_c = grid;
     } else {
+        qs::ppo::Hyper hp{clip_range, vf_coef, ent_coef, normalize_adv};
         // one network per CTA, two tiles in flight, at most one CTA per SM; the actor's tiles cost ~13 % more than the
         // critic's (loss math, more gathered columns), so it gets ~53 % of the SMs
         const int pairs_needed = (ntiles + 1) / 2;
@@ -457,10 +477,33 @@ int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const floa
         qs::ppo::ppo_grad_tc2_kernel<<<rows_a + rows_c, qs::ppo::kThreads2, qs::ppo::SmemQ::TOTAL, s>>>(b, hp, policy_params, adv_norm, partial, rows_a);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    // entries [cW1, end of the critic) and statistic 1 (value loss) come from the critic rows, everything else from the actor rows
     qs::ppo::ppo_reduce_kernel<<<nblocks(len, 256), 256, 0, s>>>(partial, rows_a, rows_c, L.cW1, L.log_std, P + 1,
                                                                  qs::ppo::partial_stride(P), len, grad);
     return check_launch("ppo_grad");
 }
+
+// Running observation normaliser (brax normalize_observations=True, train_brax_ppo.py:611): merges the batch obs [n][obs_dim]
+// into running = {count, mean[obs_dim], M2[obs_dim]} (device, doubles, zero-initialised by the caller) and refreshes the
+// policy's obs_mean / obs_inv_std entries (mean_out / inv_std_out: pointers INTO the packed parameter vector).
+int qs_obs_stats_update(const float* obs, int64_t n, int32_t obs_dim, double* running, float* mean_out, float* inv_std_out,
+                        float std_min, float std_max, void* workspace, void* stream) {
+    if (!obs || !running || !mean_out || !inv_std_out || !workspace || n <= 0) return fail(QS_EINVAL, "qs_obs_stats_update: bad argument");
+    if (obs_dim != 12 && obs_dim != 21) return fail(QS_EUNSUPPORTED, "qs_obs_stats_update: obs_dim 12 | 21");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* part = (double*)workspace;
+    const int blocks = (int)((n + 255) / 256 < qs::ppo::kObsStatBlocks ? (n + 255) / 256 : qs::ppo::kObsStatBlocks);
+    if (obs_dim == 12) {
+        qs::ppo::obs_stats_partial_kernel<12><<<blocks, 256, 0, s>>>(obs, (long long)n, part);
+        qs::ppo::obs_stats_merge_kernel<12><<<1, 32, 0, s>>>(obs, (long long)n, part, blocks, running, mean_out, inv_std_out, std_min, std_max);
+    } else {
+        qs::ppo::obs_stats_partial_kernel<21><<<blocks, 256, 0, s>>>(obs, (long long)n, part);
+        qs::ppo::obs_stats_merge_kernel<21><<<1, 32, 0, s>>>(obs, (long long)n, part, blocks, running, mean_out, inv_std_out, std_min, std_max);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return check_launch("obs_stats");
+}
+int64_t qs_obs_stats_workspace_bytes(int32_t obs_dim) { return (int64_t)qs::ppo::kObsStatBlocks * 2 * (obs_dim > 0 ? obs_dim : 1) * sizeof(double); }
 
 int qs_ppo_permutation(int32_t n, uint64_t seed, uint32_t epoch, int32_t* out, void* stream) {
     if (n <= 0 || !out) return fail(QS_EINVAL, "qs_ppo_permutation: bad argument");
@@ -503,7 +546,7 @@ struct QsPpoComm {
 
 int qs_ppo_comm_create(const QsPolicyDesc* desc, int32_t world, int32_t rank, QsPpoComm** out) {
     if (!ppo_desc_ok(desc) || !out || world < 1 || world > qs::ppo::kMaxPeers || rank < 0 || rank >= world)
-        return fail(QS_EINVAL, "qs_ppo_comm_create: bad argument (1 <= world <= 8, SB3 policy)");
+        return fail(QS_EINVAL, "qs_ppo_comm_create: bad argument (1 <= world <= 8, supported policy)");
     int sms = 0;
     const int rc = ppo_device_sms(&sms);
     if (rc != QS_OK) return rc;

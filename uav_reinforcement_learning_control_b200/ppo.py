@@ -17,7 +17,7 @@ from dataclasses import dataclass
 from . import config as Q
 from .parallel import DistContext, flat_allreduce_mean_, reduce_stats
 
-__all__ = ["PPOConfig", "ActorCritic", "FusedUpdater", "PPOTrainer", "load_sb3_policy_zip", "sb3_state_dict_to_packed",
+__all__ = ["PPOConfig", "ActorCritic", "FusedUpdater", "PPOTrainer", "init_packed_params", "load_sb3_policy_zip", "sb3_state_dict_to_packed",
            "packed_to_sb3_state_dict", "save_sb3_policy_zip"]
 
 H, A = 128, 4
@@ -38,6 +38,43 @@ class PPOConfig:
     max_grad_norm: float = 0.5
     normalize_advantage: bool = True
     timeout_bootstrap: bool = True
+    adam_eps: float = 1e-5                 # SB3's PPO default; optax.adam (brax): 1e-8
+
+    @staticmethod
+    def sb3_reference(**kw):
+        """The SB3 learner exactly as train.py:50-68 configures it (n_steps 1024, 20 epochs, batch_size 128 on 16 envs =
+        128 minibatches); the class defaults above keep the reference's loss hyper-parameters but use a rollout / minibatch
+        geometry sized for 10^4..10^6 envs per GPU."""
+        from dataclasses import replace
+        return replace(PPOConfig(n_steps=1024, n_epochs=20, num_minibatches=128), **kw)
+
+    @staticmethod
+    def brax_reference(**kw):
+        """brax ppo_train.train as train_brax_ppo.py:431-455,589-620 calls it: unroll_length 10, 16 minibatches x 4 updates
+        per batch, lr 3e-4, entropy_cost 1e-3, discounting 0.99, gae_lambda 0.95, brax's default clipping_epsilon 0.3,
+        value loss 0.5 * 0.5 * err^2, advantages normalised with the population std, optax.adam (eps 1e-8), no gradient
+        clipping, running observation normaliser."""
+        from dataclasses import replace
+        return replace(PPOConfig(n_steps=10, gamma=0.99, gae_lambda=0.95, clip_range=0.3, ent_coef=1e-3, vf_coef=0.25,
+                                 learning_rate=3e-4, n_epochs=4, num_minibatches=16, max_grad_norm=0.0,
+                                 timeout_bootstrap=False, adam_eps=1e-8), **kw)
+
+
+def init_packed_params(obs_dim: int, dist: int, seed: int = 0, log_std_init: float = 0.0):
+    """Random-init 2x128 ReLU actor-critic in the packed layout of qs_policy_param_count (lecun-uniform weights, zero
+    biases, small actor head; identity observation normaliser) -- float32 CPU tensor."""
+    import torch
+    g = torch.Generator(device="cpu"); g.manual_seed(seed)
+    Ao = 2 * A if dist == 1 else A
+    parts = []
+    for out, gain in ((Ao, 0.01), (1, 1.0)):
+        for (i, o, gn) in ((obs_dim, H, 1.0), (H, H, 1.0), (H, out, gain)):
+            lim = gn * math.sqrt(3.0 / i)
+            parts += [((torch.rand(i, o, generator=g) * 2 - 1) * lim).reshape(-1), torch.zeros(o)]
+    if dist == 0:
+        parts.append(torch.full((A,), float(log_std_init)))
+    parts += [torch.zeros(obs_dim), torch.ones(obs_dim)]
+    return torch.cat(parts).contiguous()
 
 
 class ActorCritic:
@@ -104,7 +141,7 @@ class FusedUpdater:
 
     N_STATS = 8
 
-    def __init__(self, device, obs_dim: int = 12):
+    def __init__(self, device, obs_dim: int = 12, dist: int = 0):
         import ctypes as C
         import torch
         from .engine import QuadSimError, load_library
@@ -114,8 +151,9 @@ class FusedUpdater:
         self.lib = load_library()
         self.device = torch.device(device)
         d = Q.QsPolicyDesc()
-        d.obs_dim, d.hidden, d.act_dim, d.dist = int(obs_dim), H, A, 0
+        d.obs_dim, d.hidden, d.act_dim, d.dist = int(obs_dim), H, A, int(dist)
         self.desc = d
+        self.obs_dim, self.dist = int(obs_dim), int(dist)
         with torch.cuda.device(self.device):
             nbytes = int(self.lib.qs_ppo_workspace_bytes(C.byref(d)))
         if nbytes <= 0:
@@ -129,6 +167,9 @@ class FusedUpdater:
         self.step = 0
         self.comm = None          # multi-GPU: peer-memory exchange (enable_peer)
         self.epoch = 0
+        # running observation normaliser (brax normalize_observations=True): count | mean[D] | M2[D], float64 on the device
+        self.obs_running = torch.zeros(1 + 2 * self.obs_dim, dtype=torch.float64, device=self.device)
+        self._obs_ws = None
 
     def _check(self, rc, what):
         if rc != 0:
@@ -206,9 +247,53 @@ class FusedUpdater:
     def _stream(self):
         return self.C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
+    def update_obs_stats(self, params, obs, std_min=1e-6, std_max=1e6, world: int = 1, group=None):
+        """Merge the batch ``obs`` [N, D] into the running statistics and refresh obs_mean / obs_inv_std INSIDE the packed
+        parameter vector ``params`` (qs_obs_stats_update; brax running_statistics.update, train_brax_ppo.py:611).
+        world > 1 (data-parallel ranks): every rank reduces its own shard to (n, mean, M2) with the kernel, the 1 + 2 D
+        doubles are all-gathered and merged in rank order on every rank, so the normaliser -- part of the policy -- stays
+        bitwise identical across ranks (brax pmean's its statistics for the same reason)."""
+        torch, C = self.torch, self.C
+        D = self.obs_dim
+        obs = obs.reshape(-1, D)
+        if obs.dtype != torch.float32 or not obs.is_cuda or not obs.is_contiguous():
+            raise ValueError("obs: expected a contiguous float32 CUDA tensor [N, obs_dim]")
+        if self._obs_ws is None:
+            with torch.cuda.device(self.device):
+                self._obs_ws = torch.zeros(int(self.lib.qs_obs_stats_workspace_bytes(D)), dtype=torch.uint8, device=self.device)
+        P = params.numel()
+
+        def run(running, mean_ptr, inv_ptr):
+            with torch.cuda.device(self.device):
+                self._check(self.lib.qs_obs_stats_update(C.c_void_p(obs.data_ptr()), int(obs.shape[0]), D,
+                                                         C.c_void_p(running.data_ptr()), C.c_void_p(mean_ptr), C.c_void_p(inv_ptr),
+                                                         float(std_min), float(std_max), C.c_void_p(self._obs_ws.data_ptr()),
+                                                         self._stream()), "qs_obs_stats_update")
+        if world <= 1:
+            run(self.obs_running, params.data_ptr() + 4 * (P - 2 * D), params.data_ptr() + 4 * (P - D))
+            return
+        import torch.distributed as dist
+        local = torch.zeros_like(self.obs_running)                 # merge into an empty state = this shard's (n, mean, M2)
+        scratch = torch.empty(2 * D, dtype=torch.float32, device=self.device)
+        run(local, scratch.data_ptr(), scratch.data_ptr() + 4 * D)
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local, group=group)
+        R = self.obs_running
+        for b in parts:                                            # Chan merge, rank order, float64, identical on every rank
+            na, nb = R[0].clone(), b[0]
+            tot = na + nb
+            delta = b[1:1 + D] - R[1:1 + D]
+            R[1 + D:] = R[1 + D:] + b[1 + D:] + delta * delta * na * nb / tot
+            R[1:1 + D] = R[1:1 + D] + delta * nb / tot
+            R[0] = tot
+        sd = torch.sqrt(torch.clamp(R[1 + D:] / R[0], min=0.0)).clamp(std_min, std_max)
+        params[P - 2 * D:P - D] = R[1:1 + D].float()
+        params[P - D:] = (1.0 / sd).float()
+
     def grad(self, params, obs, act, old_logp, adv, ret, idx=None, clip_range=0.2, vf_coef=0.5, ent_coef=0.0,
-             normalize_adv=True):
-        """Gradient of the SB3 PPO loss over rows ``idx`` (int32, or None: all rows) of the flattened rollout buffers.
+             normalize_adv=True, sample_seed=0):
+        """Gradient of the PPO loss (SB3 form for dist 0, brax form for dist 1) over rows ``idx`` (int32, or None: all rows) of
+        the flattened rollout buffers.  normalize_adv: False / True (unbiased std) / 2 (population std, brax).
         Returns the [P + 8] buffer: packed gradient | loss statistics (sums, see quadsim_abi.h)."""
         torch = self.torch
         N = old_logp.numel()
@@ -222,10 +307,11 @@ class FusedUpdater:
         p = lambda t: None if t is None else self.C.c_void_p(t.data_ptr())
         # peer mode: the gradient goes straight into this rank's exported slot of the NEXT update
         out = p(self.grad_buf) if self.comm is None else self.C.c_void_p(self.lib.qs_ppo_comm_slot(self.comm, self.epoch + 1))
+        self.desc.sample_seed = int(sample_seed) & 0x7FFFFFFF
         with torch.cuda.device(self.device):
             self._check(self.lib.qs_ppo_grad(self.C.byref(self.desc), p(params), p(obs), p(act), p(old_logp), p(adv), p(ret),
                                              p(idx), int(n), float(clip_range), float(vf_coef), float(ent_coef),
-                                             int(bool(normalize_adv)), p(self.workspace), out, self._stream()),
+                                             int(normalize_adv), p(self.workspace), out, self._stream()),
                         "qs_ppo_grad")
         return self.grad_buf if self.comm is None else None
 
@@ -277,34 +363,50 @@ class PPOTrainer:
         self.engine = engine
         self.cfg = cfg or PPOConfig()
         self.ctx = ctx or DistContext()
-        self.policy = ActorCritic(engine.obs_dim, engine.device, seed=seed)     # same seed on every rank
-        self.fused = (engine.obs_dim == 12) if fused is None else bool(fused)
+        # Brax env variants (21-D raw observation) train brax's tanh-normal policy with brax's loss; gym variants the SB3 one
+        self.dist = 1 if engine.cfg.mode in (Q.MODE_MJX_BRAX, Q.MODE_HOVER_BRAX) else 0
+        self.brax = self.dist == 1
+        self.fused = (True if fused is None else bool(fused))
+        if self.brax and not self.fused:
+            raise ValueError("the Brax-policy update exists as fused kernels only (fused=True)")
+        self.policy = None if self.brax else ActorCritic(engine.obs_dim, engine.device, seed=seed)     # same seed on every rank
         self.tensor_cores = self.fused if tensor_cores is None else bool(tensor_cores)
-        self.params = self.policy.pack() if self.fused else None                 # fused: THE master copy of the weights
-        self.updater = FusedUpdater(engine.device, engine.obs_dim) if self.fused else None
+        if self.brax:
+            self.params = init_packed_params(engine.obs_dim, 1, seed).to(engine.device)
+        else:
+            self.params = self.policy.pack() if self.fused else None             # fused: THE master copy of the weights
+        self.updater = FusedUpdater(engine.device, engine.obs_dim, self.dist) if self.fused else None
         if peer and self.fused and self.ctx.world > 1:
             # Set-up (CUDA IPC) is the only part that can fail for environmental reasons; enable_peer decides
             # unanimously (every rank uses the peer path or every rank stays on the NCCL all-reduce).
             self.updater.enable_peer(self.ctx.world, self.ctx.rank, self.ctx.group)
         self.shuffle_seed = (int(seed) << 20) ^ (0x5EED + 7919 * self.ctx.rank)     # every rank shuffles its own rows
         self._epochs_done = 0
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
+        self.opt = None if self.brax else torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=self.cfg.adam_eps)
         self.state = engine.new_state()
-        engine.reset(self.state)
+        # Brax AutoResetWrapper restores the episode-0 state: the engine needs that state for every env
+        self.first_state = (torch.zeros(21, engine.num_envs, device=engine.device)
+                            if engine.cfg.auto_reset == Q.RESET_RESTORE_FIRST else None)
+        engine.reset(self.state, first_state=self.first_state)
+        self._updates = 0
         self.t = 0
         self.buf = None
         self.adv = self.ret = None
 
     def collect(self):
         c, eng = self.cfg, self.engine
-        boot = c.gamma if c.timeout_bootstrap else 0.0
+        boot = c.gamma if (c.timeout_bootstrap and not self.brax) else 0.0
         self.buf = eng.rollout_policy(self.state, self.params if self.fused else self.policy.pack(), T=c.n_steps,
-                                      t0=self.t, dist=0, bootstrap_gamma=boot, tensor_cores=self.tensor_cores,
-                                      buffers=self.buf)
+                                      t0=self.t, dist=self.dist, bootstrap_gamma=boot, tensor_cores=self.tensor_cores,
+                                      buffers=self.buf, first_state=self.first_state)
         self.t += c.n_steps
         b = self.buf
         self.adv, self.ret = eng.gae(b["reward"], b["value"], b["done"], b["trunc"], b["last_value"], c.gamma,
-                                     c.gae_lambda, brax_form=False, adv=self.adv, ret=self.ret)
+                                     c.gae_lambda, brax_form=self.brax, adv=self.adv, ret=self.ret)
+        if self.brax:
+            # brax merges the batch's observations into the running normaliser before the SGD steps; the refreshed
+            # obs_mean / obs_inv_std live inside self.params, i.e. the next rollout and this update both see them
+            self.updater.update_obs_stats(self.params, b["obs"], world=self.ctx.world, group=self.ctx.group)
         return b
 
     def update(self):
@@ -324,18 +426,20 @@ class PPOTrainer:
             self._perm = perm = up.permutation(N, self.shuffle_seed, self._epochs_done, out=getattr(self, "_perm", None))
             self._epochs_done += 1
             for k in range(c.num_minibatches):
+                self._updates += 1
                 g = up.grad(self.params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb],
                             clip_range=c.clip_range, vf_coef=c.vf_coef, ent_coef=c.ent_coef,
-                            normalize_adv=c.normalize_advantage)
+                            normalize_adv=(2 if self.brax else 1) if c.normalize_advantage else 0,
+                            sample_seed=(self.shuffle_seed * 2654435761 + self._updates) & 0x7FFFFFFF)
                 if up.comm is not None:
                     # gradients meet in NVLink peer memory inside the optimiser kernel: no collective call at all
-                    up.adam_peer(self.params, c.learning_rate, max_grad_norm=c.max_grad_norm, stats_acc=acc)
+                    up.adam_peer(self.params, c.learning_rate, max_grad_norm=c.max_grad_norm, eps=c.adam_eps, stats_acc=acc)
                     continue
                 if world > 1:
                     import torch.distributed as dist
                     dist.all_reduce(g, group=self.ctx.group)       # the ONLY collective: P + 8 floats, sum
                 acc += g[up.P:]
-                up.adam(self.params, c.learning_rate, max_grad_norm=c.max_grad_norm, grad_scale=1.0 / world)
+                up.adam(self.params, c.learning_rate, max_grad_norm=c.max_grad_norm, grad_scale=1.0 / world, eps=c.adam_eps)
         s = acc.tolist()                                             # one D2H read per update
         nb = c.n_epochs * c.num_minibatches
         return {"pg_loss": s[0] / max(s[4], 1.0) * nb, "v_loss": s[1] / max(s[4], 1.0) * nb,
@@ -374,6 +478,8 @@ class PPOTrainer:
         return self.params if self.fused else self.policy.pack()
 
     def set_log_std(self, value: float):
+        if self.brax:
+            raise ValueError("the tanh-normal policy has no state-independent log_std")
         self.policy.log_std.data.fill_(float(value))
         if self.fused:
             D = self.engine.obs_dim

@@ -522,6 +522,33 @@ def main():
             ms_b = max_over_ranks(e0.elapsed_time(e1))
             line[key] = {"value": world * nb * Tb / (ms_b * 1e-3), "unit": UNIT, "num_envs_per_gpu": nb, "T": Tb,
                          "note": "JaxMJXQuadBraxEnv semantics, 21-D obs, tanh-normal 2x128 actor-critic, brax GAE"}
+        # SURVEY 8f N4, Brax side: the same env trained with brax's recipe on the device -- tcgen05 rollout -> brax GAE -> running
+        # observation normaliser -> fused tanh-normal PPO update (qs_ppo_grad for the 21-D policy + qs_ppo_adam).  Two
+        # geometries: the reference's own (train_brax_ppo.py:431-455: unroll 10, 16 minibatches x 4 updates, batch_size x
+        # num_minibatches = 16384 envs) and a throughput one (8192 envs x 256 steps, 8 minibatches x 4 epochs)
+        line["train_iter_mjx_brax"] = {}
+        for key, nenv, cfg_t in (("reference_geometry", 16384, PPOConfig.brax_reference()),
+                                 ("throughput_geometry", nb, PPOConfig.brax_reference(n_steps=256, num_minibatches=8))):
+            eng_t = Engine(Q.EnvConfig.mjx_brax(episode_length=500, auto_reset=Q.RESET_RESTORE_FIRST, seed=3, env_id_offset=rank * nenv),
+                           nenv, device=local)
+            trb = PPOTrainer(eng_t, cfg_t, ctx=DistContext(rank, world, local, None), seed=0, peer=True)
+            trb.collect(); trb.update()
+            barrier()
+            reps = 4 if key == "reference_geometry" else 1
+            ev[0].record(stream)
+            for _ in range(reps):
+                trb.collect()
+                trb.update()
+            ev[2].record(stream)
+            barrier()
+            ms_t = max_over_ranks(ev[0].elapsed_time(ev[2])) / reps
+            line["train_iter_mjx_brax"][key] = {
+                "value": world * nenv * cfg_t.n_steps / (ms_t * 1e-3), "unit": "env-steps/s incl. PPO update", "num_envs_per_gpu": nenv,
+                "T": cfg_t.n_steps, "ms_per_iteration": ms_t, "minibatches": cfg_t.n_epochs * cfg_t.num_minibatches,
+                "samples_per_minibatch": nenv * cfg_t.n_steps // cfg_t.num_minibatches, "fused": trb.fused,
+                "params_finite": bool(torch.isfinite(trb.params).all().item())}
+            trb.updater.close()
+            del trb, eng_t
         del eng_b, bufb
         # big-batch policy rollout (per-GPU shard of configs[4]): 2^18 envs x 32 steps
         nb2, T2 = 1 << 18, 32

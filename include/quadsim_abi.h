@@ -286,6 +286,20 @@ int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* gra
                 void* stream);
 
 /*
+ * Packed sample rows.  qs_ppo_pack turns the five time-major rollout / GAE arrays into ONE 128-byte row per sample,
+ * packed[N][32] = obs[obs_dim] | act[4] | old_logp | adv | ret | 0.., (128-byte aligned), once per rollout; qs_ppo_grad_packed
+ * is qs_ppo_grad reading its minibatch rows from there: a random row is then one full cache line instead of 4-7 partial
+ * sectors of five arrays (SB3's RolloutBuffer.get gathers the same five arrays, stable-baselines3 [third party]).  `adv` is the
+ * contiguous advantage array again: the minibatch statistics (normalize_adv != 0) gather 4-byte values, which is cheaper
+ * from a dense array than from 128-byte rows.
+ */
+int qs_ppo_pack(const QsPolicyDesc* desc, const float* obs, const float* act, const float* old_logp, const float* adv,
+                const float* ret, int64_t n, float* packed, void* stream);
+int qs_ppo_grad_packed(const QsPolicyDesc* desc, const float* policy_params, const float* packed, const float* adv,
+                       const int32_t* idx, int32_t n, float clip_range, float vf_coef, float ent_coef, int32_t normalize_adv,
+                       void* workspace, float* grad, void* stream);
+
+/*
  * Running observation normaliser of the Brax trainer (normalize_observations=True, train_brax_ppo.py:611;
  * brax.training.acme.running_statistics): merges obs [n][obs_dim] into running = {count, mean[obs_dim], M2[obs_dim]}
  * (device doubles, zero before the first call) with the parallel Welford update and writes mean_out / inv_std_out

@@ -63,7 +63,31 @@ struct Batch {
     const float* ret;        // [N]
     const int32_t* idx;      // [n] minibatch sample indices into the N rows, or null: rows 0..n-1
     int n;
+    const float* packed;     // optional [N][kRowF]: obs[D] | act[4] | old_logp | adv | ret | 0..: ONE 128-byte line per sample
+                             // (ppo_pack_kernel); when set, the five arrays above are not read by the gradient kernels
 };
+constexpr int kRowF = 32;    // floats per packed sample row
+
+// Five time-major rollout / GAE arrays -> one 128-byte row per sample.  The minibatch gather of the update reads random
+// rows: from five separate arrays that costs 2-3 sectors for the 48-byte observation plus one 32-byte sector for each
+// 4..16-byte field per network (ncu, round 1: 534 MB of DRAM reads for 80 MB of algorithmic bytes per 2^20 samples);
+// from packed rows it is one full line per sample, shared by the actor and the critic CTA through L2.
+// One thread per float: a warp writes one row (coalesced), reads are contiguous per field.
+__global__ void __launch_bounds__(256)
+ppo_pack_kernel(int D, const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ old_logp,
+                const float* __restrict__ adv, const float* __restrict__ ret, long long n, float* __restrict__ packed) {
+    const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long row = g >> 5;
+    const int f = (int)(g & 31);
+    if (row >= n) return;
+    float v = 0.f;
+    if (f < D) v = __ldg(obs + row * D + f);
+    else if (f < D + 4) v = __ldg(act + row * 4 + (f - D));
+    else if (f == D + 4) v = __ldg(old_logp + row);
+    else if (f == D + 5) v = __ldg(adv + row);
+    else if (f == D + 6) v = __ldg(ret + row);
+    packed[g] = v;
+}
 
 struct Hyper {
     float clip_range, vf_coef, ent_coef;
@@ -139,7 +163,7 @@ struct SmemQ {
     static constexpr int BAR = RED + 8 * 16 * 4;              // ready[2], done[2], full[2], empty[2], tmem slot
     // per slot: cp.async landing zone for the next tile's gathered rows: obs [128][12] | act [128][4] | 3 x [128] scalars
     static constexpr int STG = (BAR + 80 + 15) & ~15;
-    static constexpr int STG_ACT = 128 * 48, STG_SCAL = STG_ACT + 128 * 16, STG_BYTES = STG_SCAL + 3 * 128 * 4;
+    static constexpr int STG_ACT = 128 * 48, STG_SCAL = STG_ACT + 128 * 16, STG_BYTES = STG_SCAL + 128 * 16;   // scalars: [128][4] (packed rows) or 3 x [128]
     static constexpr int TOTAL = STG + 2 * STG_BYTES;
 };
 constexpr uint32_t kQColW = 0 /* + 128 * slot */, kQColW2 = 256, kQColW1 = 384, kQColW3 = 400, kQColB2 = 416;
@@ -245,6 +269,17 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                     if (j[q] < 0) continue;
                     const int row = q * 32 + lane;
                     const uint32_t so = smem_u32(stg + row * 48);
+                    if (b.packed) {
+                        // one 128-byte line per sample: obs (3 chunks) | act | old_logp, adv, ret, 0
+                        const float* pr = b.packed + (size_t)j[q] * kRowF;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(so + c * 16), "l"(pr + c * 4) : "memory");
+                        if (net == 0)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(stg + S::STG_ACT + row * 16)), "l"(pr + 12) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(stg + S::STG_SCAL + row * 16)), "l"(pr + 16) : "memory");
+                        continue;
+                    }
                     const float* o = b.obs + (size_t)j[q] * kD;
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
@@ -509,12 +544,14 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             if (s.valid) {
                 const float4* o = reinterpret_cast<const float4*>(stg + tid * 48);
                 s.o0 = o[0]; s.o1 = o[1]; s.o2 = o[2];
-                const float* sc = reinterpret_cast<const float*>(stg + S::STG_SCAL) + tid;
-                if (net == 0) {
-                    s.a = *reinterpret_cast<const float4*>(stg + S::STG_ACT + tid * 16);
-                    s.old_logp = sc[0]; s.adv = sc[128];
+                if (net == 0) s.a = *reinterpret_cast<const float4*>(stg + S::STG_ACT + tid * 16);
+                if (b.packed) {
+                    const float4 sc4 = *reinterpret_cast<const float4*>(stg + S::STG_SCAL + tid * 16);
+                    s.old_logp = sc4.x; s.adv = sc4.y; s.ret = sc4.z;
                 } else {
-                    s.ret = sc[256];
+                    const float* sc = reinterpret_cast<const float*>(stg + S::STG_SCAL) + tid;
+                    if (net == 0) { s.old_logp = sc[0]; s.adv = sc[128]; }
+                    else s.ret = sc[256];
                 }
             }
             mbar_arrive(&bar_empty[slot]);          // (values are in registers: the loads above have completed? see below)

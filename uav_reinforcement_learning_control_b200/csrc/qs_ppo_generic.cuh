@@ -187,7 +187,18 @@ ppo_grad_tc_kernel(Batch b, HyperG hp, const float* __restrict__ params, const f
         if (s.valid) {
             const size_t j = b.idx ? (size_t)b.idx[r] : (size_t)r;
             s.j = (int)j;
-            if constexpr (D % 4 == 0) {
+            if (b.packed) {
+                // one 128-byte line per sample: obs[D] | act[4] | old_logp | adv | ret
+                const float4* pr = reinterpret_cast<const float4*>(b.packed + j * kRowF);
+                float f[(D + 7 + 3) / 4 * 4];
+#pragma unroll
+                for (int c = 0; c < (D + 7 + 3) / 4; ++c) { const float4 v = __ldg(pr + c); f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w; }
+#pragma unroll
+                for (int k = 0; k < D; ++k) s.o[k] = f[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s.a[k] = f[D + k];
+                s.old_logp = f[D + 4]; s.adv = f[D + 5]; s.ret = f[D + 6];
+            } else if constexpr (D % 4 == 0) {
                 const float4* o = reinterpret_cast<const float4*>(b.obs + j * D);
 #pragma unroll
                 for (int c = 0; c < D / 4; ++c) { const float4 v = __ldg(o + c); s.o[4 * c] = v.x; s.o[4 * c + 1] = v.y; s.o[4 * c + 2] = v.z; s.o[4 * c + 3] = v.w; }
@@ -195,9 +206,11 @@ ppo_grad_tc_kernel(Batch b, HyperG hp, const float* __restrict__ params, const f
 #pragma unroll
                 for (int k = 0; k < D; ++k) s.o[k] = __ldg(b.obs + j * D + k);
             }
-            const float4 a4 = __ldg(reinterpret_cast<const float4*>(b.act) + j);
-            s.a[0] = a4.x; s.a[1] = a4.y; s.a[2] = a4.z; s.a[3] = a4.w;
-            s.old_logp = __ldg(b.old_logp + j); s.adv = __ldg(b.adv + j); s.ret = __ldg(b.ret + j);
+            if (!b.packed) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(b.act) + j);
+                s.a[0] = a4.x; s.a[1] = a4.y; s.a[2] = a4.z; s.a[3] = a4.w;
+                s.old_logp = __ldg(b.old_logp + j); s.adv = __ldg(b.adv + j); s.ret = __ldg(b.ret + j);
+            }
         }
     };
 

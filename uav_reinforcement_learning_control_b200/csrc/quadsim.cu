@@ -423,6 +423,9 @@ int64_t qs_ppo_workspace_bytes(const QsPolicyDesc* desc) {
     return (int64_t)(kPpoWsHeader + (size_t)sms * row * sizeof(float));
 }
 
+static int ppo_grad_impl(const QsPolicyDesc* desc, const float* policy_params, const qs::ppo::Batch& b, float clip_range,
+                         float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad, void* stream);
+
 int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const float* obs, const float* act,
                 const float* old_logp, const float* adv, const float* ret, const int32_t* idx, int32_t n,
                 float clip_range, float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad,
@@ -430,9 +433,41 @@ int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const floa
     if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, kPpoDescMsg);
     if (!policy_params || !obs || !act || !old_logp || !adv || !ret || !workspace || !grad || n <= 0)
         return fail(QS_EINVAL, "qs_ppo_grad: bad argument");
-    if (normalize_adv < 0 || normalize_adv > 2) return fail(QS_EINVAL, "qs_ppo_grad: normalize_adv is 0 (off), 1 (unbiased std) or 2 (population std)");
     if ((((uintptr_t)act | (uintptr_t)workspace | (uintptr_t)grad) & 15u) != 0 || (desc->obs_dim % 4 == 0 && ((uintptr_t)obs & 15u) != 0))
         return fail(QS_EINVAL, "qs_ppo_grad: obs (12-D), act, workspace and grad must be 16-byte aligned");
+    qs::ppo::Batch b{obs, act, old_logp, adv, ret, idx, n, nullptr};
+    return ppo_grad_impl(desc, policy_params, b, clip_range, vf_coef, ent_coef, normalize_adv, workspace, grad, stream);
+}
+
+int qs_ppo_pack(const QsPolicyDesc* desc, const float* obs, const float* act, const float* old_logp, const float* adv,
+                const float* ret, int64_t n, float* packed, void* stream) {
+    if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, kPpoDescMsg);
+    if (!obs || !act || !old_logp || !adv || !ret || !packed || n <= 0) return fail(QS_EINVAL, "qs_ppo_pack: bad argument");
+    if (((uintptr_t)packed & 127u) != 0) return fail(QS_EINVAL, "qs_ppo_pack: packed rows must be 128-byte aligned");
+    const long long threads = (long long)n * qs::ppo::kRowF;
+    qs::ppo::ppo_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        desc->obs_dim, obs, act, old_logp, adv, ret, (long long)n, packed);
+    return check_launch("ppo_pack_kernel");
+}
+
+int qs_ppo_grad_packed(const QsPolicyDesc* desc, const float* policy_params, const float* packed, const float* adv,
+                       const int32_t* idx, int32_t n, float clip_range, float vf_coef, float ent_coef, int32_t normalize_adv,
+                       void* workspace, float* grad, void* stream) {
+    if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, kPpoDescMsg);
+    if (!policy_params || !packed || !workspace || !grad || n <= 0 || (normalize_adv && !adv))
+        return fail(QS_EINVAL, "qs_ppo_grad_packed: bad argument (the advantage statistics read the contiguous adv array)");
+    if (((uintptr_t)packed & 127u) != 0 || (((uintptr_t)workspace | (uintptr_t)grad) & 15u) != 0)
+        return fail(QS_EINVAL, "qs_ppo_grad_packed: packed rows must be 128-byte, workspace and grad 16-byte aligned");
+    qs::ppo::Batch b{nullptr, nullptr, nullptr, adv, nullptr, idx, n, packed};
+    return ppo_grad_impl(desc, policy_params, b, clip_range, vf_coef, ent_coef, normalize_adv, workspace, grad, stream);
+}
+
+static int ppo_grad_impl(const QsPolicyDesc* desc, const float* policy_params, const qs::ppo::Batch& b, float clip_range,
+                         float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad, void* stream) {
+    const float* adv = b.adv;
+    const int32_t* idx = b.idx;
+    const int32_t n = b.n;
+    if (normalize_adv < 0 || normalize_adv > 2) return fail(QS_EINVAL, "qs_ppo_grad: normalize_adv is 0 (off), 1 (unbiased std) or 2 (population std)");
     int sms = 0;
     const int rc = ppo_device_sms(&sms);
     if (rc != QS_OK) return rc;
@@ -449,7 +484,6 @@ int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const floa
     const int ntiles = nblocks(n, qs::tc::kM);
     static const int mn_swap = getenv("QS_PPO_MN_SWAP") ? atoi(getenv("QS_PPO_MN_SWAP")) : 0;   // descriptor debug knob
     static const int use_v1 = getenv("QS_PPO_V1") ? atoi(getenv("QS_PPO_V1")) : 0;              // A/B: the single-tile schedule
-    qs::ppo::Batch b{obs, act, old_logp, adv, ret, idx, n};
     const int P = qs::policy_param_count(*desc);
     const qs::PolicyLayout L = qs::policy_layout(desc->obs_dim, desc->dist);
     const int len = P + qs::ppo::kPartialStats;

@@ -57,6 +57,9 @@ _EXPORTS = {
                          + [C.c_float] * 5 + [C.c_void_p] * 3),
     "qs_ppo_comm_close_peers": (C.c_int, [C.c_void_p]),
     "qs_ppo_comm_destroy": (C.c_int, [C.c_void_p]),
+    "qs_ppo_pack": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]),
+    "qs_ppo_grad_packed": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 4
+                           + [C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32] + [C.c_void_p] * 3),
     "qs_obs_stats_workspace_bytes": (C.c_int64, [C.c_int32]),
     "qs_obs_stats_update": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                       C.c_void_p, C.c_void_p]),

@@ -290,17 +290,44 @@ class FusedUpdater:
         params[P - 2 * D:P - D] = R[1:1 + D].float()
         params[P - D:] = (1.0 / sd).float()
 
-    def grad(self, params, obs, act, old_logp, adv, ret, idx=None, clip_range=0.2, vf_coef=0.5, ent_coef=0.0,
-             normalize_adv=True, sample_seed=0):
-        """Gradient of the PPO loss (SB3 form for dist 0, brax form for dist 1) over rows ``idx`` (int32, or None: all rows) of
-        the flattened rollout buffers.  normalize_adv: False / True (unbiased std) / 2 (population std, brax).
-        Returns the [P + 8] buffer: packed gradient | loss statistics (sums, see quadsim_abi.h)."""
+    ROW_FLOATS = 32      # one 128-byte line per sample (include/quadsim_abi.h: qs_ppo_pack)
+
+    def pack(self, obs, act, old_logp, adv, ret, out=None):
+        """Rollout / GAE arrays -> packed sample rows [N, 32] (obs | act | old_logp | adv | ret | 0..), once per rollout.
+        The minibatch gather of ``grad(packed=...)`` then touches one full cache line per sample (qs_ppo_pack)."""
         torch = self.torch
         N = old_logp.numel()
-        for name, t, shp in (("params", params, (self.P,)), ("obs", obs, (N, self.desc.obs_dim)), ("act", act, (N, 4)),
-                             ("old_logp", old_logp, (N,)), ("adv", adv, (N,)), ("ret", ret, (N,))):
+        for name, t, shp in (("obs", obs, (N, self.obs_dim)), ("act", act, (N, 4)), ("old_logp", old_logp, (N,)),
+                             ("adv", adv, (N,)), ("ret", ret, (N,))):
             if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shp:
                 raise ValueError(f"{name}: expected contiguous float32 CUDA tensor {shp}, got {t.dtype} {tuple(t.shape)}")
+        if out is None or tuple(out.shape) != (N, self.ROW_FLOATS):
+            out = torch.empty((N, self.ROW_FLOATS), dtype=torch.float32, device=self.device)
+        p = lambda t: self.C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            self._check(self.lib.qs_ppo_pack(self.C.byref(self.desc), p(obs), p(act), p(old_logp), p(adv), p(ret), int(N), p(out),
+                                             self._stream()), "qs_ppo_pack")
+        return out
+
+    def grad(self, params, obs=None, act=None, old_logp=None, adv=None, ret=None, idx=None, clip_range=0.2, vf_coef=0.5,
+             ent_coef=0.0, normalize_adv=True, sample_seed=0, packed=None):
+        """Gradient of the PPO loss (SB3 form for dist 0, brax form for dist 1) over rows ``idx`` (int32, or None: all rows) of
+        the flattened rollout buffers -- either the five arrays, or ``packed`` rows from ``pack`` (+ ``adv`` for the minibatch
+        statistics).  normalize_adv: False / True (unbiased std) / 2 (population std, brax).
+        Returns the [P + 8] buffer: packed gradient | loss statistics (sums, see quadsim_abi.h)."""
+        torch = self.torch
+        if packed is not None:
+            N = packed.shape[0]
+            checks = (("params", params, (self.P,)), ("packed", packed, (N, self.ROW_FLOATS))) + \
+                     ((("adv", adv, (N,)),) if normalize_adv else ())
+        else:
+            N = old_logp.numel()
+            checks = (("params", params, (self.P,)), ("obs", obs, (N, self.desc.obs_dim)), ("act", act, (N, 4)),
+                      ("old_logp", old_logp, (N,)), ("adv", adv, (N,)), ("ret", ret, (N,)))
+        for name, t, shp in checks:
+            if t is None or t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shp:
+                raise ValueError(f"{name}: expected contiguous float32 CUDA tensor {shp}, got "
+                                 f"{None if t is None else (t.dtype, tuple(t.shape))}")
         if idx is not None and (idx.dtype != torch.int32 or not idx.is_cuda or not idx.is_contiguous() or idx.dim() != 1):
             raise ValueError("idx: expected a contiguous 1-D int32 CUDA tensor")
         n = N if idx is None else idx.numel()
@@ -309,10 +336,15 @@ class FusedUpdater:
         out = p(self.grad_buf) if self.comm is None else self.C.c_void_p(self.lib.qs_ppo_comm_slot(self.comm, self.epoch + 1))
         self.desc.sample_seed = int(sample_seed) & 0x7FFFFFFF
         with torch.cuda.device(self.device):
-            self._check(self.lib.qs_ppo_grad(self.C.byref(self.desc), p(params), p(obs), p(act), p(old_logp), p(adv), p(ret),
-                                             p(idx), int(n), float(clip_range), float(vf_coef), float(ent_coef),
-                                             int(normalize_adv), p(self.workspace), out, self._stream()),
-                        "qs_ppo_grad")
+            if packed is not None:
+                self._check(self.lib.qs_ppo_grad_packed(self.C.byref(self.desc), p(params), p(packed), p(adv), p(idx), int(n),
+                                                        float(clip_range), float(vf_coef), float(ent_coef), int(normalize_adv),
+                                                        p(self.workspace), out, self._stream()), "qs_ppo_grad_packed")
+            else:
+                self._check(self.lib.qs_ppo_grad(self.C.byref(self.desc), p(params), p(obs), p(act), p(old_logp), p(adv), p(ret),
+                                                 p(idx), int(n), float(clip_range), float(vf_coef), float(ent_coef),
+                                                 int(normalize_adv), p(self.workspace), out, self._stream()),
+                            "qs_ppo_grad")
         return self.grad_buf if self.comm is None else None
 
     def adam_peer(self, params, lr, max_grad_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-5, stats_acc=None):
@@ -357,9 +389,10 @@ class PPOTrainer:
     vector ``self.params``; fused=False: torch autograd on ``self.policy``."""
 
     def __init__(self, engine, cfg: PPOConfig | None = None, ctx: DistContext | None = None, seed: int = 0,
-                 fused: bool | None = None, tensor_cores: bool | None = None, peer: bool = False):
+                 fused: bool | None = None, tensor_cores: bool | None = None, peer: bool = False, packed_rows: bool = True):
         import torch
         self.torch = torch
+        self.packed_rows = bool(packed_rows)
         self.engine = engine
         self.cfg = cfg or PPOConfig()
         self.ctx = ctx or DistContext()
@@ -422,12 +455,14 @@ class PPOTrainer:
         mb = N // c.num_minibatches
         acc = torch.zeros(up.N_STATS, dtype=torch.float32, device=obs.device)
         world = self.ctx.world
+        # one 128-byte row per sample, written once per rollout: every minibatch gather then reads full cache lines
+        self._packed = packed = up.pack(obs, act, old_logp, adv, ret, out=getattr(self, "_packed", None)) if self.packed_rows else None
         for _ in range(c.n_epochs):
             self._perm = perm = up.permutation(N, self.shuffle_seed, self._epochs_done, out=getattr(self, "_perm", None))
             self._epochs_done += 1
             for k in range(c.num_minibatches):
                 self._updates += 1
-                g = up.grad(self.params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb],
+                g = up.grad(self.params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb], packed=packed,
                             clip_range=c.clip_range, vf_coef=c.vf_coef, ent_coef=c.ent_coef,
                             normalize_adv=(2 if self.brax else 1) if c.normalize_advantage else 0,
                             sample_seed=(self.shuffle_seed * 2654435761 + self._updates) & 0x7FFFFFFF)

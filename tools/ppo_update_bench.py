@@ -25,12 +25,31 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     out = {"samples_per_minibatch": mb}
 
-    def fused(k):
-        up.grad(params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb], clip_range=0.19, vf_coef=0.5, ent_coef=1e-4)
+    packed = up.pack(obs, act, old_logp, adv, ret)
+    use_packed = os.environ.get("PPO_PACKED", "1") != "0"
+
+    def fused(k, pk=None):
+        pk = use_packed if pk is None else pk
+        up.grad(params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb], clip_range=0.19, vf_coef=0.5, ent_coef=1e-4,
+                packed=packed if pk else None)
         up.adam(params, 1.5e-4)
-    for k in range(3):
-        fused(k)
-    torch.cuda.synchronize()
+    for mode in (False, True, False, True):
+        for k in range(3):
+            fused(k, mode)
+        torch.cuda.synchronize()
+        ev[0].record()
+        for rep in range(4):
+            for k in range(8):
+                fused(k, mode)
+        ev[1].record(); torch.cuda.synchronize()
+        out.setdefault("packed_rows_ms_per_minibatch" if mode else "separate_arrays_ms_per_minibatch", []).append(ev[0].elapsed_time(ev[1]) / 32)
+    if os.environ.get("PPO_ONLY_FUSED"):
+        # profiling mode (ncu): a few launches of the selected gather mode only
+        for k in range(4):
+            fused(k)
+        torch.cuda.synchronize()
+        print(json.dumps(out))
+        return
     ev[0].record()
     for k in range(8):
         fused(k)

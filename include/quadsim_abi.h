@@ -322,7 +322,10 @@ int qs_obs_stats_update(const float* obs, int64_t n, int32_t obs_dim, double* ru
  *   qs_ppo_comm_slot    : device pointer to pass as `grad` to qs_ppo_grad for update number `epoch` (1, 2, 3, ...;
  *                         the same count on every rank; slots alternate by parity)
  *   qs_ppo_adam_peer    : the fused wait + sum + clip + Adam for that `epoch`; stats_acc (optional, device, 8 floats)
- *                         += the world-summed loss statistics.  A peer that never arrives traps the kernel (bounded wait).
+ *                         += the world-summed loss statistics.  A peer that does not arrive within QS_PEER_TIMEOUT_MS
+ *                         (environment, default 20 000 ms) makes the kernel raise an error word and return WITHOUT
+ *                         touching the parameters (no trap, the context survives).
+ *   qs_ppo_comm_error   : synchronous read of that error word: QS_OK, or QS_ECUDA with the late rank in the message
  *   tear-down           : every rank qs_ppo_comm_close_peers, a host-side barrier, then qs_ppo_comm_destroy (an exported
  *                         buffer must not be freed while a peer still maps it)
  */
@@ -334,6 +337,7 @@ void* qs_ppo_comm_slot(QsPpoComm* comm, uint32_t epoch);
 int qs_ppo_adam_peer(const QsPolicyDesc* desc, QsPpoComm* comm, uint32_t epoch, float* policy_params, float* m, float* v,
                      int32_t step, float lr, float beta1, float beta2, float eps, float max_grad_norm, float* norm_out,
                      float* stats_acc, void* stream);
+int qs_ppo_comm_error(QsPpoComm* comm);
 int qs_ppo_comm_close_peers(QsPpoComm* comm);   /* unmap the peers' buffers; call on every rank (then synchronise the ranks) before any rank destroys */
 int qs_ppo_comm_destroy(QsPpoComm* comm);
 
@@ -355,6 +359,11 @@ int qs_traj_info(QsHandle h, const float* state, const uint32_t* episode, const 
  */
 int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
                  float* done_host, void* stream);
+/* the same, additionally returning the `truncated` flags (hover_env.py:188; Gymnasium's fifth return value) when
+ * trunc_host is not NULL.  All host buffers must be page-locked (QS_EINVAL otherwise: pageable memory would silently
+ * serialise the copy / compute overlap this call is built on). */
+int qs_step_host_ex(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
+                    float* done_host, float* trunc_host, void* stream);
 
 /* launch accounting for bench.py's gpu_launches claim */
 uint64_t qs_launch_count(void);

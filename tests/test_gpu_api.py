@@ -158,3 +158,55 @@ def test_trajectory_follow_vec_env_spline_info():
         fin = (term | trunc).cpu().numpy()
         episode = episode + fin.astype(np.uint32); sc = np.where(fin, 0, sc + 1)
     assert episode.min() >= 1                                            # every env went through an auto-reset
+
+
+def test_host_buffer_step_returns_truncation_and_refuses_pageable_memory():
+    """qs_step_host_ex: terminated AND truncated come back from the kernel (VERDICT r1 / ADVICE: the vector env used to
+    infer truncation from the step counter), equal to the device-tensor path; pageable host buffers are refused with an
+    error instead of silently serialising the copy / compute overlap."""
+    import torch
+    from uav_reinforcement_learning_control_b200.engine import Engine, QuadSimError
+    n = 5000
+    cfg = Q.EnvConfig.north_star(seed=3, max_episode_steps=3)
+    eng = Engine(cfg, n, device=0)
+    st_a = eng.new_state(); eng.reset(st_a); st_b = st_a.clone()
+    pin = lambda *s: torch.empty(s, dtype=torch.float32).pin_memory().numpy()
+    h = dict(act=pin(n, 4), obs=pin(n, 12), rew=pin(n), done=pin(n), trunc=pin(n))
+    rng = np.random.default_rng(0)
+    seen_trunc = seen_term = 0
+    for t in range(5):
+        h["act"][:] = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        eng.step_host(st_a, h["act"], h["obs"], h["rew"], h["done"], h["trunc"])
+        tr = torch.zeros(n, device="cuda")
+        obs, rew, done = eng.step(st_b, torch.from_numpy(h["act"]).cuda(), truncated=tr)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(h["done"], done.cpu().numpy()); np.testing.assert_array_equal(h["trunc"], tr.cpu().numpy())
+        np.testing.assert_array_equal(h["obs"], obs.cpu().numpy()); np.testing.assert_array_equal(h["rew"], rew.cpu().numpy())
+        seen_trunc += int(h["trunc"].sum()); seen_term += int(h["done"].sum())
+    assert seen_trunc > 0 and seen_term > 0 and torch.equal(st_a, st_b)
+    with pytest.raises(QuadSimError, match="page-locked"):
+        eng.step_host(st_a, np.zeros((n, 4), np.float32), h["obs"], h["rew"], h["done"])
+    with pytest.raises(QuadSimError, match="page-locked"):
+        eng.step_host(st_a, h["act"], np.zeros((n, 12), np.float32), h["rew"], h["done"])
+
+
+def test_two_engines_leave_the_callers_device_alone():
+    """handle-taking entry points run on the handle's device and restore the caller's current device; tensors on
+    another device are refused by the binding."""
+    import torch
+    from uav_reinforcement_learning_control_b200.engine import Engine, QuadSimError
+    eng = Engine(Q.EnvConfig.north_star(), 256, device=0)
+    assert torch.cuda.current_device() == 0
+    st = eng.new_state(); eng.reset(st)
+    with pytest.raises(QuadSimError):
+        eng.step(st, torch.zeros(256, 4))                         # CPU tensor
+    if torch.cuda.device_count() > 1:
+        eng1 = Engine(Q.EnvConfig.north_star(), 256, device=1)
+        assert torch.cuda.current_device() == 0                    # qs_create did not move the caller
+        st1 = eng1.new_state(); eng1.reset(st1)
+        eng1.step(st1, torch.zeros(256, 4, device="cuda:1"))
+        eng.step(st, torch.zeros(256, 4, device="cuda:0"))
+        torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+        assert torch.cuda.current_device() == 0
+        with pytest.raises(QuadSimError):
+            eng.step(st, torch.zeros(256, 4, device="cuda:1"))

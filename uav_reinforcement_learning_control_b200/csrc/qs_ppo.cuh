@@ -902,7 +902,7 @@ struct PeerLayout {              // offsets (bytes) inside every rank's buffer; 
     __host__ __device__ size_t slot(int parity) const { return (size_t)parity * F * sizeof(float); }
     __host__ __device__ size_t flags() const { return 2 * (size_t)F * sizeof(float); }                    // uint32[64]
     __host__ __device__ size_t partials(int parity) const { return flags() + 256 + (size_t)parity * 64 * sizeof(double); }
-    __host__ __device__ size_t counters() const { return flags() + 256 + 2 * 64 * sizeof(double); }     // uint32[2]
+    __host__ __device__ size_t counters() const { return flags() + 256 + 2 * 64 * sizeof(double); }     // uint32[2] grid barriers | [4] error word
     __host__ __device__ size_t total() const { return counters() + 64; }
 };
 constexpr int kMaxPeers = 8;
@@ -922,18 +922,33 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
     return v;
 }
 
-// grid = ceil(F / 1024) CTAs of 1024 threads (all co-resident).  stats_acc (optional, device): += the 8 summed statistics.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// grid = ceil(F / 1024) CTAs of 1024 threads; the in-kernel grid barrier needs them co-resident, which qs_ppo_comm_create
+// verifies with an occupancy query.  stats_acc (optional, device): += the 8 summed statistics.
+// A peer that does not arrive within `timeout_ns` (rank skew: lazy module load, a checkpoint on one rank, a debugger) does
+// NOT kill the context: every CTA raises the error word of this rank's buffer and returns without touching the
+// parameters; the host reads it with qs_ppo_comm_error.
 __global__ void __launch_bounds__(1024)
 ppo_peer_adam_kernel(AdamArgs a, PeerLayout L, PeerPtrs peers, int world, int rank, uint32_t epoch, int P,
                      float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, float* __restrict__ norm_out,
-                     float* __restrict__ stats_acc) {
+                     float* __restrict__ stats_acc, unsigned long long timeout_ns) {
     __shared__ double sh[32];
     __shared__ float coef_s;
+    __shared__ int abort_s;
     const int parity = (int)(epoch & 1u);
     unsigned char* self = peers.base[rank];
     uint32_t* counters = reinterpret_cast<uint32_t*>(self + L.counters());
+    uint32_t* err_word = counters + 4;
     double* partials = reinterpret_cast<double*>(self + L.partials(parity));
+    const unsigned long long t_start = globaltimer_ns();
+    if (threadIdx.x == 0) abort_s = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[parity ^ 1] = 0u;        // re-arm the other epoch's grid barrier
+    __syncthreads();
     // 1. post + wait
     if (blockIdx.x == 0 && (int)threadIdx.x < world) {
         __threadfence_system();
@@ -943,12 +958,14 @@ ppo_peer_adam_kernel(AdamArgs a, PeerLayout L, PeerPtrs peers, int world, int ra
         const uint32_t* f = reinterpret_cast<const uint32_t*>(self + L.flags()) + threadIdx.x;
         bool ok = false;
 #pragma unroll 1
-        for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+        for (;;) {
             if ((int32_t)(ld_acquire_sys(f) - epoch) >= 0) { ok = true; break; }
+            if (*reinterpret_cast<volatile uint32_t*>(err_word) != 0u || globaltimer_ns() - t_start > timeout_ns) break;
         }
-        if (!ok) __trap();                                                       // a peer never arrived: fail loudly, do not hang
+        if (!ok) { atomicExch(err_word, 1u + (uint32_t)threadIdx.x); abort_s = 1; }   // which peer never arrived
     }
     __syncthreads();
+    if (abort_s) return;                                                             // whole CTA, before any state changes
     // 2. element-wise sum over the ranks' slots, rank order
     const int i = blockIdx.x * 1024 + threadIdx.x;
     float g = 0.f;
@@ -971,10 +988,11 @@ ppo_peer_adam_kernel(AdamArgs a, PeerLayout L, PeerPtrs peers, int world, int ra
         atomicAdd(&counters[parity], 1u);
         bool ok = false;
 #pragma unroll 1
-        for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+        for (;;) {
             if (*reinterpret_cast<volatile uint32_t*>(&counters[parity]) >= gridDim.x) { ok = true; break; }
+            if (*reinterpret_cast<volatile uint32_t*>(err_word) != 0u || globaltimer_ns() - t_start > 2 * timeout_ns) break;
         }
-        if (!ok) __trap();
+        if (!ok) { atomicExch(err_word, 0x100u); abort_s = 1; }                      // a CTA of this grid bailed out / never ran
         __threadfence();
         double tot = 0.0;
         for (unsigned b = 0; b < gridDim.x; ++b) tot += *reinterpret_cast<volatile double*>(&partials[b]);
@@ -983,6 +1001,7 @@ ppo_peer_adam_kernel(AdamArgs a, PeerLayout L, PeerPtrs peers, int world, int ra
         coef_s = a.max_grad_norm > 0.f ? fminf(1.0f, a.max_grad_norm / (norm + 1e-6f)) : 1.0f;
     }
     __syncthreads();
+    if (abort_s) return;
     // 4. Adam
     if (i < a.n_train) {
         const float gi = g * coef_s;

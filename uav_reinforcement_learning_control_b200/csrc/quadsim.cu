@@ -274,14 +274,19 @@ int qs_rollout_random(QsHandle h, float* state, int32_t T, uint32_t t0, float* s
 
 int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
                  float* done_host, void* stream) {
+    return qs_step_host_ex(h, state, action_host, obs_host, reward_host, done_host, nullptr, stream);
+}
+
+int qs_step_host_ex(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
+                    float* done_host, float* trunc_host, void* stream) {
     if (!h || !state || !action_host || !obs_host || !reward_host || !done_host)
         return fail(QS_EINVAL, "qs_step_host: null");
     if (h->P.auto_reset == QS_RESET_RESTORE_FIRST) return fail(QS_EUNSUPPORTED, "qs_step_host: use qs_step for brax auto-reset");
     DeviceGuard guard(h->device);
     {
         // the schedule below relies on truly asynchronous copies: pageable buffers would silently serialise it
-        const void* hb[4] = {action_host, obs_host, reward_host, done_host};
-        for (int k = 0; k < 4; ++k) {
+        const void* hb[5] = {action_host, obs_host, reward_host, done_host, trunc_host};
+        for (int k = 0; k < (trunc_host ? 5 : 4); ++k) {
             cudaPointerAttributes at;
             if (cudaPointerGetAttributes(&at, hb[k]) != cudaSuccess) { cudaGetLastError(); return fail(QS_EINVAL, "qs_step_host: cannot query a host buffer"); }
             if (at.type != cudaMemoryTypeHost)
@@ -291,11 +296,12 @@ int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)h->n, D = (size_t)h->P.obs_dim;
     if (!h->scratch) {
-        QS_CUDA(cudaMalloc(&h->scratch, n * (4 + D + 2) * sizeof(float)));
+        QS_CUDA(cudaMalloc(&h->scratch, n * (4 + D + 3) * sizeof(float)));
         for (int k = 0; k < QS_HOST_STREAMS; ++k) QS_CUDA(cudaStreamCreateWithFlags(&h->hs[k], cudaStreamNonBlocking));
         for (int k = 0; k <= QS_HOST_STREAMS; ++k) QS_CUDA(cudaEventCreateWithFlags(&h->hev[k], cudaEventDisableTiming));
     }
     float* d_act = h->scratch; float* d_obs = d_act + 4 * n; float* d_rew = d_obs + D * n; float* d_done = d_rew + n;
+    float* d_trunc = trunc_host ? d_done + n : nullptr;
     // Chunked, double-streamed: PCIe is full duplex, so the H2D of chunk k+1 and the kernel of chunk k+1 run under the
     // D2H of chunk k.  The D2H of the observations (48 of the 56 bytes per env) is what bounds the call, so the schedule
     // is built around keeping that copy engine busy: geometrically growing chunks (1/16, 1/16, 1/8, 1/4, 1/2 of the
@@ -327,7 +333,7 @@ int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_
         const size_t cnt = bounds[c + 1] - lo;
         cudaStream_t cs = h->hs[c % QS_HOST_STREAMS];
         QS_CUDA(cudaMemcpyAsync(d_act + 4 * lo, action_host + 4 * lo, 4 * cnt * sizeof(float), cudaMemcpyHostToDevice, cs));
-        int rc = launch_step(h, (int)lo, (int)cnt, state, d_act, d_obs, d_rew, d_done, nullptr, nullptr, nullptr, nullptr, cs);
+        int rc = launch_step(h, (int)lo, (int)cnt, state, d_act, d_obs, d_rew, d_done, d_trunc, nullptr, nullptr, nullptr, cs);
         if (rc != QS_OK) return rc;
         QS_CUDA(cudaMemcpyAsync(obs_host + D * lo, d_obs + D * lo, D * cnt * sizeof(float), cudaMemcpyDeviceToHost, cs));
     }
@@ -338,6 +344,7 @@ int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_
     }
     QS_CUDA(cudaMemcpyAsync(reward_host, d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
     QS_CUDA(cudaMemcpyAsync(done_host, d_done, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
+    if (trunc_host) QS_CUDA(cudaMemcpyAsync(trunc_host, d_trunc, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
     QS_CUDA(cudaEventRecord(h->hev[1], h->hs[0]));
     QS_CUDA(cudaStreamWaitEvent(s, h->hev[1], 0));                // later work on the caller's stream sees the new state
     QS_CUDA(cudaStreamSynchronize(s));
@@ -590,6 +597,13 @@ int qs_ppo_comm_create(const QsPolicyDesc* desc, int32_t world, int32_t rank, Qs
     QS_CUDA(cudaGetDevice(&c->device));
     c->L.F = qs::ppo::partial_stride(c->P);
     for (int p = 0; p < qs::ppo::kMaxPeers; ++p) { c->peers.base[p] = nullptr; c->opened[p] = false; }
+    {
+        // the optimiser kernel's grid barrier spins on a counter: all of its CTAs must be co-resident
+        int per_sm = 0;
+        const int grid = nblocks(c->L.F, 1024);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qs::ppo::ppo_peer_adam_kernel, 1024, 0) != cudaSuccess ||
+            per_sm * sms < grid) { delete c; return fail(QS_EUNSUPPORTED, "qs_ppo_comm_create: the optimiser grid cannot be co-resident on this device"); }
+    }
     if (cudaMalloc(&c->local, c->L.total()) != cudaSuccess) { delete c; return fail(QS_ENOMEM, "qs_ppo_comm_create: cudaMalloc"); }
     QS_CUDA(cudaMemset(c->local, 0, c->L.total()));
     QS_CUDA(cudaDeviceSynchronize());
@@ -642,9 +656,23 @@ int qs_ppo_adam_peer(const QsPolicyDesc* desc, QsPpoComm* c, uint32_t epoch, flo
     a.n_train = L.mean;
     const int grid = nblocks(c->L.F, 1024);
     if (grid > 64) return fail(QS_EUNSUPPORTED, "qs_ppo_adam_peer: policy too large");
+    static const unsigned long long timeout_ns =
+        (unsigned long long)(getenv("QS_PEER_TIMEOUT_MS") ? atof(getenv("QS_PEER_TIMEOUT_MS")) : 20000.0) * 1000000ull;
     qs::ppo::ppo_peer_adam_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(a, c->L, c->peers, c->world, c->rank, epoch, c->P,
-                                                                           policy_params, m, v, norm_out, stats_acc);
+                                                                           policy_params, m, v, norm_out, stats_acc, timeout_ns);
     return check_launch("ppo_peer_adam_kernel");
+}
+
+int qs_ppo_comm_error(QsPpoComm* c) {
+    if (!c) return fail(QS_EINVAL, "qs_ppo_comm_error: null");
+    DeviceGuard guard(c->device);
+    uint32_t w = 0;
+    QS_CUDA(cudaMemcpy(&w, c->local + c->L.counters() + 4 * sizeof(uint32_t), sizeof(w), cudaMemcpyDeviceToHost));
+    if (w == 0) return QS_OK;
+    char msg[160];
+    if (w >= 0x100u) snprintf(msg, sizeof(msg), "qs_ppo_adam_peer: the optimiser grid did not complete (a CTA bailed out or was never scheduled)");
+    else snprintf(msg, sizeof(msg), "qs_ppo_adam_peer: rank %u did not post its gradient within the timeout (QS_PEER_TIMEOUT_MS); parameters untouched", w - 1u);
+    return fail(QS_ECUDA, msg);
 }
 
 int qs_ppo_comm_close_peers(QsPpoComm* c) {

@@ -45,6 +45,7 @@ _EXPORTS = {
                + [C.c_void_p] * 2 + [C.c_void_p]),
     "qs_traj_info": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_void_p]),
     "qs_step_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "qs_step_host_ex": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     "qs_ppo_workspace_bytes": (C.c_int64, [C.POINTER(Q.QsPolicyDesc)]),
     "qs_ppo_grad": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 7
                     + [C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32] + [C.c_void_p] * 3),
@@ -54,7 +55,8 @@ _EXPORTS = {
     "qs_ppo_comm_import": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "qs_ppo_comm_slot": (C.c_void_p, [C.c_void_p, C.c_uint32]),
     "qs_ppo_adam_peer": (C.c_int, [C.POINTER(Q.QsPolicyDesc), C.c_void_p, C.c_uint32] + [C.c_void_p] * 3 + [C.c_int32]
-                         + [C.c_float] * 5 + [C.c_void_p] * 3),
+                         + [C.c_float] * 5 + [C.c_void_p] * 3),     # (timeout: QS_PEER_TIMEOUT_MS in the environment)
+    "qs_ppo_comm_error": (C.c_int, [C.c_void_p]),
     "qs_ppo_comm_close_peers": (C.c_int, [C.c_void_p]),
     "qs_ppo_comm_destroy": (C.c_int, [C.c_void_p]),
     "qs_ppo_pack": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]),
@@ -273,11 +275,14 @@ class Engine:
         return adv, ret
 
     def step_host(self, state, action_host: np.ndarray, obs_host: np.ndarray, reward_host: np.ndarray,
-                  done_host: np.ndarray):
-        """Env.step with HOST buffers: H2D action, step, D2H obs/reward/done, synchronise (qs_step_host)."""
-        self._check(self.lib.qs_step_host(self.handle, _ptr(state), action_host.ctypes.data_as(C.c_void_p),
-                                          obs_host.ctypes.data_as(C.c_void_p), reward_host.ctypes.data_as(C.c_void_p),
-                                          done_host.ctypes.data_as(C.c_void_p), self._stream()))
+                  done_host: np.ndarray, trunc_host: np.ndarray | None = None):
+        """Env.step with page-locked HOST buffers: H2D action, step, D2H obs / reward / done (/ truncated), synchronise
+        (qs_step_host_ex).  Pageable buffers are refused with QS_EINVAL."""
+        self._check(self.lib.qs_step_host_ex(self.handle, _ptr(state), action_host.ctypes.data_as(C.c_void_p),
+                                             obs_host.ctypes.data_as(C.c_void_p), reward_host.ctypes.data_as(C.c_void_p),
+                                             done_host.ctypes.data_as(C.c_void_p),
+                                             None if trunc_host is None else trunc_host.ctypes.data_as(C.c_void_p),
+                                             self._stream()))
 
     def launch_count(self):
         return int(self.lib.qs_launch_count())

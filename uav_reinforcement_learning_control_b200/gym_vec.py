@@ -188,14 +188,12 @@ class HoverVecEnv:
         n, D = self.num_envs, self.cfg.obs_dim
         if self._host is None:
             pin = lambda *s: torch.empty(s, dtype=torch.float32).pin_memory().numpy()
-            self._host = dict(act=pin(n, 4), obs=pin(n, D), rew=pin(n), done=pin(n))
+            self._host = dict(act=pin(n, 4), obs=pin(n, D), rew=pin(n), done=pin(n), trunc=pin(n))
         h = self._host
         np.copyto(h["act"], np.asarray(actions, dtype=np.float32).reshape(n, 4))
-        self.engine.step_host(self._planes, h["act"], h["obs"], h["rew"], h["done"])
-        term = h["done"] != 0
-        sc = self._planes[24].view(torch.int32)
-        trunc = (sc == 0).cpu().numpy() & ~term if self.cfg.auto_reset else (sc >= self.max_episode_steps).cpu().numpy()
-        return h["obs"].copy(), h["rew"].copy(), term, trunc, {}
+        # terminated AND truncated come from the kernel (an env can be both; a waypoint lap is neither)
+        self.engine.step_host(self._planes, h["act"], h["obs"], h["rew"], h["done"], h["trunc"])
+        return h["obs"].copy(), h["rew"].copy(), h["done"] != 0, h["trunc"] != 0, {}
 
     def close(self):
         self.engine.close()

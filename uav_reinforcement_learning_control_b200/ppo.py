@@ -18,7 +18,7 @@ from . import config as Q
 from .parallel import DistContext, flat_allreduce_mean_, reduce_stats
 
 __all__ = ["PPOConfig", "ActorCritic", "FusedUpdater", "PPOTrainer", "init_packed_params", "load_sb3_policy_zip", "sb3_state_dict_to_packed",
-           "packed_to_sb3_state_dict", "save_sb3_policy_zip"]
+           "packed_to_sb3_state_dict", "save_sb3_policy_weights", "save_sb3_policy_zip"]
 
 H, A = 128, 4
 
@@ -81,18 +81,23 @@ class ActorCritic:
     """Separate 2x128 ReLU actor / critic + state-independent log_std, stored as torch Parameters in the
     [in][out] orientation of the packed kernel layout (include/quadsim_abi.h, qs_policy_param_count)."""
 
-    def __init__(self, obs_dim: int, device, seed: int = 0, log_std_init: float = 0.0):
+    def __init__(self, obs_dim: int, device, seed: int = 0, log_std_init: float = 0.0, init: str = "orthogonal"):
+        """init = "orthogonal": SB3's ActorCriticPolicy default (ortho_init=True: gain sqrt(2) on the hidden layers, 0.01 on
+        the action head, 1 on the value head, zero biases); "uniform": lecun-uniform."""
         import torch
         g = torch.Generator(device="cpu"); g.manual_seed(seed)
 
-        def lin(i, o, gain=1.0):
-            lim = gain * math.sqrt(3.0 / i)
-            w = ((torch.rand(i, o, generator=g) * 2 - 1) * lim).to(device).requires_grad_(True)
-            b = torch.zeros(o, device=device, requires_grad=True)
-            return [w, b]
+        def lin(i, o, gain_ortho, gain_uniform=1.0):
+            if init == "orthogonal":
+                w = torch.empty(o, i)                       # torch.nn.Linear orientation [out][in] ...
+                torch.nn.init.orthogonal_(w, gain=gain_ortho, generator=g)
+                w = w.t().contiguous()                      # ... stored [in][out] like the packed kernel layout
+            else:
+                w = (torch.rand(i, o, generator=g) * 2 - 1) * (gain_uniform * math.sqrt(3.0 / i))
+            return [w.to(device).requires_grad_(True), torch.zeros(o, device=device, requires_grad=True)]
         self.obs_dim = obs_dim
-        self.actor = lin(obs_dim, H) + lin(H, H) + lin(H, A, 0.01)
-        self.critic = lin(obs_dim, H) + lin(H, H) + lin(H, 1, 1.0)
+        self.actor = lin(obs_dim, H, math.sqrt(2)) + lin(H, H, math.sqrt(2)) + lin(H, A, 0.01, 0.01)
+        self.critic = lin(obs_dim, H, math.sqrt(2)) + lin(H, H, math.sqrt(2)) + lin(H, 1, 1.0)
         self.log_std = torch.full((A,), float(log_std_init), device=device, requires_grad=True)
         self.obs_mean = torch.zeros(obs_dim, device=device)
         self.obs_inv_std = torch.ones(obs_dim, device=device)
@@ -462,7 +467,9 @@ class PPOTrainer:
             self._epochs_done += 1
             for k in range(c.num_minibatches):
                 self._updates += 1
-                g = up.grad(self.params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb], packed=packed,
+                # (the last minibatch takes the N % num_minibatches remainder rows, as SB3's RolloutBuffer.get does)
+                g = up.grad(self.params, obs, act, old_logp, adv, ret, packed=packed,
+                            idx=perm[k * mb:((k + 1) * mb if k + 1 < c.num_minibatches else N)],
                             clip_range=c.clip_range, vf_coef=c.vf_coef, ent_coef=c.ent_coef,
                             normalize_adv=(2 if self.brax else 1) if c.normalize_advantage else 0,
                             sample_seed=(self.shuffle_seed * 2654435761 + self._updates) & 0x7FFFFFFF)
@@ -476,6 +483,8 @@ class PPOTrainer:
                 acc += g[up.P:]
                 up.adam(self.params, c.learning_rate, max_grad_norm=c.max_grad_norm, grad_scale=1.0 / world, eps=c.adam_eps)
         s = acc.tolist()                                             # one D2H read per update
+        if up.comm is not None:                                      # (the stream is idle now) did every peer arrive in time?
+            up._check(up.lib.qs_ppo_comm_error(up.comm), "qs_ppo_adam_peer")
         nb = c.n_epochs * c.num_minibatches
         return {"pg_loss": s[0] / max(s[4], 1.0) * nb, "v_loss": s[1] / max(s[4], 1.0) * nb,
                 "clip_frac": s[2] / max(s[4], 1.0), "approx_kl": s[3] / max(s[4], 1.0), "n": nb}
@@ -491,7 +500,7 @@ class PPOTrainer:
         for _ in range(c.n_epochs):
             perm = torch.randperm(N, device=obs.device)
             for k in range(c.num_minibatches):
-                idx = perm[k * mb:(k + 1) * mb]
+                idx = perm[k * mb:((k + 1) * mb if k + 1 < c.num_minibatches else N)]
                 a_mb = adv[idx]
                 if c.normalize_advantage:
                     a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
@@ -622,10 +631,16 @@ def packed_to_sb3_state_dict(packed, obs_dim: int = 12):
     return sd
 
 
-def save_sb3_policy_zip(path: str, packed, obs_dim: int = 12):
-    """Write ``policy.pth`` (the state_dict above) into a zip laid out like ``PPO.save`` (train.py:141).  It carries the
-    policy weights only -- no optimiser state or hyper-parameter blob -- i.e. what ``load_sb3_policy_zip`` reads back and
-    what ``model.policy.load_state_dict(torch.load(...))`` needs on the reference side."""
+def save_sb3_policy_weights(path: str, packed, obs_dim: int = 12):
+    """Write ``policy.pth`` (the state_dict above) into a zip.  WEIGHTS ONLY: the archive has the member SB3's ``PPO.save``
+    calls ``policy.pth`` but none of its pickled ``data`` (observation / action spaces, hyper-parameters), so ``PPO.load``
+    cannot open it (that would need gymnasium + stable-baselines3, absent here).  On the reference side build the model
+    as train.py:50-68 does and load the weights into it:
+
+        sd = torch.load(io.BytesIO(zipfile.ZipFile(path).read("policy.pth")), weights_only=True)
+        model.policy.load_state_dict(sd)                      # evaluate.py:309,459,628 then use `model` as usual
+
+    ``load_sb3_policy_zip`` reads both this file and a real ``PPO.save`` archive."""
     import io
     import zipfile
     import torch
@@ -633,4 +648,8 @@ def save_sb3_policy_zip(path: str, packed, obs_dim: int = 12):
     torch.save(packed_to_sb3_state_dict(packed, obs_dim), buf)
     with zipfile.ZipFile(path, "w") as z:
         z.writestr("policy.pth", buf.getvalue())
-        z.writestr("data", "{}")
+        z.writestr("README.txt", "weights only (state_dict of SB3 ActorCriticPolicy pi=[128,128] vf=[128,128]); load with "
+                                 "model.policy.load_state_dict, not PPO.load")
+
+
+save_sb3_policy_zip = save_sb3_policy_weights      # former name

@@ -24,11 +24,20 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <type_traits>
 #include "qs_kernels.cuh"
 #include "qs_rollout.cuh"
 
 #ifndef QS_TC_PARTNER
 #define QS_TC_PARTNER 1
+#endif
+#ifndef QS_TC_TS_HEADS
+#define QS_TC_TS_HEADS 1     /* 1: relu(H2) stays in TENSOR MEMORY (tcgen05.st, in place over the consumed layer-2 accumulators) and the
+                                head layer runs as TS-form MMAs (A from TMEM); 0: through shared memory (SS form) */
+#endif
+#ifndef QS_TC_TS_L2
+#define QS_TC_TS_L2 1        /* 1 (one-tile CTAs only: needs 384 of the 512 TMEM columns per tile): relu(H1) also stays in tensor
+                                memory and layer 2 runs as TS-form MMAs */
 #endif
 
 namespace qs {
@@ -72,6 +81,28 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
         "}\n"
         :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u));
 }
+
+// A operand from TENSOR MEMORY (TS form): lane = row, 32-bit column c holds K elements 2c (low half) and 2c + 1 of the
+// row as bf16; a K = 16 step is 8 columns.  No shared-memory read for A: an N = 16 instruction then costs its 8-cycle
+// tensor time instead of the ~64 cycles the 4 KB A fetch of the SS form takes (profiles/README.md, round 2).
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p; \n\t"
+        "}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u));
+}
+
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers (SASS STTM)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -254,7 +285,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     using Smem = SmemT<K1, PARTNER>;
     constexpr int Ao = DIST == 1 ? 2 * kA : kA;
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr uint32_t kTmemCols = kTileCols * TILES;
+    // 256 accumulator columns per tile; one-tile CTAs with TS-form layer 2 also keep relu(H1) in columns [256, 384)
+    constexpr uint32_t kTmemCols = (TILES == 1 && QS_TC_TS_L2 != 0 && QS_TC_TS_HEADS != 0) ? 512u : kTileCols * TILES;
     float* sF = reinterpret_cast<float*>(smem + Smem::f32_off(TILES));
     constexpr int kTT = PARTNER ? 2 * kM : kM;             // threads per tile
     constexpr int NT = kTT * TILES;
@@ -380,7 +412,13 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     // relu + bf16 pack epilogue of a hidden layer (the bias is already inside the MMA): TMEM -> A2A | A2C.  PARTNER: the
     // owners take the actor half, the partners the critic half.  The TMEM load of chunk i + 1 is in flight while chunk i
     // is converted and stored.
-    auto relu_epilogue = [&]() {
+    // kDst: 0 = bf16 A operand in shared memory (A2A | A2C, SS-form consumer); 1 = tensor memory, IN PLACE over the first
+    // half of each network's (consumed) accumulator columns: actor -> [0, 64), critic -> [128, 192) (TS-form head layer);
+    // 2 = tensor memory columns [256, 320) | [320, 384) (TS-form layer 2, one-tile CTAs).  In-place is safe: a thread stores
+    // the 16 packed columns of chunk c to [16 c, 16 c + 16) after it has loaded [32 c, 32 c + 32), the one load in flight
+    // covers [32 (c + 1), 32 (c + 2)), and lanes are private to the warp that owns them.
+    auto relu_epilogue = [&](auto dst_tag) {
+        constexpr int kDst = decltype(dst_tag)::value;
         constexpr int kChunks = PARTNER ? 4 : 8;
         const int c_lo = PARTNER ? 4 * half : 0;
         uint32_t r[2][32];
@@ -391,17 +429,32 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             const int c = c_lo + i;
             if (i + 1 < kChunks) tmem_ld32_async(my_tmem + (uint32_t)((c + 1) * 32), r[(i + 1) & 1]);
             const uint32_t* v = r[i & 1];
-            const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
+            if constexpr (kDst == 0) {
+                const int dst = (c < 4) ? Smem::A2A : Smem::A2C;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t* h = v + q * 8;
-                *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
-                    make_uint4(pack_relu_bf16_u(h[0], h[1]), pack_relu_bf16_u(h[2], h[3]), pack_relu_bf16_u(h[4], h[5]),
-                               pack_relu_bf16_u(h[6], h[7]));
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t* h = v + q * 8;
+                    *reinterpret_cast<uint4*>(tsm + dst + op_offset(128, tid, (c & 3) * 4 + q)) =
+                        make_uint4(pack_relu_bf16_u(h[0], h[1]), pack_relu_bf16_u(h[2], h[3]), pack_relu_bf16_u(h[4], h[5]),
+                                   pack_relu_bf16_u(h[6], h[7]));
+                }
+            } else {
+                uint32_t pk[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) pk[q] = pack_relu_bf16_u(v[2 * q], v[2 * q + 1]);
+                const uint32_t col = kDst == 1 ? (uint32_t)(c < 4 ? 16 * c : 128 + 16 * (c - 4))
+                                               : (uint32_t)(256 + 16 * c);
+                tmem_st16(my_tmem + col, pk);
             }
             if (i + 1 < kChunks) tmem_ld_wait(r[(i + 1) & 1]);
         }
+        if constexpr (kDst != 0) tmem_st_wait();
     };
+    constexpr bool kTsHeads = QS_TC_TS_HEADS != 0;
+    constexpr bool kTsL2 = QS_TC_TS_L2 != 0 && kTsHeads && TILES == 1;
+    using DstSmem = std::integral_constant<int, 0>;
+    using DstL3 = std::integral_constant<int, kTsHeads ? 1 : 0>;
+    using DstL2 = std::integral_constant<int, kTsL2 ? 2 : 0>;
     // forward pass for the observation in `o`; returns head[Ao] and value
     auto forward = [&](const float* o, float* head, float& value) {
         // A1: normalised obs, bf16, K padded D -> K1 with a constant 1 in slots D and D + 1
@@ -433,10 +486,11 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
         QS_TCP(1);
-        // epilogue 1: h1 = relu(D1 + b1) -> bf16 A2A | A2C  (PARTNER: owners take the actor half, partners the critic half)
-        relu_epilogue();
+        // epilogue 1: h1 = relu(D1 + b1) -> bf16 A operand of layer 2: shared memory (A2A | A2C), or tensor memory columns
+        // [256, 384) in one-tile CTAs  (PARTNER: owners take the actor half, partners the critic half)
+        relu_epilogue(DstL2{});
         QS_TCP(2);
-        fence_async_smem();
+        if constexpr (!kTsL2) fence_async_smem();
         fence_before();
         tile_sync<kTT>(tile);
         if (lwarp == 0) {
@@ -444,13 +498,19 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {                                   // K = 128 in 8 steps of 16 (2 chunks of 2048 B each)
-                mma_bf16(tmem, make_desc(tbase + Smem::A2A + j * 4096, 16 * 128, 128),
-                         make_desc(sbase + Smem::W2A + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+                if constexpr (kTsL2)
+                    mma_bf16_ts(tmem, tmem + 256u + 8u * (uint32_t)j, make_desc(sbase + Smem::W2A + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+                else
+                    mma_bf16(tmem, make_desc(tbase + Smem::A2A + j * 4096, 16 * 128, 128),
+                             make_desc(sbase + Smem::W2A + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                mma_bf16(tmem + 128u, make_desc(tbase + Smem::A2C + j * 4096, 16 * 128, 128),
-                         make_desc(sbase + Smem::W2C + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+                if constexpr (kTsL2)
+                    mma_bf16_ts(tmem + 128u, tmem + 320u + 8u * (uint32_t)j, make_desc(sbase + Smem::W2C + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+                else
+                    mma_bf16(tmem + 128u, make_desc(tbase + Smem::A2C + j * 4096, 16 * 128, 128),
+                             make_desc(sbase + Smem::W2C + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
             }
             // + b2: the layer-1 A operand (constant 1 in K slots 12 / 13) times the hi / lo bias rows
             mma_bf16(tmem, dA1b, make_desc(sbase + Smem::B2A, 16 * 128, 128), idesc_l2, 1u);
@@ -462,23 +522,35 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
         QS_TCP(3);
-        // epilogue 2: h2 = relu(D2) -> bf16, written over A2A | A2C (the L2 MMAs have completed; b2 is inside D2)
-        relu_epilogue();
+        // epilogue 2: h2 = relu(D2) (b2 is inside D2) -> bf16 A operand of the head layer: tensor memory, in place over the
+        // consumed accumulators (TS form), or shared memory A2A | A2C (the L2 MMAs have completed)
+        relu_epilogue(DstL3{});
         QS_TCP(4);
-        fence_async_smem();
+        if constexpr (!kTsHeads) fence_async_smem();
         fence_before();
         tile_sync<kTT>(tile);
+        // heads: N = 16 (B rows/8 = 2 -> LBO 256 B, K step 512 B); TS form: D at columns [64, 80) | [192, 208), the upper
+        // (consumed) halves of the accumulator regions whose lower halves now hold the A operands
+        constexpr uint32_t kHeadA = kTsHeads ? 64u : 0u, kHeadC = kTsHeads ? 192u : 16u;
         if (lwarp == 0) {
             fence_after();
             if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)                                     // heads: N = 16 (B rows/8 = 2 -> LBO 256 B, K step 512 B)
-                mma_bf16(tmem, make_desc(tbase + Smem::A2A + j * 4096, 16 * 128, 128),
-                         make_desc(sbase + Smem::W3A + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+            for (int j = 0; j < 8; ++j) {
+                if constexpr (kTsHeads)
+                    mma_bf16_ts(tmem + kHeadA, tmem + 8u * (uint32_t)j, make_desc(sbase + Smem::W3A + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+                else
+                    mma_bf16(tmem + kHeadA, make_desc(tbase + Smem::A2A + j * 4096, 16 * 128, 128),
+                             make_desc(sbase + Smem::W3A + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                mma_bf16(tmem + 16u, make_desc(tbase + Smem::A2C + j * 4096, 16 * 128, 128),
-                         make_desc(sbase + Smem::W3C + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+            for (int j = 0; j < 8; ++j) {
+                if constexpr (kTsHeads)
+                    mma_bf16_ts(tmem + kHeadC, tmem + 128u + 8u * (uint32_t)j, make_desc(sbase + Smem::W3C + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+                else
+                    mma_bf16(tmem + kHeadC, make_desc(tbase + Smem::A2C + j * 4096, 16 * 128, 128),
+                             make_desc(sbase + Smem::W3C + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+            }
             mma_commit(bar);
             }
             __syncwarp();
@@ -487,11 +559,20 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         fence_after();
         QS_TCP(5);
         if (half == 0) {
-            float v[32];
-            tmem_ld32(my_tmem, v);
+            if constexpr (kTsHeads) {
+                float v[16], w[16];
+                tmem_ld16(my_tmem + kHeadA, v);
+                tmem_ld16(my_tmem + kHeadC, w);
 #pragma unroll
-            for (int j = 0; j < Ao; ++j) head[j] = v[j] + sF[Smem::kB3 + j];
-            value = v[16] + sF[Smem::kB3 + 16];
+                for (int j = 0; j < Ao; ++j) head[j] = v[j] + sF[Smem::kB3 + j];
+                value = w[0] + sF[Smem::kB3 + 16];
+            } else {
+                float v[32];
+                tmem_ld32(my_tmem, v);
+#pragma unroll
+                for (int j = 0; j < Ao; ++j) head[j] = v[j] + sF[Smem::kB3 + j];
+                value = v[16] + sF[Smem::kB3 + 16];
+            }
         }
         fence_before();       // the next forward's MMAs overwrite TMEM: order our loads before the coming barrier
         QS_TCP(6);

@@ -13,7 +13,7 @@ from uav_reinforcement_learning_control_b200 import config as Q
 from uav_reinforcement_learning_control_b200.engine import Engine
 
 dev = torch.device("cuda", 0)
-which = set(sys.argv[1:]) or {"step", "resident", "fma", "tc", "tc_large", "gae", "tc21", "ppo"}
+which = set(sys.argv[1:]) or {"step", "resident", "fma", "tc", "tc_large", "gae", "tc21", "ppo", "ppo21"}
 
 if {"step", "resident"} & which:
     n = 1 << 20
@@ -72,8 +72,28 @@ if "ppo" in which:
     params = ActorCritic(12, dev, seed=0, log_std_init=-1.0).pack()
     up = FusedUpdater(dev)
     perm = torch.randperm(N, device=dev, generator=g).to(torch.int32)
+    packed = up.pack(obs, act, old_logp, adv, ret)
     for k in range(2):
-        up.grad(params, obs, act, old_logp, adv, ret, idx=perm[k * mb:(k + 1) * mb], clip_range=0.19, vf_coef=0.5, ent_coef=1e-4)
+        up.grad(params, adv=adv, packed=packed, idx=perm[k * mb:(k + 1) * mb], clip_range=0.19, vf_coef=0.5, ent_coef=1e-4)
         up.adam(params, 1.5e-4)
+    torch.cuda.synchronize()
+    del obs, act, old_logp, adv, ret, packed, perm
+if "ppo21" in which:
+    # the Brax policy's update (21-D obs, tanh-normal head) through the single-tile kernel: two 2^18-row minibatches
+    from uav_reinforcement_learning_control_b200.ppo import FusedUpdater, init_packed_params
+    N = 8192 * 256; mb = N // 8
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    obs = torch.rand(N, 21, device=dev, generator=g) * 2 - 1
+    act = torch.randn(N, 4, device=dev, generator=g) * 0.4
+    old_logp = torch.randn(N, device=dev, generator=g) * 0.1 - 1.0
+    adv = torch.randn(N, device=dev, generator=g); ret = torch.randn(N, device=dev, generator=g)
+    params = init_packed_params(21, 1, 0).to(dev)
+    up = FusedUpdater(dev, obs_dim=21, dist=1)
+    perm = torch.randperm(N, device=dev, generator=g).to(torch.int32)
+    packed = up.pack(obs, act, old_logp, adv, ret)
+    for k in range(2):
+        up.grad(params, adv=adv, packed=packed, idx=perm[k * mb:(k + 1) * mb], clip_range=0.3, vf_coef=0.25, ent_coef=1e-3,
+                normalize_adv=2, sample_seed=k)
+        up.adam(params, 3e-4, max_grad_norm=0.0, eps=1e-8)
     torch.cuda.synchronize()
 print("profile_kernels done")

@@ -18,6 +18,8 @@ Sections written (arrays are exact little-endian bytes, see tests/golden/vector_
   hover_env   : 512 transitions of the real ``HoverEnv`` (envs/hover_env.py:159-198): state before / action / state
                 after / obs / reward / terminated / truncated / voltage, episodes re-seeded on termination.
   mjx_brax    : 512 transitions of the real ``JaxMJXQuadBraxEnv`` (train_brax_ppo.py:307-356) from ``reset(rng)``.
+  timing      : env-steps/s of the reference's two real CPU paths on the machine that ran the script (SURVEY 8d C1:
+                16 envs x 512 steps; HoverEnv x 16 in a Python loop, JaxMJXQuadBraxEnv under jit(vmap(step)) on JAX-CPU).
 
 ``--self-test`` writes the same layout with this repo's own oracle standing in for the reference (meta.source =
 "self-test"); it exists only so the consumer's plumbing can be exercised where MuJoCo is absent and is never
@@ -118,6 +120,47 @@ def dump_mujoco(ref_root: str, n: int, seed: int, steps: int):
         out["mjx_brax"] = dump_mjx_brax(xml, steps, seed)
     except Exception as e:                               # noqa: BLE001 -- brax may be absent
         out["meta"]["mjx_brax_skipped"] = repr(e)
+    try:
+        out["timing"] = time_reference_paths(xml)
+    except Exception as e:                               # noqa: BLE001
+        out["meta"]["timing_skipped"] = repr(e)
+    return out
+
+
+def time_reference_paths(xml: str, n_envs: int = 16, steps: int = 512):
+    """SURVEY 8d C1 on THIS machine's CPU: the reference's two real CPU paths, 16 envs x 512 steps, random actions
+    (BASELINE.json configs[0]) -- HoverEnv x 16 stepped in a Python loop like SB3's DummyVecEnv (train.py:48), and
+    JaxMJXQuadBraxEnv under jit(vmap(step)) on the JAX CPU backend.  bench.py reports these next to its own numbers when
+    the fixture is present (they are baselines measured elsewhere, with the machine named)."""
+    import platform
+    import time
+    import jax
+    import jax.numpy as jp
+    from envs.hover_env import HoverEnv
+    from train_brax_ppo import JaxMJXQuadBraxEnv
+    rng = np.random.default_rng(0)
+    out = {"machine": platform.processor() or platform.machine(), "cpu_count": os.cpu_count(), "n_envs": n_envs, "steps": steps}
+    envs = [HoverEnv() for _ in range(n_envs)]
+    for i, e in enumerate(envs):
+        e.reset(seed=i)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        for i, e in enumerate(envs):
+            _, _, term, trunc, _ = e.step(rng.uniform(-1, 1, 4).astype(np.float32))
+            if term or trunc:
+                e.reset()
+    out["hover_env_dummy_vec_env_steps_per_s"] = n_envs * steps / (time.perf_counter() - t0)
+    env = JaxMJXQuadBraxEnv(xml_path=xml)
+    reset = jax.jit(jax.vmap(env.reset)); step = jax.jit(jax.vmap(env.step))
+    state = reset(jax.random.split(jax.random.PRNGKey(0), n_envs))
+    acts = jp.asarray(rng.uniform(-1, 1, (steps, n_envs, 4)).astype(np.float32))
+    state = step(state, acts[0]); jax.block_until_ready(state.obs)          # compile
+    t0 = time.perf_counter()
+    for t in range(steps):
+        state = step(state, acts[t])
+    jax.block_until_ready(state.obs)
+    out["mjx_brax_env_jit_vmap_steps_per_s"] = n_envs * steps / (time.perf_counter() - t0)
+    out["jax_backend"] = jax.default_backend()
     return out
 
 

@@ -115,11 +115,6 @@ __device__ __forceinline__ uint32_t pack_mask2_bf16(float lo, float hi, uint32_t
     return p & m;
 }
 
-#ifndef QS_PPO_TS_HEADS
-#define QS_PPO_TS_HEADS 1        /* two-tile kernel: relu(H2) is ALSO stored into tensor memory (in place over the first 64 of the
-                                    slot's consumed working columns) and OUT = A2 . W3 runs as TS-form MMAs (A from TMEM, ~8
-                                    instead of ~64 cycles per N = 16 instruction); OUT lands in working columns [64, 80) */
-#endif
 #ifndef QS_PPO_DYNAMIC_ISSUE
 #define QS_PPO_DYNAMIC_ISSUE 0   /* 1: the issuer serves whichever slot is ready first (-10 % issuer idle time in the phase
                                     profile, no gain in the measured minibatch time, and the accumulation order -- hence the
@@ -369,13 +364,8 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                             break;
                         case 2:     // OUT = A2 . W3
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-#if QS_PPO_TS_HEADS
-                                mma_bf16_ts(tw + 64u, tw + 8u * (uint32_t)j, dk(S::W3 + j * 512, 16), id_kk16, j > 0);
-#else
+                            for (int j = 0; j < 8; ++j)
                                 mma_bf16(tw, dk(a2 + j * 4096, 128), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
-#endif
-                            }
                             break;
                         case 3:     // dH2 = dOUT . W3^T ; dW3 += A2^T . dOUT (must finish before D2 overwrites A2)
                             mma_bf16(tw, dk(dout, 128), dmn(S::W3, 256u), id_kmn128, 0u);
@@ -448,13 +438,8 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                             break;
                         case 2:     // OUT = A2 . W3
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-#if QS_PPO_TS_HEADS
-                                mma_bf16_ts(tw + 64u, tw + 8u * (uint32_t)j, dk(S::W3 + j * 512, 16), id_kk16, j > 0);
-#else
+                            for (int j = 0; j < 8; ++j)
                                 mma_bf16(tw, dk(a2 + j * 4096, 128), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
-#endif
-                            }
                             break;
                         case 3:     // dH2 = dOUT . W3^T ; dW3 += A2^T . dOUT (must finish before D2 overwrites A2)
                             mma_bf16(tw, dk(dout, 128), dmn(S::W3, 256u), id_kmn128, 0u);
@@ -509,10 +494,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         auto signal = [&]() { fence_async_smem(); fence_before(); mbar_arrive(ready); };
         auto wait_done = [&]() { mbar_wait(done, ph); ph ^= 1u; fence_after(); };
         // Epilogues: the TMEM load of column chunk c + 1 is in flight while chunk c is converted and stored.
-        // also_tmem: the packed activations additionally go back into tensor memory, in place over the first half of the
-        // (consumed) working columns -- chunk c's 16 packed columns to [16 c, 16 c + 16) after [32 c, 32 c + 32) was loaded,
-        // the one load in flight covers [32 (c + 1), 32 (c + 2)) -- as the A operand of a TS-form MMA
-        auto epilogue_relu = [&](int dst, bool also_tmem) {
+        auto epilogue_relu = [&](int dst) {
             uint32_t r[2][32];
             tmem_ld32_async(tw, r[0]);
             tmem_ld_wait(r[0]);
@@ -520,17 +502,15 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             for (int c = 0; c < 4; ++c) {
                 if (c + 1 < 4) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
                 const uint32_t* v = r[c & 1];
-                uint32_t pk[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) pk[q] = pack_relu_bf16_u(v[2 * q], v[2 * q + 1]);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t* h = v + q * 8;
                     *reinterpret_cast<uint4*>(sl + dst + op_offset(128, tid, c * 4 + q)) =
-                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                if (also_tmem) tmem_st16(tw + (uint32_t)(16 * c), pk);
+                        make_uint4(pack_relu_bf16_u(h[0], h[1]), pack_relu_bf16_u(h[2], h[3]), pack_relu_bf16_u(h[4], h[5]),
+                                   pack_relu_bf16_u(h[6], h[7]));
+                }
                 if (c + 1 < 4) tmem_ld_wait(r[(c + 1) & 1]);
             }
-            if (also_tmem) tmem_st_wait();
         };
         auto epilogue_mask_inplace = [&](int buf) {       // buf <- bf16(working columns * [buf > 0])
             uint32_t r[2][32];
@@ -607,19 +587,19 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         for (int it = 0; it < iters; ++it) {
             wait_done();                           // H1
             QS_PPOP(0);
-            epilogue_relu(S::A1, false);
+            epilogue_relu(S::A1);
             signal();
             QS_PPOP(1);
             wait_done();                           // H2
             QS_PPOP(2);
-            epilogue_relu(S::A2, QS_PPO_TS_HEADS != 0);
+            epilogue_relu(S::A2);
             signal();
             QS_PPOP(3);
             wait_done();                           // OUT
             QS_PPOP(4);
             {
                 float out[16];
-                tmem_ld16(tw + (QS_PPO_TS_HEADS ? 64u : 0u), out);
+                tmem_ld16(tw, out);
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
                 if (net == 0) {
                     const float a[4] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w};

@@ -267,6 +267,16 @@ int qs_rollout_random(QsHandle h, float* state, int32_t T, uint32_t t0, float* s
     if (h->P.auto_reset == QS_RESET_RESTORE_FIRST && !first_state)
         return fail(QS_EINVAL, "qs_rollout_random: auto_reset=restore_first needs first_state");
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        // plain north-star configuration, even env count: two envs per thread on the packed FP32 pipe (qs_step2.cuh)
+        const QsParams& Pq = h->P;
+        static const int use_step2 = getenv("QS_STEP2") ? atoi(getenv("QS_STEP2")) : 1;      // A/B knob
+        if (use_step2 && Pq.mode == QS_MODE_HOVER_GYM && !Pq.battery && !Pq.rate_wrapper && !Pq.waypoint_mode && !Pq.pre_clip_action &&
+            (h->n & 1) == 0 && (((uintptr_t)state | (uintptr_t)stats) & 7u) == 0) {
+            qs::rollout_random2_kernel<<<nblocks(h->n / 2, qs::kBlock2), qs::kBlock2, 0, s>>>(h->P, h->n, h->n / 2, state, T, t0, stats);
+            return check_launch("rollout_random2_kernel");
+        }
+    }
     QS_DISPATCH_MODE(h->P.mode, (qs::rollout_random_kernel<M_><<<nblocks(h->n, qs::kBlock), qs::kBlock, 0, s>>>(
         h->P, h->tables(), h->n, state, T, t0, stats, first_state)));
     return check_launch("rollout_random_kernel");

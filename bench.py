@@ -52,13 +52,14 @@ STATE_SETS = 4              # 4 x 294 MB of state/obs/action traffic rotate, so 
 
 
 def source_fingerprint():
-    """sha256 over the kernel sources: ties a committed ncu traffic measurement to the code that was measured."""
-    import glob
+    """sha256 over the STEP kernel's sources (its include closure + the launcher + the ABI header): ties a committed ncu
+    traffic measurement to the code that was measured."""
     import hashlib
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "uav_reinforcement_learning_control_b200", "csrc")
-    for f in sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")) +
-                    [os.path.join(ROOT, "include", "quadsim_abi.h")]):
+    files = [os.path.join(csrc, f) for f in ("qs_dynamics.cuh", "qs_env.cuh", "qs_kernels.cuh", "qs_math.cuh", "qs_pack2.cuh",
+                                             "qs_philox.cuh", "qs_step2.cuh", "qs_traj.cuh", "quadsim.cu")]
+    for f in files + [os.path.join(ROOT, "include", "quadsim_abi.h")]:
         with open(f, "rb") as fh:
             h.update(os.path.basename(f).encode()); h.update(fh.read())
     return h.hexdigest()[:16]
@@ -359,7 +360,7 @@ def main():
                                 "126 MB, writes are short of the algorithmic 168 MB because dirty lines still sit in the 126 MB L2 "
                                 "when the kernel ends; traffic_steady_state = the same launches without cache flushes, where every "
                                 "launch also absorbs its predecessor's write-backs",
-                "kernel": "qs::step_kernel<QS_MODE_HOVER_GYM, FeatLean>", "bytes_per_env_step": bytes_per,
+                "kernel": "qs::step2_kernel (two envs per thread, packed f32x2; QS_STEP2=0 selects qs::step_kernel<QS_MODE_HOVER_GYM, FeatLean>)", "bytes_per_env_step": bytes_per,
                 "bytes_per_launch": bytes_per * n, "us_per_launch": us_per_launch,
                 "traffic_source": None if traffic_rec is None else traffic_rec.get("how"),
                 "peak_source": peak_src}

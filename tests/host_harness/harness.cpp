@@ -11,6 +11,7 @@
 
 #include "../../uav_reinforcement_learning_control_b200/csrc/qs_env.cuh"
 #include "../../uav_reinforcement_learning_control_b200/csrc/qs_traj.cuh"
+#include "../../uav_reinforcement_learning_control_b200/csrc/qs_umma_desc.cuh"
 
 using namespace qs;
 
@@ -138,5 +139,9 @@ void hh_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, 
     U4 r = philox4x32_10(U4{c0, c1, c2, c3}, k0, k1);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
+
+// the tcgen05 descriptor packing the tensor-core kernels use (qs_umma_desc.cuh), for tests/test_umma_desc.py
+uint64_t hh_umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) { return tc::make_desc(saddr, lbo_bytes, sbo_bytes); }
+uint32_t hh_umma_idesc(int M, int N, int a_mn, int b_mn) { return tc::idesc_mn(M, N, a_mn, b_mn); }
 
 }  // extern "C"

@@ -100,7 +100,7 @@ class HostHarness:
             src = os.path.join(HARNESS_DIR, "harness.cpp")
             csrc = os.path.join(ROOT, "uav_reinforcement_learning_control_b200", "csrc")
             deps = [src, os.path.join(ROOT, "include", "quadsim_abi.h")] + [
-                os.path.join(csrc, f) for f in ("qs_env.cuh", "qs_dynamics.cuh", "qs_philox.cuh", "qs_math.cuh", "qs_traj.cuh")]
+                os.path.join(csrc, f) for f in ("qs_env.cuh", "qs_dynamics.cuh", "qs_philox.cuh", "qs_math.cuh", "qs_traj.cuh", "qs_umma_desc.cuh")]
             if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
                 subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC",
                                        "-o", so, src])

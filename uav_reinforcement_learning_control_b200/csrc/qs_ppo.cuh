@@ -96,9 +96,6 @@ struct Hyper {
 
 constexpr uint32_t kTmemCols = 512;
 
-__device__ __forceinline__ uint32_t idesc_mn(int M, int N, int a_mn, int b_mn) {
-    return make_idesc(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
-}
 
 // dh * [h > 0] for two elements (h: the packed bf16 pair of the forward activation, >= 0 after the relu), bf16-packed
 __device__ __forceinline__ uint32_t pack_mask_bf16(float lo, float hi, uint32_t hpair) {

@@ -27,6 +27,7 @@
 #include <type_traits>
 #include "qs_kernels.cuh"
 #include "qs_rollout.cuh"
+#include "qs_umma_desc.cuh"
 
 #ifndef QS_TC_PARTNER
 #define QS_TC_PARTNER 1
@@ -57,20 +58,7 @@ constexpr uint32_t kTileCols = 256;     // TMEM columns per tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);                 // start address  [0,14)
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;        // leading byte offset [16,30)
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;        // stride byte offset  [32,46)
-    d |= (uint64_t)1 << 46;                                   // descriptor version 1 (Blackwell)
-    return d;                                                 // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
-}
-
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
+// make_desc / make_idesc / idesc_mn: qs_umma_desc.cuh (host-testable bit packing)
 
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

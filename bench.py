@@ -368,7 +368,10 @@ def main():
     # ---------------------------------------------------------------- e2e: host buffers through the C ABI
     pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory()
     h_act = [(torch.rand(n, 4) * 2 - 1).pin_memory() for _ in range(2)]
-    h_obs, h_rew, h_done = pin(n, 12), pin(n), pin(n)
+    # done comes back as bytes (qs_step_host_bytes: the bool array the reference's step returns), unless the shard is odd
+    D2H = 48 + 4 + (1 if n % 4 == 0 else 4)
+    h_obs, h_rew = pin(n, 12), pin(n)
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory() if n % 4 == 0 else pin(n)
     Ke = max(5, min(K, 40))
     for i in range(3):
         eng.step_host(state, h_act[i % 2].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
@@ -381,8 +384,8 @@ def main():
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     # what bounds it: the D2H of obs / reward / done.  Measure the plain pinned D2H copy rate of this box for the same
     # number of bytes (one cudaMemcpyAsync, all ranks at once, like the e2e loop) so the PCIe fraction is explicit.
-    d_probe = torch.empty((48 + 8) * n // 4, dtype=torch.float32, device=dev)
-    h_probe = torch.empty((48 + 8) * n // 4, dtype=torch.float32).pin_memory()
+    d_probe = torch.empty(D2H * n, dtype=torch.uint8, device=dev)
+    h_probe = torch.empty(D2H * n, dtype=torch.uint8).pin_memory()
     h_probe.copy_(d_probe, non_blocking=True)
     barrier()
     e0.record(stream)
@@ -391,15 +394,15 @@ def main():
     e1.record(stream)
     barrier()
     ms_probe = max_over_ranks(e0.elapsed_time(e1)) / 5
-    pcie_d2h_peak = (48 + 8) * n / (ms_probe * 1e-3) / 1e9
+    pcie_d2h_peak = D2H * n / (ms_probe * 1e-3) / 1e9
     del d_probe, h_probe
     e2e = {"value": world * n * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 * n,
-           "d2h_bytes_per_step": (48 + 8) * n, "steps": Ke, "ms_per_step": ms_e2e / Ke,
-           "pcie_d2h_gbs_per_gpu": (48 + 8) * n * Ke / (ms_e2e * 1e-3) / 1e9,      # what bounds it: obs/reward/done over PCIe
+           "d2h_bytes_per_step": D2H * n, "steps": Ke, "ms_per_step": ms_e2e / Ke,
+           "pcie_d2h_gbs_per_gpu": D2H * n * Ke / (ms_e2e * 1e-3) / 1e9,      # what bounds it: obs/reward/done over PCIe
            "pcie_h2d_gbs_per_gpu": 16 * n * Ke / (ms_e2e * 1e-3) / 1e9,
            "pcie_d2h_copy_peak_gbs_per_gpu": pcie_d2h_peak,                       # measured: same bytes, one plain pinned copy
-           "pcie_frac": ((48 + 8) * n * Ke / (ms_e2e * 1e-3) / 1e9) / pcie_d2h_peak,
-           "api": "qs_step_host (C ABI, pinned host buffers; what HoverVecEnv.step(numpy) calls)"}
+           "pcie_frac": (D2H * n * Ke / (ms_e2e * 1e-3) / 1e9) / pcie_d2h_peak,
+           "api": "qs_step_host_bytes (C ABI, pinned host buffers: float32 actions in, float32 obs / reward and byte done flags out; what HoverVecEnv.step(numpy) calls)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

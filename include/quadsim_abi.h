@@ -365,6 +365,12 @@ int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_
 int qs_step_host_ex(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
                     float* done_host, float* trunc_host, void* stream);
 
+/* the same with the flags as bytes (0 / 1) -- the dtype the reference returns: Gymnasium's `terminated` / `truncated` are
+ * bools (hover_env.py:186-198), SB3's `dones` a bool array -- which also takes 3 of the 56 bytes per env-step off the
+ * device-to-host link this call is bound by.  num_envs must be a multiple of 4. */
+int qs_step_host_bytes(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
+                    uint8_t* done_host, uint8_t* trunc_host, void* stream);
+
 /* launch accounting for bench.py's gpu_launches claim */
 uint64_t qs_launch_count(void);
 

@@ -190,6 +190,39 @@ def test_host_buffer_step_returns_truncation_and_refuses_pageable_memory():
         eng.step_host(st_a, h["act"], np.zeros((n, 12), np.float32), h["rew"], h["done"])
 
 
+@pytest.mark.parametrize("n", [5000, 1 << 18, 4])
+def test_host_buffer_step_with_byte_flags(n):
+    """qs_step_host_bytes: terminated / truncated as bytes (the bool arrays Gymnasium / SB3 return) are the float flags of
+    the device path, for a one-chunk batch and for one that goes through the chunked schedule; odd batches are refused."""
+    import torch
+    from uav_reinforcement_learning_control_b200.engine import Engine, QuadSimError
+    cfg = Q.EnvConfig.north_star(seed=5, max_episode_steps=3)
+    eng = Engine(cfg, n, device=0)
+    st_a = eng.new_state(); eng.reset(st_a); st_b = st_a.clone()
+    pin = lambda *s: torch.empty(s, dtype=torch.float32).pin_memory().numpy()
+    pin8 = lambda *s: torch.full(s, 7, dtype=torch.uint8).pin_memory().numpy()
+    h = dict(act=pin(n, 4), obs=pin(n, 12), rew=pin(n), done=pin8(n), trunc=pin8(n))
+    rng = np.random.default_rng(1)
+    for t in range(4):
+        h["act"][:] = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        eng.step_host(st_a, h["act"], h["obs"], h["rew"], h["done"], h["trunc"] if t % 2 == 0 else None)
+        tr = torch.zeros(n, device="cuda")
+        obs, rew, done = eng.step(st_b, torch.from_numpy(h["act"]).cuda(), truncated=tr)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(h["done"], done.cpu().numpy().astype(np.uint8))
+        if t % 2 == 0:
+            np.testing.assert_array_equal(h["trunc"], tr.cpu().numpy().astype(np.uint8))
+        np.testing.assert_array_equal(h["obs"], obs.cpu().numpy()); np.testing.assert_array_equal(h["rew"], rew.cpu().numpy())
+    assert torch.equal(st_a, st_b)
+    if n == 4:
+        eng3 = Engine(cfg, 6, device=0)
+        s3 = eng3.new_state(); eng3.reset(s3)
+        with pytest.raises(QuadSimError, match="multiple of 4"):
+            eng3.step_host(s3, pin(6, 4), pin(6, 12), pin(6), pin8(6))
+    with pytest.raises(QuadSimError, match="same dtype"):
+        eng.step_host(st_a, h["act"], h["obs"], h["rew"], h["done"], pin(n))
+
+
 def test_two_engines_leave_the_callers_device_alone():
     """handle-taking entry points run on the handle's device and restore the caller's current device; tensors on
     another device are refused by the binding."""

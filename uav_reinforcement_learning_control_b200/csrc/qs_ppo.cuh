@@ -112,6 +112,14 @@ __device__ __forceinline__ uint32_t pack_mask2_bf16(float lo, float hi, uint32_t
     return p & m;
 }
 
+#ifndef QS_PPO_TS_HEADS
+#define QS_PPO_TS_HEADS 1        /* relu(H2) is ALSO stored into tensor memory (in place over the first 64 of the slot's consumed
+                                    working columns) and OUT = A2 . W3 runs as TS-form MMAs (A from TMEM): 32 KB less shared-
+                                    memory operand traffic per tile; OUT lands in working columns [64, 80) */
+#endif
+#ifndef QS_PPO_STAGGER
+#define QS_PPO_STAGGER 3         /* dynamic issue: slot 1 starts once slot 0 has been issued this phase of its first tile */
+#endif
 #ifndef QS_PPO_DYNAMIC_ISSUE
 #define QS_PPO_DYNAMIC_ISSUE 0   /* 1: the issuer serves whichever slot is ready first (-10 % issuer idle time in the phase
                                     profile, no gain in the measured minibatch time, and the accumulation order -- hence the
@@ -152,7 +160,8 @@ namespace ppo {
 //     committed before the workers are released), so a slot needs 72 KB of operands.
 struct SmemQ {
     static constexpr int W1 = 0, W2 = 4096, W3 = W2 + 32768, B2 = W3 + 4096, WEND = B2 + 4096;
-    static constexpr int A0 = 0, A1 = 2 * 4096, A2 = A1 + 32768, DOUT = A2 + 32768, SLOT_BYTES = DOUT + 4096;   // per slot
+    // per slot; ONES (128 rows x 16: a constant 1 in K slot 0) sits directly below A1: [ONES | A1] is ONE MN-major operand
+    static constexpr int A0 = 0, ONES = 2 * 4096, A1 = ONES + 4096, A2 = A1 + 32768, DOUT = A2 + 32768, SLOT_BYTES = DOUT + 4096;
     static constexpr int SLOT0 = WEND;
     static constexpr int F32 = SLOT0 + 2 * SLOT_BYTES;
     static constexpr int kB3 = 0, kLogStd = 4, kInvSig = 8, kMean = 12, kInvStd = 24, kNumF = 36;
@@ -163,7 +172,8 @@ struct SmemQ {
     static constexpr int STG_ACT = 128 * 48, STG_SCAL = STG_ACT + 128 * 16, STG_BYTES = STG_SCAL + 128 * 16;   // scalars: [128][4] (packed rows) or 3 x [128]
     static constexpr int TOTAL = STG + 2 * STG_BYTES;
 };
-constexpr uint32_t kQColW = 0 /* + 128 * slot */, kQColW2 = 256, kQColW1 = 384, kQColW3 = 400, kQColB2 = 416;
+// working columns [128 slot, 128 slot + 128) | db2 (column 0 of 16) + dW2^T (128): lane = output feature | dW1^T | dW3
+constexpr uint32_t kQColW = 0 /* + 128 * slot */, kQColW2 = 256, kQColW1 = 400, kQColW3 = 416;
 constexpr int kThreads2 = 320;       // 2 x 128 workers + issuer warp + gather warp
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -216,6 +226,11 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     for (int i = gtid; i < kH * kH; i += kThreads2) put(S::W2, 128, i % kH, i / kH, __ldg(params + oW2 + i));   // 8 loads in flight
     if (net == 0) { for (int i = gtid; i < kH * kA; i += kThreads2) put(S::W3, 16, i % kA, i / kA, params[L.aW3 + i]); }
     else          { for (int k = gtid; k < kH; k += kThreads2) put(S::W3, 16, 0, k, params[L.cW3 + k]); }
+    for (int i = gtid; i < 2 * 2 * 128; i += kThreads2) {          // ONES: [slot][K chunk][row] x 16 B, a bf16 1.0 in K slot 0
+        const int sl_ = i >> 8, c = (i >> 7) & 1, row = i & 127;
+        *reinterpret_cast<uint4*>(smem + S::SLOT0 + sl_ * S::SLOT_BYTES + S::ONES + op_offset(128, row, c)) =
+            make_uint4(c == 0 ? 0x3F80u : 0u, 0u, 0u, 0u);
+    }
     if (gtid < kA) {
         sF[S::kB3 + gtid] = net ? (gtid == 0 ? params[L.cb3] : 0.f) : params[L.ab3 + gtid];
         const float ls = params[L.log_std + gtid];
@@ -306,37 +321,87 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             auto dmn = [&](int off, uint32_t grp_stride) { return (grp_stride == 2048u ? dMN2048 : dMN256) + (uint64_t)(off >> 4); };
             const uint32_t id_kk128 = idesc_mn(128, 128, 0, 0), id_kk16 = idesc_mn(128, 16, 0, 0);
             const uint32_t id_kmn128 = idesc_mn(128, 128, 0, 1);
-            const uint32_t id_mm128 = idesc_mn(128, 128, 1, 1), id_mm16 = idesc_mn(128, 16, 1, 1);
+            const uint32_t id_mm144 = idesc_mn(128, 144, 1, 1), id_mm16 = idesc_mn(128, 16, 1, 1);
             uint32_t ph[2] = {0u, 0u};
             // Every hand-off is strictly "workers signal ready -> issuer issues -> commit -> workers wait", one phase at
             // a time per slot: a slot can never run two phases ahead of the issuer, which would alias the mbarrier parity.
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {               // prologue: H1 of each slot's first tile
+            // one phase of slot s (tile `it` of the slot); `first` = 0 only for the very first accumulation of the CTA
+            auto issue_phase = [&](int s, int phase, int it) {
                 const int base = S::SLOT0 + s * S::SLOT_BYTES;
-                mbar_wait(&bar_ready[s], ph[s]); ph[s] ^= 1u;
-                fence_after();
+                const int a0 = base + S::A0 + (it & 1) * 4096, a1 = base + S::A1, a2 = base + S::A2, dout = base + S::DOUT;
+                const int ones = base + S::ONES;
+                const uint32_t tw = tmem + kQColW + (uint32_t)(s * 128);
+                const uint32_t first = (it == 0 && s == 0) ? 0u : 1u;
                 if (elect_one()) {
-                    mma_bf16(tmem + kQColW + (uint32_t)(s * 128), dk(base + S::A0, 128), dk(S::W1, 128), id_kk128, 0u);
+                    switch (phase) {
+                    case 0:     // H1 of the slot's first tile
+                        mma_bf16(tw, dk(base + S::A0, 128), dk(S::W1, 128), id_kk128, 0u);
+                        break;
+                    case 1:     // H2 = A1 . W2 + b2
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            mma_bf16(tw, dk(a1 + j * 4096, 128), dk(S::W2 + j * 4096, 128), id_kk128, j > 0);
+                        mma_bf16(tw, dk(a0, 128), dk(S::B2, 128), id_kk128, 1u);
+                        break;
+                    case 2:     // OUT = A2 . W3: TS form, relu(H2) read from working columns [0, 64), OUT -> [64, 80)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+#if QS_PPO_TS_HEADS
+                            mma_bf16_ts(tw + 64u, tw + 8u * (uint32_t)j, dk(S::W3 + j * 512, 16), id_kk16, j > 0);
+#else
+                            mma_bf16(tw, dk(a2 + j * 4096, 128), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
+#endif
+                        }
+                        break;
+                    case 3:     // dH2 = dOUT . W3^T ; dW3 += A2^T . dOUT (must finish before D2 overwrites A2)
+                        mma_bf16(tw, dk(dout, 128), dmn(S::W3, 256u), id_kmn128, 0u);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            mma_bf16(tmem + kQColW3, dmn(a2 + j * 256, 2048u), dmn(dout + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
+                        break;
+                    case 4:     // dH1 = D2 . W2^T ; db2 | dW2^T += D2^T . [1 | A1]   (D2 lives in the A2 buffer; the constant
+                                // ONES block sits right below A1, so one N = 144 instruction per K step reads both)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            mma_bf16(tw, dk(a2 + j * 4096, 128), dmn(S::W2 + j * 256, 2048u), id_kmn128, j > 0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            mma_bf16(tmem + kQColW2, dmn(a2 + j * 256, 2048u), dmn(ones + j * 256, 2048u), id_mm144, j > 0 ? 1u : first);
+                        break;
+                    default:    // dW1^T | db1 += D1^T . A0 (D1 lives in the A1 buffer), then H1 of the slot's NEXT tile,
+                                // whose A0 the workers wrote into the other A0 buffer together with D1
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            mma_bf16(tmem + kQColW1, dmn(a1 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
+                        if (it + 1 < iters)
+                            mma_bf16(tw, dk(base + S::A0 + ((it + 1) & 1) * 4096, 128), dk(S::W1, 128), id_kk128, 0u);
+                        break;
+                    }
                     mma_commit(&bar_done[s]);
                 }
                 __syncwarp();
-            }
-#if QS_PPO_DYNAMIC_ISSUE
-            // After the prologue the two slots are served in whatever order they become ready (a fixed 0,1,0,1 order made
-            // the pipe wait for the slower slot: ~35 % of the issuer's time).  The ready test is done by lane 0 and
-            // broadcast, so control flow stays warp-uniform.
-            int pnext[2] = {1, 1}, itn[2] = {0, 0};
-            uint32_t acc3 = 0u, acc2 = 0u, acc1 = 0u;          // 0 until the first MMA into the dW3 / dW2,db2 / dW1 accumulators
-            int left = 2 * iters * 5;
+            };
 #ifdef QS_PPO_PROFILE
             long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             long long pc_ = clock64();
 #endif
+#if QS_PPO_DYNAMIC_ISSUE
+            // Order-constrained dynamic service (tuning knob, measured SLOWER than the fixed order: profiles/README.md).
+            // Slot 1 starts its first tile once slot 0 has been issued phase QS_PPO_STAGGER; after that each slot is served
+            // as soon as it is ready, except that the phases which accumulate into the shared gradient columns (3: dW3,
+            // 4: dW2 | db2, 5: dW1) are taken strictly alternately, slot 0 first, so the summation order of every
+            // accumulator -- hence the gradient, bit for bit -- does not depend on timing.
+            int pnext[2] = {0, 0}, itn[2] = {0, 0};            // phase 0 = H1 of the slot's first tile
+            int turn[3] = {0, 0, 0};                           // whose accumulation comes next, per accumulating phase
+            int left = 2 * (iters * 5 + 1);
 #pragma unroll 1
             while (left > 0) {
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     if (itn[s] >= iters) continue;
+                    const int phase = pnext[s], it = itn[s];
+                    if (phase >= 3 && turn[phase - 3] != s) continue;
+                    if (s == 1 && phase == 0 && itn[0] == 0 && pnext[0] <= QS_PPO_STAGGER && iters > 1) continue;
                     uint32_t ok = 0u;
                     if (lane == 0) {
                         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
@@ -346,54 +411,9 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                     if (!ok) continue;
                     ph[s] ^= 1u;
                     fence_after();
-                    const int phase = pnext[s], it = itn[s];
-                    const int base = S::SLOT0 + s * S::SLOT_BYTES;
-                    const int a0 = base + S::A0 + (it & 1) * 4096, a1 = base + S::A1, a2 = base + S::A2, dout = base + S::DOUT;
-                    const uint32_t tw = tmem + kQColW + (uint32_t)(s * 128);
                     QS_PPOP(0);
-                    if (elect_one()) {
-                        switch (phase) {
-                        case 1:     // H2 = A1 . W2 + b2
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tw, dk(a1 + j * 4096, 128), dk(S::W2 + j * 4096, 128), id_kk128, j > 0);
-                            mma_bf16(tw, dk(a0, 128), dk(S::B2, 128), id_kk128, 1u);
-                            break;
-                        case 2:     // OUT = A2 . W3
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tw, dk(a2 + j * 4096, 128), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
-                            break;
-                        case 3:     // dH2 = dOUT . W3^T ; dW3 += A2^T . dOUT (must finish before D2 overwrites A2)
-                            mma_bf16(tw, dk(dout, 128), dmn(S::W3, 256u), id_kmn128, 0u);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tmem + kQColW3, dmn(a2 + j * 256, 2048u), dmn(dout + j * 256, 2048u), id_mm16, j > 0 ? 1u : acc3);
-                            break;
-                        case 4:     // dH1 = D2 . W2^T ; dW2 += A1^T . D2 ; db2 += D2^T . A0   (D2 lives in the A2 buffer)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tw, dk(a2 + j * 4096, 128), dmn(S::W2 + j * 256, 2048u), id_kmn128, j > 0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tmem + kQColW2, dmn(a1 + j * 256, 2048u), dmn(a2 + j * 256, 2048u), id_mm128, j > 0 ? 1u : acc2);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tmem + kQColB2, dmn(a2 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : acc2);
-                            break;
-                        default:    // dW1^T | db1 += D1^T . A0 (D1 lives in the A1 buffer), then H1 of the slot's NEXT tile,
-                                    // whose A0 the workers wrote into the other A0 buffer together with D1
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tmem + kQColW1, dmn(a1 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : acc1);
-                            if (it + 1 < iters)
-                                mma_bf16(tw, dk(base + S::A0 + ((it + 1) & 1) * 4096, 128), dk(S::W1, 128), id_kk128, 0u);
-                            break;
-                        }
-                        mma_commit(&bar_done[s]);
-                    }
-                    __syncwarp();
-                    if (phase == 3) acc3 = 1u; else if (phase == 4) acc2 = 1u; else if (phase == 5) acc1 = 1u;
+                    issue_phase(s, phase, it);
+                    if (phase >= 3) turn[phase - 3] ^= 1;
                     if (++pnext[s] == 6) { pnext[s] = 1; ++itn[s]; }
                     --left;
                     QS_PPOP(1);
@@ -406,67 +426,24 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                        net, prof_[1] / iters, (prof_[0] + prof_[2]) / iters);
 #endif
 #else
-#ifdef QS_PPO_PROFILE
-            long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            long long pc_ = clock64();
-#endif
             // fixed service order slot 0, slot 1, slot 0, ...: the accumulation order into the gradient accumulators is
             // then the same in every run, i.e. the gradient is bitwise reproducible
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {               // prologue: H1 of each slot's first tile
+                mbar_wait(&bar_ready[s], ph[s]); ph[s] ^= 1u;
+                fence_after();
+                issue_phase(s, 0, 0);
+            }
 #pragma unroll 1
             for (int it = 0; it < iters; ++it) {
 #pragma unroll 1
                 for (int phase = 1; phase < 6; ++phase) {
 #pragma unroll
                     for (int s = 0; s < 2; ++s) {
-                        const int base = S::SLOT0 + s * S::SLOT_BYTES;
-                        const int a0 = base + S::A0 + (it & 1) * 4096, a1 = base + S::A1, a2 = base + S::A2, dout = base + S::DOUT;
-                        const uint32_t tw = tmem + kQColW + (uint32_t)(s * 128);
-                        const uint32_t first = (it == 0 && s == 0) ? 0u : 1u;
                         mbar_wait(&bar_ready[s], ph[s]); ph[s] ^= 1u;
                         fence_after();
                         QS_PPOP(0);
-                        if (elect_one()) {
-                        switch (phase) {
-                        case 1:     // H2 = A1 . W2 + b2
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tw, dk(a1 + j * 4096, 128), dk(S::W2 + j * 4096, 128), id_kk128, j > 0);
-                            mma_bf16(tw, dk(a0, 128), dk(S::B2, 128), id_kk128, 1u);
-                            break;
-                        case 2:     // OUT = A2 . W3
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tw, dk(a2 + j * 4096, 128), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
-                            break;
-                        case 3:     // dH2 = dOUT . W3^T ; dW3 += A2^T . dOUT (must finish before D2 overwrites A2)
-                            mma_bf16(tw, dk(dout, 128), dmn(S::W3, 256u), id_kmn128, 0u);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tmem + kQColW3, dmn(a2 + j * 256, 2048u), dmn(dout + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
-                            break;
-                        case 4:     // dH1 = D2 . W2^T ; dW2 += A1^T . D2 ; db2 += D2^T . A0   (D2 lives in the A2 buffer)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tw, dk(a2 + j * 4096, 128), dmn(S::W2 + j * 256, 2048u), id_kmn128, j > 0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tmem + kQColW2, dmn(a1 + j * 256, 2048u), dmn(a2 + j * 256, 2048u), id_mm128, j > 0 ? 1u : first);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tmem + kQColB2, dmn(a2 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
-                            break;
-                        default:    // dW1^T | db1 += D1^T . A0 (D1 lives in the A1 buffer), then H1 of the slot's NEXT tile,
-                                    // whose A0 the workers wrote into the other A0 buffer together with D1
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mma_bf16(tmem + kQColW1, dmn(a1 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
-                            if (it + 1 < iters)
-                                mma_bf16(tw, dk(base + S::A0 + ((it + 1) & 1) * 4096, 128), dk(S::W1, 128), id_kk128, 0u);
-                            break;
-                        }
-                        mma_commit(&bar_done[s]);
-                        }
-                        __syncwarp();
+                        issue_phase(s, phase, it);
                         QS_PPOP(1);
                     }
                 }
@@ -491,7 +468,10 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         auto signal = [&]() { fence_async_smem(); fence_before(); mbar_arrive(ready); };
         auto wait_done = [&]() { mbar_wait(done, ph); ph ^= 1u; fence_after(); };
         // Epilogues: the TMEM load of column chunk c + 1 is in flight while chunk c is converted and stored.
-        auto epilogue_relu = [&](int dst) {
+        // also_tmem: the packed activations additionally go back into tensor memory, in place over the first half of the
+        // (consumed) working columns -- chunk c's 16 packed columns to [16 c, 16 c + 16) after [32 c, 32 c + 32) was loaded,
+        // the one load in flight covers [32 (c + 1), 32 (c + 2)) -- as the A operand of a TS-form MMA
+        auto epilogue_relu = [&](int dst, bool also_tmem) {
             uint32_t r[2][32];
             tmem_ld32_async(tw, r[0]);
             tmem_ld_wait(r[0]);
@@ -499,15 +479,17 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             for (int c = 0; c < 4; ++c) {
                 if (c + 1 < 4) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
                 const uint32_t* v = r[c & 1];
+                uint32_t pk[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t* h = v + q * 8;
+                for (int q = 0; q < 16; ++q) pk[q] = pack_relu_bf16_u(v[2 * q], v[2 * q + 1]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
                     *reinterpret_cast<uint4*>(sl + dst + op_offset(128, tid, c * 4 + q)) =
-                        make_uint4(pack_relu_bf16_u(h[0], h[1]), pack_relu_bf16_u(h[2], h[3]), pack_relu_bf16_u(h[4], h[5]),
-                                   pack_relu_bf16_u(h[6], h[7]));
-                }
+                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                if (also_tmem) tmem_st16(tw + (uint32_t)(16 * c), pk);
                 if (c + 1 < 4) tmem_ld_wait(r[(c + 1) & 1]);
             }
+            if (also_tmem) tmem_st_wait();
         };
         auto epilogue_mask_inplace = [&](int buf) {       // buf <- bf16(working columns * [buf > 0])
             uint32_t r[2][32];
@@ -584,19 +566,19 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         for (int it = 0; it < iters; ++it) {
             wait_done();                           // H1
             QS_PPOP(0);
-            epilogue_relu(S::A1);
+            epilogue_relu(S::A1, false);
             signal();
             QS_PPOP(1);
             wait_done();                           // H2
             QS_PPOP(2);
-            epilogue_relu(S::A2);
+            epilogue_relu(S::A2, QS_PPO_TS_HEADS != 0);
             signal();
             QS_PPOP(3);
             wait_done();                           // OUT
             QS_PPOP(4);
             {
                 float out[16];
-                tmem_ld16(tw, out);
+                tmem_ld16(tw + (QS_PPO_TS_HEADS ? 64u : 0u), out);
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
                 if (net == 0) {
                     const float a[4] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w};
@@ -678,22 +660,23 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     const float scale = 1.0f / (float)b.n;
     if (wg == 0) {
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        {
+            float v0[16];
+            tmem_ld16(tmem + lane_off + kQColW2, v0);         // lane = output feature n of layer 2; column 0: db2
+            out[ob2 + tid] = v0[0] * scale;
+        }
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {           // dW2: lane = input feature k, column = output feature n
+        for (int c = 0; c < 4; ++c) {           // dW2^T: column 16 + k = input feature k; a warp stores 32 consecutive n per k
             float v[32];
-            tmem_ld32(tmem + lane_off + kQColW2 + (uint32_t)(c * 32), v);
-            float4* d4 = reinterpret_cast<float4*>(out + oW2 + tid * kH + c * 32);
+            tmem_ld32(tmem + lane_off + kQColW2 + 16u + (uint32_t)(c * 32), v);
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                d4[q] = make_float4(v[4 * q] * scale, v[4 * q + 1] * scale, v[4 * q + 2] * scale, v[4 * q + 3] * scale);
+            for (int k = 0; k < 32; ++k) out[oW2 + (c * 32 + k) * kH + tid] = v[k] * scale;
         }
         float v[16];
         tmem_ld16(tmem + lane_off + kQColW1, v);  // lane = hidden n, column = obs k | 12: bias
 #pragma unroll
         for (int k = 0; k < kD; ++k) out[oW1 + k * kH + tid] = v[k] * scale;
         out[ob1 + tid] = v[kD] * scale;
-        tmem_ld16(tmem + lane_off + kQColB2, v);
-        out[ob2 + tid] = v[kD] * scale;
         tmem_ld16(tmem + lane_off + kQColW3, v);  // lane = hidden k, column = head output
         if (net == 0) {
 #pragma unroll

@@ -287,8 +287,37 @@ int qs_step_host(QsHandle h, float* state, const float* action_host, float* obs_
     return qs_step_host_ex(h, state, action_host, obs_host, reward_host, done_host, nullptr, stream);
 }
 
+namespace qs {
+// float 0/1 flags -> bytes (Gymnasium's `terminated` / `truncated` are bool arrays): 4 flags per thread
+__global__ void __launch_bounds__(256)
+flags_u8_kernel(const float4* __restrict__ done, const float4* __restrict__ trunc, uchar4* __restrict__ done8,
+                uchar4* __restrict__ trunc8, int n4) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n4) return;
+    const float4 d = done[i];
+    done8[i] = make_uchar4(d.x != 0.f, d.y != 0.f, d.z != 0.f, d.w != 0.f);
+    if (trunc) {
+        const float4 t = trunc[i];
+        trunc8[i] = make_uchar4(t.x != 0.f, t.y != 0.f, t.z != 0.f, t.w != 0.f);
+    }
+}
+}  // namespace qs
+
+static int step_host_impl(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
+                          void* done_host, void* trunc_host, bool flags_u8, void* stream);
+
 int qs_step_host_ex(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
                     float* done_host, float* trunc_host, void* stream) {
+    return step_host_impl(h, state, action_host, obs_host, reward_host, done_host, trunc_host, false, stream);
+}
+
+int qs_step_host_bytes(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
+                    uint8_t* done_host, uint8_t* trunc_host, void* stream) {
+    return step_host_impl(h, state, action_host, obs_host, reward_host, done_host, trunc_host, true, stream);
+}
+
+static int step_host_impl(QsHandle h, float* state, const float* action_host, float* obs_host, float* reward_host,
+                          void* done_host, void* trunc_host, bool flags_u8, void* stream) {
     if (!h || !state || !action_host || !obs_host || !reward_host || !done_host)
         return fail(QS_EINVAL, "qs_step_host: null");
     if (h->P.auto_reset == QS_RESET_RESTORE_FIRST) return fail(QS_EUNSUPPORTED, "qs_step_host: use qs_step for brax auto-reset");
@@ -306,12 +335,15 @@ int qs_step_host_ex(QsHandle h, float* state, const float* action_host, float* o
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)h->n, D = (size_t)h->P.obs_dim;
     if (!h->scratch) {
-        QS_CUDA(cudaMalloc(&h->scratch, n * (4 + D + 3) * sizeof(float)));
+        QS_CUDA(cudaMalloc(&h->scratch, n * (4 + D + 3) * sizeof(float) + 2 * ((n + 15) & ~(size_t)15)));   // + byte flags
         for (int k = 0; k < QS_HOST_STREAMS; ++k) QS_CUDA(cudaStreamCreateWithFlags(&h->hs[k], cudaStreamNonBlocking));
         for (int k = 0; k <= QS_HOST_STREAMS; ++k) QS_CUDA(cudaEventCreateWithFlags(&h->hev[k], cudaEventDisableTiming));
     }
     float* d_act = h->scratch; float* d_obs = d_act + 4 * n; float* d_rew = d_obs + D * n; float* d_done = d_rew + n;
     float* d_trunc = trunc_host ? d_done + n : nullptr;
+    uint8_t* d_done8 = reinterpret_cast<uint8_t*>(h->scratch + n * (4 + D + 3));
+    uint8_t* d_trunc8 = d_done8 + ((n + 15) & ~(size_t)15);
+    if (flags_u8 && (n & 3u) != 0) return fail(QS_EUNSUPPORTED, "qs_step_host_bytes: num_envs must be a multiple of 4");
     // Chunked, double-streamed: PCIe is full duplex, so the H2D of chunk k+1 and the kernel of chunk k+1 run under the
     // D2H of chunk k.  The D2H of the observations (48 of the 56 bytes per env) is what bounds the call, so the schedule
     // is built around keeping that copy engine busy: geometrically growing chunks (1/16, 1/16, 1/8, 1/4, 1/2 of the
@@ -346,6 +378,15 @@ int qs_step_host_ex(QsHandle h, float* state, const float* action_host, float* o
         int rc = launch_step(h, (int)lo, (int)cnt, state, d_act, d_obs, d_rew, d_done, d_trunc, nullptr, nullptr, nullptr, cs);
         if (rc != QS_OK) return rc;
         QS_CUDA(cudaMemcpyAsync(obs_host + D * lo, d_obs + D * lo, D * cnt * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        if (flags_u8) {
+            // chunk boundaries are multiples of the block size (128) except the last one, and n % 4 == 0
+            const int n4 = (int)(cnt / 4);
+            qs::flags_u8_kernel<<<nblocks(n4, 256), 256, 0, cs>>>(
+                reinterpret_cast<const float4*>(d_done + lo), d_trunc ? reinterpret_cast<const float4*>(d_trunc + lo) : nullptr,
+                reinterpret_cast<uchar4*>(d_done8 + lo), reinterpret_cast<uchar4*>(d_trunc8 + lo), n4);
+            int rc2 = check_launch("flags_u8_kernel");
+            if (rc2 != QS_OK) return rc2;
+        }
     }
     // reward / done: one copy each on stream 0, after every stream's last kernel (d_rew and d_done are adjacent)
     for (int k = 1; k < QS_HOST_STREAMS; ++k) {
@@ -353,8 +394,13 @@ int qs_step_host_ex(QsHandle h, float* state, const float* action_host, float* o
         QS_CUDA(cudaStreamWaitEvent(h->hs[0], h->hev[1 + k], 0));
     }
     QS_CUDA(cudaMemcpyAsync(reward_host, d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
-    QS_CUDA(cudaMemcpyAsync(done_host, d_done, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
-    if (trunc_host) QS_CUDA(cudaMemcpyAsync(trunc_host, d_trunc, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
+    if (flags_u8) {
+        QS_CUDA(cudaMemcpyAsync(done_host, d_done8, n, cudaMemcpyDeviceToHost, h->hs[0]));
+        if (trunc_host) QS_CUDA(cudaMemcpyAsync(trunc_host, d_trunc8, n, cudaMemcpyDeviceToHost, h->hs[0]));
+    } else {
+        QS_CUDA(cudaMemcpyAsync(done_host, d_done, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
+        if (trunc_host) QS_CUDA(cudaMemcpyAsync(trunc_host, d_trunc, n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[0]));
+    }
     QS_CUDA(cudaEventRecord(h->hev[1], h->hs[0]));
     QS_CUDA(cudaStreamWaitEvent(s, h->hev[1], 0));                // later work on the caller's stream sees the new state
     QS_CUDA(cudaStreamSynchronize(s));

@@ -46,6 +46,7 @@ _EXPORTS = {
     "qs_traj_info": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_void_p]),
     "qs_step_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
     "qs_step_host_ex": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
+    "qs_step_host_bytes": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     "qs_ppo_workspace_bytes": (C.c_int64, [C.POINTER(Q.QsPolicyDesc)]),
     "qs_ppo_grad": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 7
                     + [C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32] + [C.c_void_p] * 3),
@@ -276,9 +277,16 @@ class Engine:
 
     def step_host(self, state, action_host: np.ndarray, obs_host: np.ndarray, reward_host: np.ndarray,
                   done_host: np.ndarray, trunc_host: np.ndarray | None = None):
-        """Env.step with page-locked HOST buffers: H2D action, step, D2H obs / reward / done (/ truncated), synchronise
-        (qs_step_host_ex).  Pageable buffers are refused with QS_EINVAL."""
-        self._check(self.lib.qs_step_host_ex(self.handle, _ptr(state), action_host.ctypes.data_as(C.c_void_p),
+        """Env.step with page-locked HOST buffers: H2D action, step, D2H obs / reward / done (/ truncated), synchronise.
+        Flags come back in the dtype of `done_host`: uint8 / bool (qs_step_host_bytes: what Gymnasium and SB3 return, and 3
+        bytes per env-step less on the PCIe link) or float32 (qs_step_host_ex).  Pageable buffers are refused with QS_EINVAL."""
+        u8 = done_host.dtype.itemsize == 1
+        if trunc_host is not None and (trunc_host.dtype.itemsize == 1) != u8:
+            raise QuadSimError("step_host: done_host and trunc_host must have the same dtype")
+        if not u8 and done_host.dtype != np.float32:
+            raise QuadSimError("step_host: flags must be uint8 / bool or float32")
+        fn = self.lib.qs_step_host_bytes if u8 else self.lib.qs_step_host_ex
+        self._check(fn(self.handle, _ptr(state), action_host.ctypes.data_as(C.c_void_p),
                                              obs_host.ctypes.data_as(C.c_void_p), reward_host.ctypes.data_as(C.c_void_p),
                                              done_host.ctypes.data_as(C.c_void_p),
                                              None if trunc_host is None else trunc_host.ctypes.data_as(C.c_void_p),

@@ -188,12 +188,16 @@ class HoverVecEnv:
         n, D = self.num_envs, self.cfg.obs_dim
         if self._host is None:
             pin = lambda *s: torch.empty(s, dtype=torch.float32).pin_memory().numpy()
-            self._host = dict(act=pin(n, 4), obs=pin(n, D), rew=pin(n), done=pin(n), trunc=pin(n))
+            pin8 = lambda *s: torch.empty(s, dtype=torch.uint8).pin_memory().numpy()
+            # flags as bytes (qs_step_host_bytes) when the batch allows it: they ARE the bool arrays Gymnasium returns
+            flag = pin8 if n % 4 == 0 else pin
+            self._host = dict(act=pin(n, 4), obs=pin(n, D), rew=pin(n), done=flag(n), trunc=flag(n))
         h = self._host
         np.copyto(h["act"], np.asarray(actions, dtype=np.float32).reshape(n, 4))
         # terminated AND truncated come from the kernel (an env can be both; a waypoint lap is neither)
         self.engine.step_host(self._planes, h["act"], h["obs"], h["rew"], h["done"], h["trunc"])
-        return h["obs"].copy(), h["rew"].copy(), h["done"] != 0, h["trunc"] != 0, {}
+        as_bool = lambda f: f.view(np.bool_).copy() if f.dtype == np.uint8 else f != 0
+        return h["obs"].copy(), h["rew"].copy(), as_bool(h["done"]), as_bool(h["trunc"]), {}
 
     def close(self):
         self.engine.close()

@@ -169,12 +169,29 @@ struct SmemQ {
     static constexpr int BAR = RED + 8 * 16 * 4;              // ready[2], done[2], full[2], empty[2], tmem slot
     // per slot: cp.async landing zone for the next tile's gathered rows: obs [128][12] | act [128][4] | 3 x [128] scalars
     static constexpr int STG = (BAR + 80 + 15) & ~15;
-    static constexpr int STG_ACT = 128 * 48, STG_SCAL = STG_ACT + 128 * 16, STG_BYTES = STG_SCAL + 128 * 16;   // scalars: [128][4] (packed rows) or 3 x [128]
+    static constexpr int STG_ACT = 128 * 48, STG_SCAL = STG_ACT + 128 * 16, STG_BYTES = STG_SCAL + 128 * 16;   // five-array gather: obs | act | 3 x [128] scalars
+    static constexpr int STG_ROW = 80;     // packed-row gather (bulk copies): [128][80 B] = obs[12] | act[4] | old_logp, adv, ret, 0 per row
     static constexpr int TOTAL = STG + 2 * STG_BYTES;
 };
 // working columns [128 slot, 128 slot + 128) | db2 (column 0 of 16) + dW2^T (128): lane = output feature | dW1^T | dW3
 constexpr uint32_t kQColW = 0 /* + 128 * slot */, kQColW2 = 256, kQColW1 = 400, kQColW3 = 416;
-constexpr int kThreads2 = 320;       // 2 x 128 workers + issuer warp + gather warp
+#ifndef QS_PPO_MASK_BITS
+#define QS_PPO_MASK_BITS 0       /* the relu masks [h > 0] of both hidden layers stay in registers as bit masks (one bit per
+                                    column of the thread's row) from the forward epilogue to the backward one, instead of being
+                                    re-read from the bf16 activations in shared memory: the kernel is bound by shared-memory
+                                    bandwidth (UMMA operand fetch + epilogue traffic), this takes 64 KB per tile off it */
+#endif
+#ifndef QS_PPO_GATHER_BULK
+#define QS_PPO_GATHER_BULK 1     /* packed rows: one cp.async.bulk of 80 bytes per sample instead of five 16-byte cp.async (A/B knob) */
+#endif
+#ifndef QS_PPO_HALVES
+#define QS_PPO_HALVES 2          /* worker warpgroups per slot: each takes 128 / QS_PPO_HALVES of the 128 columns of every epilogue
+                                    (a second warpgroup reads the same TMEM lanes), so the epilogues -- 40 % of a tile's
+                                    latency chain -- take about half as long */
+#endif
+constexpr int kNH = QS_PPO_HALVES;
+constexpr int kIssuerWarp = 8 * kNH, kGatherWarp = 8 * kNH + 1;
+constexpr int kThreads2 = 2 * kNH * 128 + 64;       // 2 slots x kNH x 128 workers + issuer warp + gather warp
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -239,11 +256,13 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     }
     if (gtid < kD) { sF[S::kMean + gtid] = params[L.mean + gtid]; sF[S::kInvStd + gtid] = params[L.inv_std + gtid]; }
     if (gtid == 0) {
-        mbar_init(&bar_ready[0], kM); mbar_init(&bar_ready[1], kM); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
-        mbar_init(&bar_full[0], 32); mbar_init(&bar_full[1], 32); mbar_init(&bar_empty[0], kM); mbar_init(&bar_empty[1], kM);
+        mbar_init(&bar_ready[0], kM * kNH); mbar_init(&bar_ready[1], kM * kNH); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
+        // full[s]: 32 cp.async arrivals (five-array gather) or lane 0's expect_tx arrival + the bulk copies' byte count
+        const int full_count = (b.packed && QS_PPO_GATHER_BULK) ? 1 : 32;
+        mbar_init(&bar_full[0], full_count); mbar_init(&bar_full[1], full_count); mbar_init(&bar_empty[0], kM * kNH); mbar_init(&bar_empty[1], kM * kNH);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp_id == 8) {
+    if (warp_id == kIssuerWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -259,7 +278,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     float g_b3[kA] = {0.f, 0.f, 0.f, 0.f}, g_ls[kA] = {0.f, 0.f, 0.f, 0.f};
     float st_loss = 0.f, st_clip = 0.f, st_kl = 0.f, st_n = 0.f;
 
-    if (warp_id == 9) {
+    if (warp_id == kGatherWarp) {
         // =============================================== gather warp ===================================================
         // tile t of slot s: rows (2 (cta + t ncta) + s) 128 .. + 127 of the minibatch, 4 rows per lane
         uint32_t ph_e[2] = {0u, 0u};
@@ -275,6 +294,27 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 for (int q = 0; q < 4; ++q) {
                     const int r = row0 + q * 32 + lane;
                     j[q] = r < b.n ? (b.idx ? __ldg(b.idx + r) : r) : -1;
+                }
+                if (b.packed && QS_PPO_GATHER_BULK) {
+                    // one bulk copy (TMA, no tensor map) per sample: the first 80 bytes of its 128-byte row -- obs | act |
+                    // old_logp, adv, ret, 0 -- land as ONE staging row, completion through full[s]'s transaction count.
+                    // (A 16-byte cp.async per lane costs one shared-memory wavefront EACH -- ncu: 32 per LDGSTS.128, a quarter
+                    // of the kernel's LSU wavefronts, on a shared-memory pipe that UMMA operand fetch + epilogues keep ~90 %
+                    // busy; loading through registers instead made the gather warp's latency chain the bottleneck.)
+                    const int nvalid = min(max(b.n - row0, 0), kM);
+                    const uint32_t fb = smem_u32(&bar_full[s]);
+                    if (lane == 0)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fb), "r"((uint32_t)(nvalid * S::STG_ROW)) : "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (j[q] < 0) continue;
+                        const int row = q * 32 + lane;
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     :: "r"(smem_u32(stg + row * S::STG_ROW)), "l"(b.packed + (size_t)j[q] * kRowF), "r"((uint32_t)S::STG_ROW), "r"(fb)
+                                     : "memory");
+                    }
+                    continue;
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -309,7 +349,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&bar_full[s])) : "memory");
             }
         }
-    } else if (warp_id == 8) {
+    } else if (warp_id == kIssuerWarp) {
         // =============================================== issuer ========================================================
         // the whole warp walks the schedule (uniform control flow); one elected lane issues
         {
@@ -343,11 +383,11 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                             mma_bf16(tw, dk(a1 + j * 4096, 128), dk(S::W2 + j * 4096, 128), id_kk128, j > 0);
                         mma_bf16(tw, dk(a0, 128), dk(S::B2, 128), id_kk128, 1u);
                         break;
-                    case 2:     // OUT = A2 . W3: TS form, relu(H2) read from working columns [0, 64), OUT -> [64, 80)
+                    case 2:     // OUT = A2 . W3: TS form, relu(H2) read from working columns [0, 32) | [64, 96), OUT -> [32, 48)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
 #if QS_PPO_TS_HEADS
-                            mma_bf16_ts(tw + 64u, tw + 8u * (uint32_t)j, dk(S::W3 + j * 512, 16), id_kk16, j > 0);
+                            mma_bf16_ts(tw + 32u, tw + 64u * (uint32_t)(j >> 2) + 8u * (uint32_t)(j & 3), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
 #else
                             mma_bf16(tw, dk(a2 + j * 4096, 128), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
 #endif
@@ -457,7 +497,13 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         }
     } else {
         // =============================================== workers =======================================================
-        const int slot = wg;
+        // kNH warpgroups per slot; all see the slot's 128 TMEM lanes (warp & 3 selects the lane quarter), each takes its
+        // share of the column chunks of every epilogue.  The first one also owns the per-sample loss, the last one the
+        // next tile's layer-1 operand.
+        const int slot = wg / kNH, half = wg % kNH;
+        const bool do_loss = half == 0, do_a0 = half == kNH - 1;
+        constexpr int kCh = 4 / kNH;                     // 32-column chunks per warpgroup
+        const int c_lo = half * kCh;
         unsigned char* sl = smem + S::SLOT0 + slot * S::SLOT_BYTES;
         const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16) + kQColW + (uint32_t)(slot * 128);
         uint64_t* ready = &bar_ready[slot];
@@ -468,37 +514,69 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         auto signal = [&]() { fence_async_smem(); fence_before(); mbar_arrive(ready); };
         auto wait_done = [&]() { mbar_wait(done, ph); ph ^= 1u; fence_after(); };
         // Epilogues: the TMEM load of column chunk c + 1 is in flight while chunk c is converted and stored.
-        // also_tmem: the packed activations additionally go back into tensor memory, in place over the first half of the
-        // (consumed) working columns -- chunk c's 16 packed columns to [16 c, 16 c + 16) after [32 c, 32 c + 32) was loaded,
-        // the one load in flight covers [32 (c + 1), 32 (c + 2)) -- as the A operand of a TS-form MMA
-        auto epilogue_relu = [&](int dst, bool also_tmem) {
+        // also_tmem: the packed activations additionally go back into tensor memory as the A operand of a TS-form MMA, in
+        // place over consumed working columns: the 16 packed columns of chunk c (columns [32 c, 32 c + 32), loaded before)
+        // go to [64 (c >> 1) + 16 (c & 1), + 16) -- inside the range this warpgroup itself has already loaded, whatever kNH
+        // relu_bits[layer][i]: bit q = column 2 q, bit 16 + q = column 2 q + 1 of this thread's chunk i is positive
+        uint32_t relu_bits[2][kCh];
+        auto epilogue_relu = [&](int dst, bool also_tmem, int layer) {
             uint32_t r[2][32];
-            tmem_ld32_async(tw, r[0]);
+            tmem_ld32_async(tw + (uint32_t)(c_lo * 32), r[0]);
             tmem_ld_wait(r[0]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c + 1 < 4) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
-                const uint32_t* v = r[c & 1];
+            for (int i = 0; i < kCh; ++i) {
+                const int c = c_lo + i;
+                if (i + 1 < kCh) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(i + 1) & 1]);
+                const uint32_t* v = r[i & 1];
                 uint32_t pk[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) pk[q] = pack_relu_bf16_u(v[2 * q], v[2 * q + 1]);
+#if QS_PPO_MASK_BITS
+                {
+                    uint32_t bits = 0u;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        uint32_t m;
+                        asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(pk[q]), "r"(0u));
+                        bits |= (m & 0x00010001u) << q;
+                    }
+                    relu_bits[layer][i] = bits;
+                }
+#endif
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     *reinterpret_cast<uint4*>(sl + dst + op_offset(128, tid, c * 4 + q)) =
                         make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                if (also_tmem) tmem_st16(tw + (uint32_t)(16 * c), pk);
-                if (c + 1 < 4) tmem_ld_wait(r[(c + 1) & 1]);
+                if (also_tmem) tmem_st16(tw + (uint32_t)(64 * (c >> 1) + 16 * (c & 1)), pk);
+                if (i + 1 < kCh) tmem_ld_wait(r[(i + 1) & 1]);
             }
             if (also_tmem) tmem_st_wait();
         };
-        auto epilogue_mask_inplace = [&](int buf) {       // buf <- bf16(working columns * [buf > 0])
+        auto epilogue_mask_inplace = [&](int buf, int layer) {       // buf <- bf16(working columns * [buf > 0])
             uint32_t r[2][32];
-            tmem_ld32_async(tw, r[0]);
+            tmem_ld32_async(tw + (uint32_t)(c_lo * 32), r[0]);
             tmem_ld_wait(r[0]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c + 1 < 4) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
-                const uint32_t* v = r[c & 1];
+            for (int i = 0; i < kCh; ++i) {
+                const int c = c_lo + i;
+                if (i + 1 < kCh) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(i + 1) & 1]);
+                const uint32_t* v = r[i & 1];
+#if QS_PPO_MASK_BITS
+                const uint32_t bits = relu_bits[layer][i];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t* g = v + q * 8;
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t m = ((bits >> (4 * q + e)) & 0x00010001u) * 0xFFFFu;      // 0xffff per positive half
+                        o[e] = pack_bf16(__uint_as_float(g[2 * e]), __uint_as_float(g[2 * e + 1])) & m;
+                    }
+                    *reinterpret_cast<uint4*>(sl + buf + op_offset(128, tid, c * 4 + q)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                if (i + 1 < kCh) tmem_ld_wait(r[(i + 1) & 1]);
+                continue;
+#endif
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t* g = v + q * 8;
@@ -509,54 +587,66 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                                      pack_mask2_bf16(__uint_as_float(g[4]), __uint_as_float(g[5]), h.z),
                                      pack_mask2_bf16(__uint_as_float(g[6]), __uint_as_float(g[7]), h.w));
                 }
-                if (c + 1 < 4) tmem_ld_wait(r[(c + 1) & 1]);
+                if (i + 1 < kCh) tmem_ld_wait(r[(i + 1) & 1]);
             }
         };
-        // this tile's rows arrive through the gather warp's staging area (full / empty mbarriers)
+        // this tile's rows arrive through the gather warp's staging area (full / empty mbarriers); every warpgroup of the
+        // slot takes what its role needs and releases the buffer: the loss warpgroup keeps action + scalars in registers
+        // until the tile's loss, the layer-1 warpgroup turns the observation straight into the A0 operand
         unsigned char* stg = smem + S::STG + slot * S::STG_BYTES;
         uint32_t ph_f = 0u;
-        auto take_rows = [&](int tile, Sample& s) {
+        struct LossIn { float4 a; float old_logp, adv, ret; bool valid; };
+        auto take_rows = [&](int tile, int a0, LossIn& s) {
             mbar_wait(&bar_full[slot], ph_f); ph_f ^= 1u;
-            s.valid = tile * kM + tid < b.n;
-            s.o0 = s.o1 = s.o2 = s.a = make_float4(0.f, 0.f, 0.f, 0.f);
-            s.old_logp = 0.f; s.adv = 0.f; s.ret = 0.f;
-            if (s.valid) {
-                const float4* o = reinterpret_cast<const float4*>(stg + tid * 48);
-                s.o0 = o[0]; s.o1 = o[1]; s.o2 = o[2];
-                if (net == 0) s.a = *reinterpret_cast<const float4*>(stg + S::STG_ACT + tid * 16);
-                if (b.packed) {
-                    const float4 sc4 = *reinterpret_cast<const float4*>(stg + S::STG_SCAL + tid * 16);
-                    s.old_logp = sc4.x; s.adv = sc4.y; s.ret = sc4.z;
-                } else {
-                    const float* sc = reinterpret_cast<const float*>(stg + S::STG_SCAL) + tid;
-                    if (net == 0) { s.old_logp = sc[0]; s.adv = sc[128]; }
-                    else s.ret = sc[256];
+            const bool valid = tile * kM + tid < b.n;
+            if (do_loss) {
+                s.valid = valid;
+                s.a = make_float4(0.f, 0.f, 0.f, 0.f);
+                s.old_logp = 0.f; s.adv = 0.f; s.ret = 0.f;
+                if (valid) {
+                    if (b.packed && QS_PPO_GATHER_BULK) {
+                        if (net == 0) s.a = *reinterpret_cast<const float4*>(stg + tid * S::STG_ROW + 48);
+                        const float4 sc4 = *reinterpret_cast<const float4*>(stg + tid * S::STG_ROW + 64);
+                        s.old_logp = sc4.x; s.adv = sc4.y; s.ret = sc4.z;
+                    } else if (b.packed) {
+                        if (net == 0) s.a = *reinterpret_cast<const float4*>(stg + S::STG_ACT + tid * 16);
+                        const float4 sc4 = *reinterpret_cast<const float4*>(stg + S::STG_SCAL + tid * 16);
+                        s.old_logp = sc4.x; s.adv = sc4.y; s.ret = sc4.z;
+                    } else {
+                        if (net == 0) s.a = *reinterpret_cast<const float4*>(stg + S::STG_ACT + tid * 16);
+                        const float* sc = reinterpret_cast<const float*>(stg + S::STG_SCAL) + tid;
+                        if (net == 0) { s.old_logp = sc[0]; s.adv = sc[128]; }
+                        else s.ret = sc[256];
+                    }
                 }
             }
-            mbar_arrive(&bar_empty[slot]);          // (values are in registers: the loads above have completed? see below)
-        };
-        auto write_a0 = [&](const Sample& sm, int a0) {
-            // bf16 normalised observation, constant 1 in K slots 12 / 13 (0 for the padding rows of a ragged tile)
-            const float o[kD] = {sm.o0.x, sm.o0.y, sm.o0.z, sm.o0.w, sm.o1.x, sm.o1.y, sm.o1.z, sm.o1.w,
-                                 sm.o2.x, sm.o2.y, sm.o2.z, sm.o2.w};
-            const float4* m4 = reinterpret_cast<const float4*>(sF + S::kMean);        // 6 x LDS.128: mean | inv_std
-            const float4 m0 = m4[0], m1 = m4[1], m2 = m4[2], i0 = m4[3], i1 = m4[4], i2 = m4[5];
-            const float mu[kD] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w};
-            const float is[kD] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w};
-            const float one = sm.valid ? 1.0f : 0.f;
-            float x[16];
+            if (do_a0) {
+                // bf16 normalised observation, constant 1 in K slots 12 / 13 (0 for the padding rows of a ragged tile)
+                float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0;
+                if (valid) {
+                    const float4* o = reinterpret_cast<const float4*>(stg + tid * ((b.packed && QS_PPO_GATHER_BULK) ? S::STG_ROW : 48));
+                    o0 = o[0]; o1 = o[1]; o2 = o[2];
+                }
+                const float o[kD] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w};
+                const float4* m4 = reinterpret_cast<const float4*>(sF + S::kMean);        // 6 x LDS.128: mean | inv_std
+                const float4 m0 = m4[0], m1 = m4[1], m2 = m4[2], i0 = m4[3], i1 = m4[4], i2 = m4[5];
+                const float mu[kD] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w};
+                const float is[kD] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w};
+                const float one = valid ? 1.0f : 0.f;
+                float x[16];
 #pragma unroll
-            for (int k = 0; k < kD; ++k) x[k] = (o[k] - mu[k]) * is[k] * one;          // rows of padding samples are zero
-            x[12] = one; x[13] = one; x[14] = 0.f; x[15] = 0.f;
+                for (int k = 0; k < kD; ++k) x[k] = (o[k] - mu[k]) * is[k] * one;          // rows of padding samples are zero
+                x[12] = one; x[13] = one; x[14] = 0.f; x[15] = 0.f;
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-                *reinterpret_cast<uint4*>(sl + a0 + op_offset(128, tid, c)) =
-                    make_uint4(pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
-                               pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
+                for (int c = 0; c < 2; ++c)
+                    *reinterpret_cast<uint4*>(sl + a0 + op_offset(128, tid, c)) =
+                        make_uint4(pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
+                                   pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
+            }
+            mbar_arrive(&bar_empty[slot]);          // the staged values have been consumed (the arrive orders after the loads)
         };
-        Sample cur;
-        take_rows(2 * cta + slot, cur);
-        write_a0(cur, S::A0);
+        LossIn cur;
+        take_rows(2 * cta + slot, S::A0, cur);
         signal();
 #ifdef QS_PPO_PROFILE
         long long prof_[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -566,19 +656,19 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         for (int it = 0; it < iters; ++it) {
             wait_done();                           // H1
             QS_PPOP(0);
-            epilogue_relu(S::A1, false);
+            epilogue_relu(S::A1, false, 0);
             signal();
             QS_PPOP(1);
             wait_done();                           // H2
             QS_PPOP(2);
-            epilogue_relu(S::A2, QS_PPO_TS_HEADS != 0);
+            epilogue_relu(S::A2, QS_PPO_TS_HEADS != 0, 1);
             signal();
             QS_PPOP(3);
             wait_done();                           // OUT
             QS_PPOP(4);
-            {
+            if (do_loss) {
                 float out[16];
-                tmem_ld16(tw + (QS_PPO_TS_HEADS ? 64u : 0u), out);
+                tmem_ld16(tw + (QS_PPO_TS_HEADS ? 32u : 0u), out);
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
                 if (net == 0) {
                     const float a[4] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w};
@@ -622,29 +712,25 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             QS_PPOP(5);
             wait_done();                           // dH2 (and dW3: A2 may be overwritten)
             QS_PPOP(6);
-            epilogue_mask_inplace(S::A2);          // D2
+            epilogue_mask_inplace(S::A2, 1);       // D2
             signal();
             QS_PPOP(7);
             wait_done();                           // dH1 (and dW2, db2: A1 may be overwritten)
             QS_PPOP(8);
-            epilogue_mask_inplace(S::A1);          // D1
+            epilogue_mask_inplace(S::A1, 0);       // D1
             QS_PPOP(9);
-            Sample nxt = cur;
-            if (it + 1 < iters) {
-                take_rows(2 * (cta + (it + 1) * ncta) + slot, nxt);                   // copied a whole tile ago
-                QS_PPOP(10);
-                write_a0(nxt, S::A0 + ((it + 1) & 1) * 4096);                         // next tile's A0, other buffer
-            }
+            if (it + 1 < iters)                    // next tile's rows (copied a whole tile ago) -> loss inputs, A0 in the other buffer
+                take_rows(2 * (cta + (it + 1) * ncta) + slot, S::A0 + ((it + 1) & 1) * 4096, cur);
+            QS_PPOP(10);
             QS_PPOP(11);
             QS_PPOP(12);
             signal();                              // dW1 of this tile + H1 of the next one
             QS_PPOP(13);
-            cur = nxt;
         }
 #ifdef QS_PPO_PROFILE
         if (cta == 0 && tid == 0)
-            printf("ppoprof net %d slot %d iters %d: waitH1 %lld | E1 %lld | waitH2 %lld | E2 %lld | waitOUT %lld | loss %lld | wait3 %lld | E4 %lld | wait4 %lld | E5 %lld | gather_wait %lld | write_a0 %lld | gather_async %lld | signal %lld (cycles/tile)\n",
-                   net, slot, iters, prof_[0] / iters, prof_[1] / iters, prof_[2] / iters, prof_[3] / iters, prof_[4] / iters,
+            printf("ppoprof net %d slot %d half %d iters %d: waitH1 %lld | E1 %lld | waitH2 %lld | E2 %lld | waitOUT %lld | loss %lld | wait3 %lld | E4 %lld | wait4 %lld | E5 %lld | gather_wait %lld | write_a0 %lld | gather_async %lld | signal %lld (cycles/tile)\n",
+                   net, slot, half, iters, prof_[0] / iters, prof_[1] / iters, prof_[2] / iters, prof_[3] / iters, prof_[4] / iters,
                    prof_[5] / iters, prof_[6] / iters, prof_[7] / iters, prof_[8] / iters, prof_[9] / iters, prof_[10] / iters,
                    prof_[11] / iters, prof_[12] / iters, prof_[13] / iters);
 #endif
@@ -696,9 +782,9 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
         }
-        if (wg < 2 && lane == 0) {
+        if (wg < 2 * kNH && (wg % kNH) == 0 && lane == 0) {      // the loss warpgroup of each slot: 2 x 4 warps
 #pragma unroll
-            for (int k = 0; k < 12; ++k) sRed[(gtid >> 5) * 16 + k] = r[k];
+            for (int k = 0; k < 12; ++k) sRed[((wg / kNH) * 4 + warp) * 16 + k] = r[k];
         }
         __syncthreads();
         if (gtid < 12) {
@@ -719,7 +805,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     }
     fence_before();
     __syncthreads();
-    if (warp_id == 8) {
+    if (warp_id == kIssuerWarp) {
         fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
     }

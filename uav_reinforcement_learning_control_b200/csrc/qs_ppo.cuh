@@ -112,30 +112,11 @@ __device__ __forceinline__ uint32_t pack_mask2_bf16(float lo, float hi, uint32_t
     return p & m;
 }
 
-#ifndef QS_PPO_TS_HEADS
-#define QS_PPO_TS_HEADS 1        /* relu(H2) is ALSO stored into tensor memory (in place over the first 64 of the slot's consumed
-                                    working columns) and OUT = A2 . W3 runs as TS-form MMAs (A from TMEM): 32 KB less shared-
-                                    memory operand traffic per tile; OUT lands in working columns [64, 80) */
-#endif
-#ifndef QS_PPO_STAGGER
-#define QS_PPO_STAGGER 3         /* dynamic issue: slot 1 starts once slot 0 has been issued this phase of its first tile */
-#endif
-#ifndef QS_PPO_DYNAMIC_ISSUE
-#define QS_PPO_DYNAMIC_ISSUE 0   /* 1: the issuer serves whichever slot is ready first (-10 % issuer idle time in the phase
-                                    profile, no gain in the measured minibatch time, and the accumulation order -- hence the
-                                    low bits of the gradient -- then depends on timing); 0: fixed order, bitwise reproducible */
-#endif
 #ifdef QS_PPO_PROFILE
 #define QS_PPOP(k) do { const long long c_ = clock64(); prof_[k] += c_ - pc_; pc_ = c_; } while (0)
 #else
 #define QS_PPOP(k) do { } while (0)
 #endif
-
-struct Sample {
-    float4 o0, o1, o2, a;
-    float old_logp, adv, ret;
-    bool valid;
-};
 
 }  // namespace ppo
 }  // namespace qs
@@ -147,17 +128,32 @@ namespace ppo {
 // ppo_grad_tc2_kernel -- the production schedule.  Same GEMMs, operands and rounding points as ppo_grad_tc_kernel, but
 //   * one network per CTA (the first n_actor CTAs: actor, the rest: critic; every CTA walks over ALL tiles with its network's stride), which
 //     halves the TMEM accumulator columns (176) and the weight operands (44 KB) a CTA has to hold, so that
-//   * TWO 128-sample tiles are in flight per CTA (two worker warpgroups, each with its own operand buffers and 128
-//     working TMEM columns) and share the gradient accumulators, and
-//   * a dedicated issuer thread (warp 8) owns the tensor pipe: workers hand a phase over with fence + mbarrier.arrive
-//     on ready[slot] and wait on done[slot]; the issuer serves the two slots alternately, so one tile's MMAs run under
+//   * TWO 128-sample tiles are in flight per CTA (two slots, each with its own operand buffers and 128 working TMEM
+//     columns, served by kNH worker warpgroups that split the columns of every epilogue) and share the gradient
+//     accumulators, and
+//   * a dedicated issuer warp owns the tensor pipe: workers hand a phase over with fence + mbarrier.arrive on
+//     ready[slot] and wait on done[slot]; the issuer serves the two slots alternately, so one tile's MMAs run under
 //     the other tile's epilogue (ping-pong), and no worker warp ever spends issue slots on tcgen05.mma.
-//   * a gather warp (warp 9) fetches the next tile's minibatch rows (random rows of the rollout buffers) into a small
+//   * a gather warp fetches the next tile's minibatch rows (random rows of the rollout buffers) into a small
 //     shared staging area with cp.async, one tile ahead, and hands them over through full / empty mbarriers: the workers
 //     never have a global load outstanding (ptxas parked the epilogues behind such loads: shared scoreboards) nor a
 //     cp.async of their own (their fence.proxy.async would wait for it);
 //   * D2 / D1 are written IN PLACE over relu(H2) / relu(H1) (their only other readers, the dW3 / dW2 MMAs, are
-//     committed before the workers are released), so a slot needs 72 KB of operands.
+//     committed before the workers are released), so a slot needs 80 KB of operands.
+// What bounds it (ncu, round 2): the shared-memory data pipe.  UMMA operand fetch (SS form: A and B both from shared
+// memory, 8 KB per M128 N128 K16 instruction = 128 B per clock at the tensor pipe's full rate) takes 45 % of the pipe's
+// peak, the workers' epilogue loads / stores another 45 %.  Hence, per tile and network:
+//   * db2 | dW2^T = D2^T . [1 | A1] is ONE N = 144 instruction per K step (a constant ONES block sits directly below A1,
+//     so [ONES | A1] is one MN-major operand): 8 instead of 16 instructions and 28 KB less operand traffic than the
+//     separate dW2 = A1^T . D2 and db2 = D2^T . A0 of the single-tile kernel; the accumulator is the TRANSPOSE of dW2
+//     (lane = output feature), which the flush writes out with warp-coalesced stores;
+//   * the head layer OUT = A2 . W3 runs in TS form: relu(H2) is ALSO stored into tensor memory (in place over consumed
+//     working columns), so its eight N = 16 instructions read 0.5 KB instead of 4.5 KB each.
+// 51 tcgen05.mma per tile and network (43 SS + 8 TS) instead of 59.  Measured and NOT kept (commit ee1aa8d has the code,
+// profiles/README.md the numbers): relu masks as register bit masks instead of re-reading the activations (-64 KB of
+// loads, but +7 % time: the epilogues' ALU work is on the tile's latency chain), the gather through registers or as
+// 80-byte bulk copies (cp.async costs a wavefront per 16 bytes, but both alternatives were slower), and a staggered
+// dynamic service order (the slots then contend for the pipe instead of taking turns).
 struct SmemQ {
     static constexpr int W1 = 0, W2 = 4096, W3 = W2 + 32768, B2 = W3 + 4096, WEND = B2 + 4096;
     // per slot; ONES (128 rows x 16: a constant 1 in K slot 0) sits directly below A1: [ONES | A1] is ONE MN-major operand
@@ -170,24 +166,15 @@ struct SmemQ {
     // per slot: cp.async landing zone for the next tile's gathered rows: obs [128][12] | act [128][4] | 3 x [128] scalars
     static constexpr int STG = (BAR + 80 + 15) & ~15;
     static constexpr int STG_ACT = 128 * 48, STG_SCAL = STG_ACT + 128 * 16, STG_BYTES = STG_SCAL + 128 * 16;   // five-array gather: obs | act | 3 x [128] scalars
-    static constexpr int STG_ROW = 80;     // packed-row gather (bulk copies): [128][80 B] = obs[12] | act[4] | old_logp, adv, ret, 0 per row
     static constexpr int TOTAL = STG + 2 * STG_BYTES;
 };
 // working columns [128 slot, 128 slot + 128) | db2 (column 0 of 16) + dW2^T (128): lane = output feature | dW1^T | dW3
 constexpr uint32_t kQColW = 0 /* + 128 * slot */, kQColW2 = 256, kQColW1 = 400, kQColW3 = 416;
-#ifndef QS_PPO_MASK_BITS
-#define QS_PPO_MASK_BITS 0       /* the relu masks [h > 0] of both hidden layers stay in registers as bit masks (one bit per
-                                    column of the thread's row) from the forward epilogue to the backward one, instead of being
-                                    re-read from the bf16 activations in shared memory: the kernel is bound by shared-memory
-                                    bandwidth (UMMA operand fetch + epilogue traffic), this takes 64 KB per tile off it */
-#endif
-#ifndef QS_PPO_GATHER_BULK
-#define QS_PPO_GATHER_BULK 1     /* packed rows: one cp.async.bulk of 80 bytes per sample instead of five 16-byte cp.async (A/B knob) */
-#endif
 #ifndef QS_PPO_HALVES
 #define QS_PPO_HALVES 2          /* worker warpgroups per slot: each takes 128 / QS_PPO_HALVES of the 128 columns of every epilogue
-                                    (a second warpgroup reads the same TMEM lanes), so the epilogues -- 40 % of a tile's
-                                    latency chain -- take about half as long */
+                                    (a second warpgroup reads the same TMEM lanes).  Measured 0.3485 vs 0.3511 ms per 2^20-sample
+                                    minibatch for 2 vs 1: the epilogues do NOT get twice as fast, they wait for the shared-memory
+                                    data pipe, which UMMA operand fetch and epilogue traffic share (profiles/README.md) */
 #endif
 constexpr int kNH = QS_PPO_HALVES;
 constexpr int kIssuerWarp = 8 * kNH, kGatherWarp = 8 * kNH + 1;
@@ -257,9 +244,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
     if (gtid < kD) { sF[S::kMean + gtid] = params[L.mean + gtid]; sF[S::kInvStd + gtid] = params[L.inv_std + gtid]; }
     if (gtid == 0) {
         mbar_init(&bar_ready[0], kM * kNH); mbar_init(&bar_ready[1], kM * kNH); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
-        // full[s]: 32 cp.async arrivals (five-array gather) or lane 0's expect_tx arrival + the bulk copies' byte count
-        const int full_count = (b.packed && QS_PPO_GATHER_BULK) ? 1 : 32;
-        mbar_init(&bar_full[0], full_count); mbar_init(&bar_full[1], full_count); mbar_init(&bar_empty[0], kM * kNH); mbar_init(&bar_empty[1], kM * kNH);
+        mbar_init(&bar_full[0], 32); mbar_init(&bar_full[1], 32); mbar_init(&bar_empty[0], kM * kNH); mbar_init(&bar_empty[1], kM * kNH);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp_id == kIssuerWarp) {
@@ -294,27 +279,6 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 for (int q = 0; q < 4; ++q) {
                     const int r = row0 + q * 32 + lane;
                     j[q] = r < b.n ? (b.idx ? __ldg(b.idx + r) : r) : -1;
-                }
-                if (b.packed && QS_PPO_GATHER_BULK) {
-                    // one bulk copy (TMA, no tensor map) per sample: the first 80 bytes of its 128-byte row -- obs | act |
-                    // old_logp, adv, ret, 0 -- land as ONE staging row, completion through full[s]'s transaction count.
-                    // (A 16-byte cp.async per lane costs one shared-memory wavefront EACH -- ncu: 32 per LDGSTS.128, a quarter
-                    // of the kernel's LSU wavefronts, on a shared-memory pipe that UMMA operand fetch + epilogues keep ~90 %
-                    // busy; loading through registers instead made the gather warp's latency chain the bottleneck.)
-                    const int nvalid = min(max(b.n - row0, 0), kM);
-                    const uint32_t fb = smem_u32(&bar_full[s]);
-                    if (lane == 0)
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fb), "r"((uint32_t)(nvalid * S::STG_ROW)) : "memory");
-                    __syncwarp();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (j[q] < 0) continue;
-                        const int row = q * 32 + lane;
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     :: "r"(smem_u32(stg + row * S::STG_ROW)), "l"(b.packed + (size_t)j[q] * kRowF), "r"((uint32_t)S::STG_ROW), "r"(fb)
-                                     : "memory");
-                    }
-                    continue;
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -386,11 +350,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                     case 2:     // OUT = A2 . W3: TS form, relu(H2) read from working columns [0, 32) | [64, 96), OUT -> [32, 48)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-#if QS_PPO_TS_HEADS
                             mma_bf16_ts(tw + 32u, tw + 64u * (uint32_t)(j >> 2) + 8u * (uint32_t)(j & 3), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
-#else
-                            mma_bf16(tw, dk(a2 + j * 4096, 128), dk(S::W3 + j * 512, 16), id_kk16, j > 0);
-#endif
                         }
                         break;
                     case 3:     // dH2 = dOUT . W3^T ; dW3 += A2^T . dOUT (must finish before D2 overwrites A2)
@@ -425,47 +385,6 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             long long pc_ = clock64();
 #endif
-#if QS_PPO_DYNAMIC_ISSUE
-            // Order-constrained dynamic service (tuning knob, measured SLOWER than the fixed order: profiles/README.md).
-            // Slot 1 starts its first tile once slot 0 has been issued phase QS_PPO_STAGGER; after that each slot is served
-            // as soon as it is ready, except that the phases which accumulate into the shared gradient columns (3: dW3,
-            // 4: dW2 | db2, 5: dW1) are taken strictly alternately, slot 0 first, so the summation order of every
-            // accumulator -- hence the gradient, bit for bit -- does not depend on timing.
-            int pnext[2] = {0, 0}, itn[2] = {0, 0};            // phase 0 = H1 of the slot's first tile
-            int turn[3] = {0, 0, 0};                           // whose accumulation comes next, per accumulating phase
-            int left = 2 * (iters * 5 + 1);
-#pragma unroll 1
-            while (left > 0) {
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    if (itn[s] >= iters) continue;
-                    const int phase = pnext[s], it = itn[s];
-                    if (phase >= 3 && turn[phase - 3] != s) continue;
-                    if (s == 1 && phase == 0 && itn[0] == 0 && pnext[0] <= QS_PPO_STAGGER && iters > 1) continue;
-                    uint32_t ok = 0u;
-                    if (lane == 0) {
-                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                                     : "=r"(ok) : "r"(smem_u32(&bar_ready[s])), "r"(ph[s]) : "memory");
-                    }
-                    ok = __shfl_sync(0xffffffffu, ok, 0);
-                    if (!ok) continue;
-                    ph[s] ^= 1u;
-                    fence_after();
-                    QS_PPOP(0);
-                    issue_phase(s, phase, it);
-                    if (phase >= 3) turn[phase - 3] ^= 1;
-                    if (++pnext[s] == 6) { pnext[s] = 1; ++itn[s]; }
-                    --left;
-                    QS_PPOP(1);
-                }
-                QS_PPOP(2);
-            }
-#ifdef QS_PPO_PROFILE
-            if (cta == 0 && lane == 0)
-                printf("ppoprof net %d issuer (cycles per iteration of 2 tiles): issuing %lld | polling %lld\n",
-                       net, prof_[1] / iters, (prof_[0] + prof_[2]) / iters);
-#endif
-#else
             // fixed service order slot 0, slot 1, slot 0, ...: the accumulation order into the gradient accumulators is
             // then the same in every run, i.e. the gradient is bitwise reproducible
 #pragma unroll
@@ -493,7 +412,6 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 printf("ppoprof net %d issuer (cycles per iteration of 2 tiles): issuing %lld | waiting for ready %lld\n",
                        net, prof_[1] / iters, prof_[0] / iters);
 #endif
-#endif
         }
     } else {
         // =============================================== workers =======================================================
@@ -517,9 +435,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         // also_tmem: the packed activations additionally go back into tensor memory as the A operand of a TS-form MMA, in
         // place over consumed working columns: the 16 packed columns of chunk c (columns [32 c, 32 c + 32), loaded before)
         // go to [64 (c >> 1) + 16 (c & 1), + 16) -- inside the range this warpgroup itself has already loaded, whatever kNH
-        // relu_bits[layer][i]: bit q = column 2 q, bit 16 + q = column 2 q + 1 of this thread's chunk i is positive
-        uint32_t relu_bits[2][kCh];
-        auto epilogue_relu = [&](int dst, bool also_tmem, int layer) {
+        auto epilogue_relu = [&](int dst, bool also_tmem) {
             uint32_t r[2][32];
             tmem_ld32_async(tw + (uint32_t)(c_lo * 32), r[0]);
             tmem_ld_wait(r[0]);
@@ -531,18 +447,6 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 uint32_t pk[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) pk[q] = pack_relu_bf16_u(v[2 * q], v[2 * q + 1]);
-#if QS_PPO_MASK_BITS
-                {
-                    uint32_t bits = 0u;
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        uint32_t m;
-                        asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(pk[q]), "r"(0u));
-                        bits |= (m & 0x00010001u) << q;
-                    }
-                    relu_bits[layer][i] = bits;
-                }
-#endif
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     *reinterpret_cast<uint4*>(sl + dst + op_offset(128, tid, c * 4 + q)) =
@@ -552,7 +456,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             }
             if (also_tmem) tmem_st_wait();
         };
-        auto epilogue_mask_inplace = [&](int buf, int layer) {       // buf <- bf16(working columns * [buf > 0])
+        auto epilogue_mask_inplace = [&](int buf) {       // buf <- bf16(working columns * [buf > 0])
             uint32_t r[2][32];
             tmem_ld32_async(tw + (uint32_t)(c_lo * 32), r[0]);
             tmem_ld_wait(r[0]);
@@ -561,22 +465,6 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 const int c = c_lo + i;
                 if (i + 1 < kCh) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(i + 1) & 1]);
                 const uint32_t* v = r[i & 1];
-#if QS_PPO_MASK_BITS
-                const uint32_t bits = relu_bits[layer][i];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t* g = v + q * 8;
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t m = ((bits >> (4 * q + e)) & 0x00010001u) * 0xFFFFu;      // 0xffff per positive half
-                        o[e] = pack_bf16(__uint_as_float(g[2 * e]), __uint_as_float(g[2 * e + 1])) & m;
-                    }
-                    *reinterpret_cast<uint4*>(sl + buf + op_offset(128, tid, c * 4 + q)) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-                if (i + 1 < kCh) tmem_ld_wait(r[(i + 1) & 1]);
-                continue;
-#endif
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t* g = v + q * 8;
@@ -604,11 +492,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 s.a = make_float4(0.f, 0.f, 0.f, 0.f);
                 s.old_logp = 0.f; s.adv = 0.f; s.ret = 0.f;
                 if (valid) {
-                    if (b.packed && QS_PPO_GATHER_BULK) {
-                        if (net == 0) s.a = *reinterpret_cast<const float4*>(stg + tid * S::STG_ROW + 48);
-                        const float4 sc4 = *reinterpret_cast<const float4*>(stg + tid * S::STG_ROW + 64);
-                        s.old_logp = sc4.x; s.adv = sc4.y; s.ret = sc4.z;
-                    } else if (b.packed) {
+                    if (b.packed) {
                         if (net == 0) s.a = *reinterpret_cast<const float4*>(stg + S::STG_ACT + tid * 16);
                         const float4 sc4 = *reinterpret_cast<const float4*>(stg + S::STG_SCAL + tid * 16);
                         s.old_logp = sc4.x; s.adv = sc4.y; s.ret = sc4.z;
@@ -624,7 +508,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 // bf16 normalised observation, constant 1 in K slots 12 / 13 (0 for the padding rows of a ragged tile)
                 float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0;
                 if (valid) {
-                    const float4* o = reinterpret_cast<const float4*>(stg + tid * ((b.packed && QS_PPO_GATHER_BULK) ? S::STG_ROW : 48));
+                    const float4* o = reinterpret_cast<const float4*>(stg + tid * 48);
                     o0 = o[0]; o1 = o[1]; o2 = o[2];
                 }
                 const float o[kD] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w};
@@ -656,19 +540,19 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         for (int it = 0; it < iters; ++it) {
             wait_done();                           // H1
             QS_PPOP(0);
-            epilogue_relu(S::A1, false, 0);
+            epilogue_relu(S::A1, false);
             signal();
             QS_PPOP(1);
             wait_done();                           // H2
             QS_PPOP(2);
-            epilogue_relu(S::A2, QS_PPO_TS_HEADS != 0, 1);
+            epilogue_relu(S::A2, true);
             signal();
             QS_PPOP(3);
             wait_done();                           // OUT
             QS_PPOP(4);
             if (do_loss) {
                 float out[16];
-                tmem_ld16(tw + (QS_PPO_TS_HEADS ? 32u : 0u), out);
+                tmem_ld16(tw + 32u, out);
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
                 if (net == 0) {
                     const float a[4] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w};
@@ -712,12 +596,12 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             QS_PPOP(5);
             wait_done();                           // dH2 (and dW3: A2 may be overwritten)
             QS_PPOP(6);
-            epilogue_mask_inplace(S::A2, 1);       // D2
+            epilogue_mask_inplace(S::A2);          // D2
             signal();
             QS_PPOP(7);
             wait_done();                           // dH1 (and dW2, db2: A1 may be overwritten)
             QS_PPOP(8);
-            epilogue_mask_inplace(S::A1, 0);       // D1
+            epilogue_mask_inplace(S::A1);          // D1
             QS_PPOP(9);
             if (it + 1 < iters)                    // next tile's rows (copied a whole tile ago) -> loss inputs, A0 in the other buffer
                 take_rows(2 * (cta + (it + 1) * ncta) + slot, S::A0 + ((it + 1) & 1) * 4096, cur);

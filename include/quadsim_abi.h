@@ -342,6 +342,21 @@ int qs_ppo_comm_close_peers(QsPpoComm* comm);   /* unmap the peers' buffers; cal
 int qs_ppo_comm_destroy(QsPpoComm* comm);
 
 /*
+ * qs_ppo_update_epoch: ONE epoch of minibatch updates -- what SB3's PPO.train() (train.py:50-68) / brax's sgd_step scan
+ * (train_brax_ppo.py:589-620) run per pass over the rollout -- launched back to back from native code: for minibatch
+ * k = 0 .. num_minibatches-1 over rows perm[k mb .. (k+1) mb) (mb = n_total / num_minibatches; the last one also takes the
+ * remainder) of the packed sample rows: advantage statistics, qs_ppo_grad_packed, then qs_ppo_adam with step step0 + k
+ * (comm == NULL; `grad` is the P + 8 float scratch) or, with a peer communicator, the gradient goes to slot epoch0 + k and
+ * qs_ppo_adam_peer sums the ranks.  stats_acc (optional, device, 8 floats) += every minibatch's statistics.  desc's
+ * sample_seed is replaced by (sample_seed0 + k) & 0x7fffffff per minibatch.  Bitwise identical to issuing the calls one by one.
+ */
+int qs_ppo_update_epoch(const QsPolicyDesc* desc, float* policy_params, const float* packed, const float* adv,
+                        const int32_t* perm, int32_t n_total, int32_t num_minibatches, float clip_range, float vf_coef,
+                        float ent_coef, int32_t normalize_adv, float* m, float* v, int32_t step0, float lr, float beta1,
+                        float beta2, float eps, float max_grad_norm, QsPpoComm* comm, uint32_t epoch0, void* workspace,
+                        float* grad, float* stats_acc, float* norm_out, uint64_t sample_seed0, void* stream);
+
+/*
  * qs_traj_info: TrajectoryFollowEnv's info["target" | "target_vel" | "target_acc"] (envs/trajectory_follow_env.py:
  * 162-168 in step, :245-250 in reset), out9 [B][9] float32 = pos(3) | vel(3) | acc(3) of each env's natural-cubic-
  * spline reference (:176-218).  Nothing is stored per env: the spline of an episode is re-derived from the Philox

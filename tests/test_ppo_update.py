@@ -544,6 +544,38 @@ def test_trainer_runs_fused_on_mjx_brax():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["hover_gym", "mjx_brax"])
+def test_native_epoch_loop_is_bitwise_the_per_minibatch_loop(mode):
+    """qs_ppo_update_epoch (one native call per epoch: statistics accumulated inside the optimiser kernel, minibatch
+    slicing, seeds and optimiser steps counted in C) against the same update issued minibatch by minibatch from Python:
+    parameters, Adam moments and the reported statistics must agree bit for bit, for both learners, incl. a minibatch
+    count that does not divide the rollout (the last minibatch takes the remainder rows)."""
+    import torch
+    from uav_reinforcement_learning_control_b200 import config as Q
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    from uav_reinforcement_learning_control_b200.ppo import PPOConfig, PPOTrainer
+    out = []
+    for native in (True, False):
+        if mode == "hover_gym":
+            eng = Engine(Q.EnvConfig.north_star(seed=2), 1000, device=0)
+            cfg = PPOConfig(n_steps=16, n_epochs=3, num_minibatches=7, learning_rate=1e-3)
+        else:
+            eng = Engine(Q.EnvConfig.mjx_brax(episode_length=500, auto_reset=Q.RESET_RESTORE_FIRST, seed=3), 1024, device=0)
+            cfg = PPOConfig.brax_reference()
+        tr = PPOTrainer(eng, cfg, seed=1, native_epochs=native)
+        assert tr.fused and tr.native_epochs == native
+        log = tr.train(2)
+        torch.cuda.synchronize()
+        out.append((tr.params.clone(), tr.updater.m.clone(), tr.updater.v.clone(), tr.updater.step, log))
+    (pa, ma, va, sa, la), (pb, mb_, vb, sb, lb) = out
+    assert sa == sb and sa == 2 * cfg.n_epochs * cfg.num_minibatches
+    assert torch.equal(pa, pb) and torch.equal(ma, mb_) and torch.equal(va, vb)
+    for x, y in zip(la, lb):
+        for k in ("pg_loss", "v_loss", "clip_frac", "approx_kl"):
+            assert x[k] == y[k], (k, x[k], y[k])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("obs_dim,dist,n,N", [(12, 0, 4096, 20000), (12, 0, 1000, 1000), (21, 1, 2048, 9000)])
 def test_packed_rows_give_the_same_gradient_bitwise(obs_dim, dist, n, N):
     """qs_ppo_pack + qs_ppo_grad_packed (one 128-byte line per sample) against qs_ppo_grad on the five separate arrays, same

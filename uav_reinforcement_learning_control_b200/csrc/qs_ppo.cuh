@@ -797,7 +797,10 @@ constexpr int kAdamPerThread = 40;        // 1024 threads x 40 >= the trained pa
 // parameters.  A single CTA doing both passes with dependent trips to L2 took 43 us.
 __global__ void __launch_bounds__(1024)
 ppo_adam_kernel(AdamArgs a, float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m,
-                float* __restrict__ v, float* __restrict__ norm_out) {
+                float* __restrict__ v, float* __restrict__ norm_out, const float* __restrict__ stats,
+                float* __restrict__ stats_acc) {
+    // (optional) running sums of the minibatch statistics: stats_acc[0..8) += stats[0..8)
+    if (stats_acc && blockIdx.x == 0 && threadIdx.x < kPartialStats) stats_acc[threadIdx.x] += stats[threadIdx.x];
     __shared__ double sh[32];
     __shared__ float coef_s;
     float g[kAdamPerThread];

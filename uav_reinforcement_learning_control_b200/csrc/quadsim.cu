@@ -616,11 +616,9 @@ int qs_ppo_permutation(int32_t n, uint64_t seed, uint32_t epoch, int32_t* out, v
     return check_launch("ppo_permutation_kernel");
 }
 
-int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* grad, float* m, float* v, int32_t step,
-                float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, float* norm_out,
-                void* stream) {
-    if (!desc || desc->hidden != 128 || desc->act_dim != 4) return fail(QS_EINVAL, "qs_ppo_adam: bad policy description");
-    if (!policy_params || !grad || !m || !v || step <= 0) return fail(QS_EINVAL, "qs_ppo_adam: bad argument");
+static int launch_adam(const QsPolicyDesc* desc, float* policy_params, const float* grad, float* m, float* v, int32_t step,
+                       float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, float* norm_out,
+                       float* stats_acc, void* stream) {
     const qs::PolicyLayout L = qs::policy_layout(desc->obs_dim, desc->dist);
     qs::ppo::AdamArgs a;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_grad_norm = max_grad_norm; a.grad_scale = grad_scale;
@@ -628,8 +626,17 @@ int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* gra
     a.bias2 = (float)(1.0 - pow((double)beta2, (double)step));
     a.n_train = L.mean;
     if (a.n_train > qs::ppo::kAdamPerThread * 1024) return fail(QS_EUNSUPPORTED, "qs_ppo_adam: policy too large for the single-CTA optimiser step");
-    qs::ppo::ppo_adam_kernel<<<nblocks(a.n_train, 1024), 1024, 0, (cudaStream_t)stream>>>(a, policy_params, grad, m, v, norm_out);
+    qs::ppo::ppo_adam_kernel<<<nblocks(a.n_train, 1024), 1024, 0, (cudaStream_t)stream>>>(
+        a, policy_params, grad, m, v, norm_out, grad + qs::policy_param_count(*desc), stats_acc);
     return check_launch("ppo_adam_kernel");
+}
+
+int qs_ppo_adam(const QsPolicyDesc* desc, float* policy_params, const float* grad, float* m, float* v, int32_t step,
+                float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, float* norm_out,
+                void* stream) {
+    if (!desc || desc->hidden != 128 || desc->act_dim != 4) return fail(QS_EINVAL, "qs_ppo_adam: bad policy description");
+    if (!policy_params || !grad || !m || !v || step <= 0) return fail(QS_EINVAL, "qs_ppo_adam: bad argument");
+    return launch_adam(desc, policy_params, grad, m, v, step, lr, beta1, beta2, eps, max_grad_norm, grad_scale, norm_out, nullptr, stream);
 }
 
 // ---- multi-GPU PPO update over NVLink peer memory (qs_ppo.cuh: ppo_peer_adam_kernel) ------------------------------------
@@ -717,6 +724,39 @@ int qs_ppo_adam_peer(const QsPolicyDesc* desc, QsPpoComm* c, uint32_t epoch, flo
     qs::ppo::ppo_peer_adam_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(a, c->L, c->peers, c->world, c->rank, epoch, c->P,
                                                                            policy_params, m, v, norm_out, stats_acc, timeout_ns);
     return check_launch("ppo_peer_adam_kernel");
+}
+
+// One epoch of minibatch updates launched back to back from native code: for the small minibatches of the reference's own
+// geometry (train_brax_ppo.py:589-620: 10 240 samples) the four launches of an update cost less GPU time than their
+// Python / ctypes round trips, and the statistics accumulate inside the optimiser kernel instead of a separate torch add.
+int qs_ppo_update_epoch(const QsPolicyDesc* desc, float* policy_params, const float* packed, const float* adv,
+                        const int32_t* perm, int32_t n_total, int32_t num_minibatches, float clip_range, float vf_coef,
+                        float ent_coef, int32_t normalize_adv, float* m, float* v, int32_t step0, float lr, float beta1,
+                        float beta2, float eps, float max_grad_norm, QsPpoComm* comm, uint32_t epoch0, void* workspace,
+                        float* grad, float* stats_acc, float* norm_out, uint64_t sample_seed0, void* stream) {
+    if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, kPpoDescMsg);
+    if (!policy_params || !packed || !perm || !m || !v || !workspace || n_total <= 0 || num_minibatches <= 0 ||
+        num_minibatches > n_total || step0 <= 0 || (normalize_adv && !adv) || (!comm && !grad) || (comm && epoch0 == 0))
+        return fail(QS_EINVAL, "qs_ppo_update_epoch: bad argument");
+    if (((uintptr_t)packed & 127u) != 0 || (((uintptr_t)workspace | (uintptr_t)grad) & 15u) != 0)
+        return fail(QS_EINVAL, "qs_ppo_update_epoch: packed rows must be 128-byte, workspace and grad 16-byte aligned");
+    const int32_t mb = n_total / num_minibatches;
+    QsPolicyDesc d = *desc;
+    for (int32_t k = 0; k < num_minibatches; ++k) {
+        // (the last minibatch takes the n_total % num_minibatches remainder rows, as SB3's RolloutBuffer.get does)
+        const int32_t n = k + 1 < num_minibatches ? mb : n_total - k * mb;
+        d.sample_seed = (int32_t)((sample_seed0 + (uint64_t)k) & 0x7FFFFFFFull);
+        float* out = comm ? (float*)qs_ppo_comm_slot(comm, epoch0 + (uint32_t)k) : grad;
+        qs::ppo::Batch b{nullptr, nullptr, nullptr, adv, nullptr, perm + (size_t)k * mb, n, packed};
+        int rc = ppo_grad_impl(&d, policy_params, b, clip_range, vf_coef, ent_coef, normalize_adv, workspace, out, stream);
+        if (rc != QS_OK) return rc;
+        rc = comm ? qs_ppo_adam_peer(&d, comm, epoch0 + (uint32_t)k, policy_params, m, v, step0 + k, lr, beta1, beta2, eps,
+                                     max_grad_norm, norm_out, stats_acc, stream)
+                  : launch_adam(&d, policy_params, grad, m, v, step0 + k, lr, beta1, beta2, eps, max_grad_norm, 1.0f, norm_out,
+                                stats_acc, stream);
+        if (rc != QS_OK) return rc;
+    }
+    return QS_OK;
 }
 
 int qs_ppo_comm_error(QsPpoComm* c) {

@@ -68,6 +68,9 @@ _EXPORTS = {
                                       C.c_void_p, C.c_void_p]),
     "qs_ppo_adam": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_float] * 6
                     + [C.c_void_p] * 2),
+    "qs_ppo_update_epoch": (C.c_int, [C.POINTER(Q.QsPolicyDesc)] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32]
+                            + [C.c_float] * 3 + [C.c_int32] + [C.c_void_p] * 2 + [C.c_int32] + [C.c_float] * 5
+                            + [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p]),
 }
 
 

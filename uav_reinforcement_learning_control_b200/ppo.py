@@ -352,6 +352,37 @@ class FusedUpdater:
                             "qs_ppo_grad")
         return self.grad_buf if self.comm is None else None
 
+    def update_epoch(self, params, packed, adv, perm, num_minibatches, lr, clip_range=0.2, vf_coef=0.5, ent_coef=0.0,
+                     normalize_adv=True, max_grad_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-5, stats_acc=None, sample_seed0=0):
+        """One epoch of minibatch updates over ``perm`` (int32 permutation of the N packed rows), launched back to back from
+        native code (qs_ppo_update_epoch): per minibatch {advantage statistics, gradient, optimiser step} -- through the
+        peer-memory exchange when ``enable_peer`` succeeded -- with the loss statistics accumulated into ``stats_acc``
+        (8 floats) inside the optimiser kernel.  Bitwise identical to calling ``grad`` + ``adam`` / ``adam_peer`` per
+        minibatch; it exists because the reference's own geometry (train_brax_ppo.py: 10 240-sample minibatches) spends
+        more time in the Python / ctypes round trips of those calls than on the GPU."""
+        torch = self.torch
+        N = packed.shape[0]
+        for name, t, shp, dt in (("params", params, (self.P,), torch.float32), ("packed", packed, (N, self.ROW_FLOATS), torch.float32),
+                                 ("perm", perm, (N,), torch.int32)) + \
+                                ((("adv", adv, (N,), torch.float32),) if normalize_adv else ()) + \
+                                ((("stats_acc", stats_acc, (self.N_STATS,), torch.float32),) if stats_acc is not None else ()):
+            if t is None or t.dtype != dt or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shp:
+                raise ValueError(f"{name}: expected contiguous {dt} CUDA tensor {shp}, got "
+                                 f"{None if t is None else (t.dtype, tuple(t.shape))}")
+        p = lambda t: None if t is None else self.C.c_void_p(t.data_ptr())
+        k = int(num_minibatches)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.qs_ppo_update_epoch(
+                self.C.byref(self.desc), p(params), p(packed), p(adv), p(perm), int(N), k, float(clip_range), float(vf_coef),
+                float(ent_coef), int(normalize_adv), p(self.m), p(self.v), int(self.step + 1), float(lr), float(beta1), float(beta2),
+                float(eps), float(max_grad_norm), self.comm, int(self.epoch + 1) if self.comm is not None else 0, p(self.workspace),
+                p(self.grad_buf), p(stats_acc), p(self.norm), int(sample_seed0) & 0xFFFFFFFFFFFFFFFF, self._stream()),
+                "qs_ppo_update_epoch")
+        self.step += k
+        if self.comm is not None:
+            self.epoch += k
+        return self.norm
+
     def adam_peer(self, params, lr, max_grad_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-5, stats_acc=None):
         """Peer mode: wait for every rank's slot of this update, sum them over NVLink, clip, Adam -- one kernel."""
         self.step += 1
@@ -394,10 +425,12 @@ class PPOTrainer:
     vector ``self.params``; fused=False: torch autograd on ``self.policy``."""
 
     def __init__(self, engine, cfg: PPOConfig | None = None, ctx: DistContext | None = None, seed: int = 0,
-                 fused: bool | None = None, tensor_cores: bool | None = None, peer: bool = False, packed_rows: bool = True):
+                 fused: bool | None = None, tensor_cores: bool | None = None, peer: bool = False, packed_rows: bool = True,
+                 native_epochs: bool = True):
         import torch
         self.torch = torch
         self.packed_rows = bool(packed_rows)
+        self.native_epochs = bool(native_epochs)       # False: one grad + adam call per minibatch from Python (A/B, tests)
         self.engine = engine
         self.cfg = cfg or PPOConfig()
         self.ctx = ctx or DistContext()
@@ -462,16 +495,26 @@ class PPOTrainer:
         world = self.ctx.world
         # one 128-byte row per sample, written once per rollout: every minibatch gather then reads full cache lines
         self._packed = packed = up.pack(obs, act, old_logp, adv, ret, out=getattr(self, "_packed", None)) if self.packed_rows else None
+        norm_mode = (2 if self.brax else 1) if c.normalize_advantage else 0
+        # single GPU, or gradients exchanged through peer memory: the whole epoch is one native call; only the NCCL
+        # fallback needs the host between the gradient and the optimiser step
+        native = self.native_epochs and packed is not None and (world == 1 or up.comm is not None)
         for _ in range(c.n_epochs):
             self._perm = perm = up.permutation(N, self.shuffle_seed, self._epochs_done, out=getattr(self, "_perm", None))
             self._epochs_done += 1
+            if native:
+                up.update_epoch(self.params, packed, adv, perm, c.num_minibatches, c.learning_rate, clip_range=c.clip_range,
+                                vf_coef=c.vf_coef, ent_coef=c.ent_coef, normalize_adv=norm_mode, max_grad_norm=c.max_grad_norm,
+                                eps=c.adam_eps, stats_acc=acc, sample_seed0=self.shuffle_seed * 2654435761 + self._updates + 1)
+                self._updates += c.num_minibatches
+                continue
             for k in range(c.num_minibatches):
                 self._updates += 1
                 # (the last minibatch takes the N % num_minibatches remainder rows, as SB3's RolloutBuffer.get does)
                 g = up.grad(self.params, obs, act, old_logp, adv, ret, packed=packed,
                             idx=perm[k * mb:((k + 1) * mb if k + 1 < c.num_minibatches else N)],
                             clip_range=c.clip_range, vf_coef=c.vf_coef, ent_coef=c.ent_coef,
-                            normalize_adv=(2 if self.brax else 1) if c.normalize_advantage else 0,
+                            normalize_adv=norm_mode,
                             sample_seed=(self.shuffle_seed * 2654435761 + self._updates) & 0x7FFFFFFF)
                 if up.comm is not None:
                     # gradients meet in NVLink peer memory inside the optimiser kernel: no collective call at all

@@ -169,7 +169,13 @@ struct SmemQ {
     static constexpr int TOTAL = STG + 2 * STG_BYTES;
 };
 // working columns [128 slot, 128 slot + 128) | db2 (column 0 of 16) + dW2^T (128): lane = output feature | dW1^T | dW3
-constexpr uint32_t kQColW = 0 /* + 128 * slot */, kQColW2 = 256, kQColW1 = 400, kQColW3 = 416;
+constexpr uint32_t kQColW = 0 /* + 128 * slot */, kQColW2 = 256, kQColW1 = 400, kQColW3 = 416, kQColX = 432 /* + 32 * slot */;
+#ifndef QS_PPO_TS_HALF
+#define QS_PPO_TS_HALF 1         /* the first four K steps (features 0..63) of layer 2 (A = relu(H1)) and of dH1 = D2 . W2^T (A = D2)
+                                    read their A operand from the 2 x 32 spare TMEM columns (TS form) instead of shared memory:
+                                    32 KB less operand fetch per tile and network.  (All eight would need 2 x 64 columns:
+                                    2 x (128 + 64) + 176 > 512.) */
+#endif
 #ifndef QS_PPO_HALVES
 #define QS_PPO_HALVES 2          /* worker warpgroups per slot: each takes 128 / QS_PPO_HALVES of the 128 columns of every epilogue
                                     (a second warpgroup reads the same TMEM lanes).  Measured 0.3485 vs 0.3511 ms per 2^20-sample
@@ -345,7 +351,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 const int base = S::SLOT0 + s * S::SLOT_BYTES;
                 const int a0 = base + S::A0 + (it & 1) * 4096, a1 = base + S::A1, a2 = base + S::A2, dout = base + S::DOUT;
                 const int ones = base + S::ONES;
-                const uint32_t tw = tmem + kQColW + (uint32_t)(s * 128);
+                const uint32_t tw = tmem + kQColW + (uint32_t)(s * 128), tx = tmem + kQColX + (uint32_t)(s * 32);
                 const uint32_t first = (it == 0 && s == 0) ? 0u : 1u;
                 if (elect_one()) {
                     switch (phase) {
@@ -354,8 +360,10 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                         break;
                     case 1:     // H2 = A1 . W2 + b2
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            mma_bf16(tw, dk(a1 + j * 4096, 128), dk(S::W2 + j * 4096, 128), id_kk128, j > 0);
+                        for (int j = 0; j < 8; ++j) {
+                            if (QS_PPO_TS_HALF && j < 4) mma_bf16_ts(tw, tx + 8u * (uint32_t)j, dk(S::W2 + j * 4096, 128), id_kk128, j > 0);
+                            else mma_bf16(tw, dk(a1 + j * 4096, 128), dk(S::W2 + j * 4096, 128), id_kk128, j > 0);
+                        }
                         mma_bf16(tw, dk(a0, 128), dk(S::B2, 128), id_kk128, 1u);
                         break;
                     case 2:     // OUT = A2 . W3: TS form, relu(H2) read from working columns [0, 32) | [64, 96), OUT -> [32, 48)
@@ -373,8 +381,10 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                     case 4:     // dH1 = D2 . W2^T ; db2 | dW2^T += D2^T . [1 | A1]   (D2 lives in the A2 buffer; the constant
                                 // ONES block sits right below A1, so one N = 144 instruction per K step reads both)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            mma_bf16(tw, dk(a2 + j * 4096, 128), dmn(S::W2 + j * 256, 2048u), id_kmn128, j > 0);
+                        for (int j = 0; j < 8; ++j) {
+                            if (QS_PPO_TS_HALF && j < 4) mma_bf16_ts(tw, tx + 8u * (uint32_t)j, dmn(S::W2 + j * 256, 2048u), id_kmn128, j > 0);
+                            else mma_bf16(tw, dk(a2 + j * 4096, 128), dmn(S::W2 + j * 256, 2048u), id_kmn128, j > 0);
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             mma_bf16(tmem + kQColW2, dmn(a2 + j * 256, 2048u), dmn(ones + j * 256, 2048u), id_mm144, j > 0 ? 1u : first);
@@ -446,6 +456,7 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
         // also_tmem: the packed activations additionally go back into tensor memory as the A operand of a TS-form MMA, in
         // place over consumed working columns: the 16 packed columns of chunk c (columns [32 c, 32 c + 32), loaded before)
         // go to [64 (c >> 1) + 16 (c & 1), + 16) -- inside the range this warpgroup itself has already loaded, whatever kNH
+        const uint32_t tx = tmem + ((uint32_t)(warp * 32) << 16) + kQColX + (uint32_t)(slot * 32);    // TS-form copy of features 0..63
         auto epilogue_relu = [&](int dst, bool also_tmem) {
             uint32_t r[2][32];
             tmem_ld32_async(tw + (uint32_t)(c_lo * 32), r[0]);
@@ -463,11 +474,13 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                     *reinterpret_cast<uint4*>(sl + dst + op_offset(128, tid, c * 4 + q)) =
                         make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 if (also_tmem) tmem_st16(tw + (uint32_t)(64 * (c >> 1) + 16 * (c & 1)), pk);
+                else if (QS_PPO_TS_HALF && c < 2) tmem_st16(tx + (uint32_t)(16 * c), pk);        // layer 1: A1's first four K steps
                 if (i + 1 < kCh) tmem_ld_wait(r[(i + 1) & 1]);
             }
-            if (also_tmem) tmem_st_wait();
+            if (also_tmem || (QS_PPO_TS_HALF && c_lo < 2)) tmem_st_wait();
         };
-        auto epilogue_mask_inplace = [&](int buf) {       // buf <- bf16(working columns * [buf > 0])
+        // also_tx: the first four K steps of the result additionally go to the spare TMEM columns (dH1's TS-form A operand)
+        auto epilogue_mask_inplace = [&](int buf, bool also_tx) {       // buf <- bf16(working columns * [buf > 0])
             uint32_t r[2][32];
             tmem_ld32_async(tw + (uint32_t)(c_lo * 32), r[0]);
             tmem_ld_wait(r[0]);
@@ -477,17 +490,22 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
                 if (i + 1 < kCh) tmem_ld32_async(tw + (uint32_t)((c + 1) * 32), r[(i + 1) & 1]);
                 const uint32_t* v = r[i & 1];
 #pragma unroll
+                uint32_t pk[16];
+#pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t* g = v + q * 8;
                     uint4* p4 = reinterpret_cast<uint4*>(sl + buf + op_offset(128, tid, c * 4 + q));
                     const uint4 h = *p4;
-                    *p4 = make_uint4(pack_mask2_bf16(__uint_as_float(g[0]), __uint_as_float(g[1]), h.x),
-                                     pack_mask2_bf16(__uint_as_float(g[2]), __uint_as_float(g[3]), h.y),
-                                     pack_mask2_bf16(__uint_as_float(g[4]), __uint_as_float(g[5]), h.z),
-                                     pack_mask2_bf16(__uint_as_float(g[6]), __uint_as_float(g[7]), h.w));
+                    pk[4 * q] = pack_mask2_bf16(__uint_as_float(g[0]), __uint_as_float(g[1]), h.x);
+                    pk[4 * q + 1] = pack_mask2_bf16(__uint_as_float(g[2]), __uint_as_float(g[3]), h.y);
+                    pk[4 * q + 2] = pack_mask2_bf16(__uint_as_float(g[4]), __uint_as_float(g[5]), h.z);
+                    pk[4 * q + 3] = pack_mask2_bf16(__uint_as_float(g[6]), __uint_as_float(g[7]), h.w);
+                    *p4 = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
+                if (QS_PPO_TS_HALF && also_tx && c < 2) tmem_st16(tx + (uint32_t)(16 * c), pk);
                 if (i + 1 < kCh) tmem_ld_wait(r[(i + 1) & 1]);
             }
+            if (QS_PPO_TS_HALF && also_tx && c_lo < 2) tmem_st_wait();
         };
         // this tile's rows arrive through the gather warp's staging area (full / empty mbarriers); every warpgroup of the
         // slot takes what its role needs and releases the buffer: the loss warpgroup keeps action + scalars in registers
@@ -607,12 +625,12 @@ ppo_grad_tc2_kernel(Batch b, Hyper hp, const float* __restrict__ params, const f
             QS_PPOP(5);
             wait_done();                           // dH2 (and dW3: A2 may be overwritten)
             QS_PPOP(6);
-            epilogue_mask_inplace(S::A2);          // D2
+            epilogue_mask_inplace(S::A2, true);    // D2 (+ its first four K steps in TMEM for dH1)
             signal();
             QS_PPOP(7);
             wait_done();                           // dH1 (and dW2, db2: A1 may be overwritten)
             QS_PPOP(8);
-            epilogue_mask_inplace(S::A1);          // D1
+            epilogue_mask_inplace(S::A1, false);   // D1
             QS_PPOP(9);
             if (it + 1 < iters)                    // next tile's rows (copied a whole tile ago) -> loss inputs, A0 in the other buffer
                 take_rows(2 * (cta + (it + 1) * ncta) + slot, S::A0 + ((it + 1) & 1) * 4096, cur);

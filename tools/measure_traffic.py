@@ -92,7 +92,7 @@ def main():
                             "how": "same capture with --cache-control none: each launch also takes the previous launch's write-backs"},
            "source_fingerprint": bench.source_fingerprint(),
            "how": "tools/measure_traffic.py (cold launch, ncu flushes caches before each): ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on "
-                  f"{COUNT} step_kernel launches of bench.py's loop (2^20 envs, {bench.STATE_SETS} rotating state sets), shipped libquadsim.so"}
+                  f"{COUNT} step2_kernel launches of bench.py's loop (2^20 envs, {bench.STATE_SETS} rotating state sets), shipped libquadsim.so"}
     with open(os.path.join(OUT, "step_kernel_traffic.json"), "w") as f:
         json.dump(rec, f, indent=1)
     print(json.dumps(rec))

@@ -34,7 +34,18 @@ for rep in range(3):
         for k in range(8): fused(k)
     ev[1].record(); torch.cuda.synchronize()
     res.append(ev[0].elapsed_time(ev[1]) / 32)
-print(json.dumps({"ms_per_minibatch": res, "finite": bool(torch.isfinite(params).all())}))
+# the trainer's form: one native call per epoch of 8 minibatches (qs_ppo_update_epoch)
+acc = torch.zeros(up.N_STATS, device=dev)
+res2 = []
+if hasattr(up, "update_epoch"):
+    for rep in range(3):
+        up.update_epoch(params, packed, adv, perm, 8, 1.5e-4, clip_range=0.19, vf_coef=0.5, ent_coef=1e-4, stats_acc=acc)
+        torch.cuda.synchronize(); ev[0].record()
+        for r in range(4):
+            up.update_epoch(params, packed, adv, perm, 8, 1.5e-4, clip_range=0.19, vf_coef=0.5, ent_coef=1e-4, stats_acc=acc)
+        ev[1].record(); torch.cuda.synchronize()
+        res2.append(ev[0].elapsed_time(ev[1]) / 32)
+print(json.dumps({"ms_per_minibatch": res, "epoch_call_ms_per_minibatch": res2, "finite": bool(torch.isfinite(params).all())}))
 ''' % ROOT
 
 tests = ["tests/test_ppo_update.py", "-q", "-x", "-m", "gpu", "-k",

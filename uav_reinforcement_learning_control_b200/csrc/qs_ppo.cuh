@@ -776,12 +776,20 @@ ppo_reduce_kernel(const float* __restrict__ partial, int rows_a, int rows_c, int
 
 // mean and 1 / (std + 1e-8) of the minibatch's advantages (ddof 1: unbiased std, as torch.Tensor.std; ddof 0: population).  Double-precision block
 // sums, one atomicAdd pair per block; the last block to finish writes the result and re-arms the scratch.
-// scratch: 2 doubles (sums) + 1 unsigned (blocks done), zero before the first call
+// scratch: 2 doubles (sums) + 1 unsigned (blocks done), zero before the first call.
+// gridDim.y > 1: ALL minibatches of an epoch in one launch -- minibatch k = blockIdx.y covers idx[k mb_stride .. + n) (the last
+// one up to n_total), with its own 32-byte scratch record scratch + 4 k and its own result adv_norm + 2 k.
 __global__ void __launch_bounds__(256)
 ppo_adv_stats_kernel(const float* __restrict__ adv, const int32_t* __restrict__ idx, int n, int ddof,
-                     double* __restrict__ scratch, float* __restrict__ adv_norm) {
+                     double* __restrict__ scratch, float* __restrict__ adv_norm, int mb_stride, int n_total) {
     __shared__ double sh[2][8];
     __shared__ bool last;
+    if (gridDim.y > 1) {
+        const int k = blockIdx.y;
+        if (idx) idx += (size_t)k * mb_stride; else adv += (size_t)k * mb_stride;
+        if (k + 1 == (int)gridDim.y) n = n_total - k * mb_stride;
+        scratch += 4 * k; adv_norm += 2 * k;
+    }
     double s = 0.0, q = 0.0;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const double a = (double)adv[idx ? idx[i] : i];

@@ -450,6 +450,10 @@ int qs_gae(int32_t T, int32_t B, const float* reward, const float* value, const 
 // ---- PPO update on device: implemented in qs_ppo.cuh ------------------------------------------------
 namespace {
 constexpr size_t kPpoWsHeader = 128;   // bytes: 2 doubles + 1 counter (advantage sums) | 2 floats (mean, 1/std) at byte 32
+// tail of the workspace (behind the partial-gradient rows): per-minibatch records for the one-launch-per-epoch advantage
+// statistics of qs_ppo_update_epoch: kPpoMaxEpochMb x {2 doubles + counter (32 B)} | kPpoMaxEpochMb x {mean, 1/std}
+constexpr int kPpoMaxEpochMb = 1024;
+constexpr size_t kPpoWsTail = (size_t)kPpoMaxEpochMb * (32 + 8);
 
 int ppo_device_sms(int* sms) {
     int dev = 0, major = 0;
@@ -483,11 +487,12 @@ int64_t qs_ppo_workspace_bytes(const QsPolicyDesc* desc) {
     const int rc = ppo_device_sms(&sms);
     if (rc != QS_OK) return rc;
     const size_t row = (size_t)qs::ppo::partial_stride(qs::policy_param_count(*desc));
-    return (int64_t)(kPpoWsHeader + (size_t)sms * row * sizeof(float));
+    return (int64_t)(kPpoWsHeader + (size_t)sms * row * sizeof(float) + kPpoWsTail);
 }
 
 static int ppo_grad_impl(const QsPolicyDesc* desc, const float* policy_params, const qs::ppo::Batch& b, float clip_range,
-                         float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad, void* stream);
+                         float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad, void* stream,
+                         const float* adv_norm_ready = nullptr);
 
 int qs_ppo_grad(const QsPolicyDesc* desc, const float* policy_params, const float* obs, const float* act,
                 const float* old_logp, const float* adv, const float* ret, const int32_t* idx, int32_t n,
@@ -526,7 +531,8 @@ int qs_ppo_grad_packed(const QsPolicyDesc* desc, const float* policy_params, con
 }
 
 static int ppo_grad_impl(const QsPolicyDesc* desc, const float* policy_params, const qs::ppo::Batch& b, float clip_range,
-                         float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad, void* stream) {
+                         float vf_coef, float ent_coef, int32_t normalize_adv, void* workspace, float* grad, void* stream,
+                         const float* adv_norm_ready) {
     const float* adv = b.adv;
     const int32_t* idx = b.idx;
     const int32_t n = b.n;
@@ -537,11 +543,11 @@ static int ppo_grad_impl(const QsPolicyDesc* desc, const float* policy_params, c
     cudaStream_t s = (cudaStream_t)stream;
     unsigned char* ws = (unsigned char*)workspace;
     double* adv_scratch = (double*)ws;
-    float* adv_norm = (float*)(ws + 32);
+    const float* adv_norm = adv_norm_ready ? adv_norm_ready : (const float*)(ws + 32);
     float* partial = (float*)(ws + kPpoWsHeader);
-    if (normalize_adv) {
+    if (normalize_adv && !adv_norm_ready) {
         const int blocks = nblocks(n, 256) < 4 * sms ? nblocks(n, 256) : 4 * sms;
-        qs::ppo::ppo_adv_stats_kernel<<<blocks, 256, 0, s>>>(adv, idx, n, normalize_adv == 2 ? 0 : 1, adv_scratch, adv_norm);
+        qs::ppo::ppo_adv_stats_kernel<<<blocks, 256, 0, s>>>(adv, idx, n, normalize_adv == 2 ? 0 : 1, adv_scratch, (float*)(ws + 32), 0, n);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     const int ntiles = nblocks(n, qs::tc::kM);
@@ -742,13 +748,31 @@ int qs_ppo_update_epoch(const QsPolicyDesc* desc, float* policy_params, const fl
         return fail(QS_EINVAL, "qs_ppo_update_epoch: packed rows must be 128-byte, workspace and grad 16-byte aligned");
     const int32_t mb = n_total / num_minibatches;
     QsPolicyDesc d = *desc;
+    // the advantage statistics of ALL minibatches of the epoch in one launch (they depend on the shuffle only, not on the
+    // parameters): one record per minibatch in the tail of the workspace
+    const float* norm_all = nullptr;
+    if (normalize_adv && num_minibatches <= kPpoMaxEpochMb) {
+        int sms = 0;
+        const int rc0 = ppo_device_sms(&sms);
+        if (rc0 != QS_OK) return rc0;
+        const size_t row = (size_t)qs::ppo::partial_stride(qs::policy_param_count(*desc));
+        unsigned char* tail = (unsigned char*)workspace + kPpoWsHeader + (size_t)sms * row * sizeof(float);
+        float* norms = (float*)(tail + (size_t)kPpoMaxEpochMb * 32);
+        const int blocks = nblocks(mb, 256) < 4 * sms ? nblocks(mb, 256) : 4 * sms;
+        qs::ppo::ppo_adv_stats_kernel<<<dim3((unsigned)blocks, (unsigned)num_minibatches), 256, 0, (cudaStream_t)stream>>>(
+            adv, perm, mb, normalize_adv == 2 ? 0 : 1, (double*)tail, norms, mb, n_total);
+        const int rc1 = check_launch("ppo_adv_stats_kernel (epoch)");
+        if (rc1 != QS_OK) return rc1;
+        norm_all = norms;
+    }
     for (int32_t k = 0; k < num_minibatches; ++k) {
         // (the last minibatch takes the n_total % num_minibatches remainder rows, as SB3's RolloutBuffer.get does)
         const int32_t n = k + 1 < num_minibatches ? mb : n_total - k * mb;
         d.sample_seed = (int32_t)((sample_seed0 + (uint64_t)k) & 0x7FFFFFFFull);
         float* out = comm ? (float*)qs_ppo_comm_slot(comm, epoch0 + (uint32_t)k) : grad;
         qs::ppo::Batch b{nullptr, nullptr, nullptr, adv, nullptr, perm + (size_t)k * mb, n, packed};
-        int rc = ppo_grad_impl(&d, policy_params, b, clip_range, vf_coef, ent_coef, normalize_adv, workspace, out, stream);
+        int rc = ppo_grad_impl(&d, policy_params, b, clip_range, vf_coef, ent_coef, normalize_adv, workspace, out, stream,
+                               norm_all ? norm_all + 2 * k : nullptr);
         if (rc != QS_OK) return rc;
         rc = comm ? qs_ppo_adam_peer(&d, comm, epoch0 + (uint32_t)k, policy_params, m, v, step0 + k, lr, beta1, beta2, eps,
                                      max_grad_norm, norm_out, stats_acc, stream)

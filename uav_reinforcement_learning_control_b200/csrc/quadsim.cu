@@ -512,9 +512,12 @@ int qs_ppo_pack(const QsPolicyDesc* desc, const float* obs, const float* act, co
     if (!ppo_desc_ok(desc)) return fail(QS_EUNSUPPORTED, kPpoDescMsg);
     if (!obs || !act || !old_logp || !adv || !ret || !packed || n <= 0) return fail(QS_EINVAL, "qs_ppo_pack: bad argument");
     if (((uintptr_t)packed & 127u) != 0) return fail(QS_EINVAL, "qs_ppo_pack: packed rows must be 128-byte aligned");
-    const long long threads = (long long)n * qs::ppo::kRowF;
-    qs::ppo::ppo_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        desc->obs_dim, obs, act, old_logp, adv, ret, (long long)n, packed);
+    if ((((uintptr_t)obs | (uintptr_t)act) & 15u) != 0) return fail(QS_EINVAL, "qs_ppo_pack: obs and act must be 16-byte aligned");
+    const unsigned blocks = (unsigned)((n + qs::ppo::kPackRows - 1) / qs::ppo::kPackRows);
+    if (desc->obs_dim == 12)
+        qs::ppo::ppo_pack_kernel<12><<<blocks, qs::ppo::kPackRows, 0, (cudaStream_t)stream>>>(obs, act, old_logp, adv, ret, (long long)n, packed);
+    else
+        qs::ppo::ppo_pack_kernel<21><<<blocks, qs::ppo::kPackRows, 0, (cudaStream_t)stream>>>(obs, act, old_logp, adv, ret, (long long)n, packed);
     return check_launch("ppo_pack_kernel");
 }
 

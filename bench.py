@@ -511,7 +511,8 @@ def main():
             "gradient_exchange": "none (1 GPU)" if world == 1 else ("NVLink peer memory inside the optimiser kernel (qs_ppo_adam_peer)"
                                                                     if tr.updater.comm is not None else "NCCL all-reduce"),
             "note": "qs_rollout_policy (tcgen05) + qs_gae + 32 x {qs_ppo_grad (tcgen05 forward + backward, weight gradients "
-                    "in TMEM) + qs_ppo_adam}; includes the per-epoch qs_ppo_permutation shuffle and the statistics read-back"}
+                    "in TMEM) + qs_ppo_adam}, issued as one qs_ppo_update_epoch call per epoch; includes qs_ppo_pack, the per-epoch "
+                    "qs_ppo_permutation shuffles (computed on a side stream next to the rollout) and the statistics read-back"}
         tr.updater.close()
         del tr
         del eng_p

@@ -621,7 +621,8 @@ int qs_ppo_permutation(int32_t n, uint64_t seed, uint32_t epoch, int32_t* out, v
     qs::ppo::PermKeys K;
     K.k0 = k0;
     for (uint32_t r = 0; r < 4; ++r) K.rk[r] = qs::ppo::perm_mix(k1 + r);
-    qs::ppo::ppo_permutation_kernel<<<nblocks(n, 256), 256, 0, (cudaStream_t)stream>>>((uint32_t)n, half_bits, K, out);
+    // one warp per chunk of kPermChunk elements, 8 warps per block
+    qs::ppo::ppo_permutation_kernel<<<nblocks(nblocks(n, qs::ppo::kPermChunk), 8), 256, 0, (cudaStream_t)stream>>>((uint32_t)n, half_bits, K, out);
     return check_launch("ppo_permutation_kernel");
 }
 

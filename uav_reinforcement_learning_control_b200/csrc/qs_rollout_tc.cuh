@@ -36,6 +36,10 @@
 #define QS_TC_TS_HEADS 1     /* 1: relu(H2) stays in TENSOR MEMORY (tcgen05.st, in place over the consumed layer-2 accumulators) and the
                                 head layer runs as TS-form MMAs (A from TMEM); 0: through shared memory (SS form) */
 #endif
+#ifndef QS_TC_SPLIT_CRITIC
+#define QS_TC_SPLIT_CRITIC 1 /* 1 (partner-warpgroup CTAs): the critic's layer-2 / head MMAs and epilogues run BEHIND the actor's, off the
+                                owners' per-step latency chain (own mbarrier, issued / consumed by the partner warpgroup) */
+#endif
 #ifndef QS_TC_TS_L2
 #define QS_TC_TS_L2 1        /* 1 (one-tile CTAs only: needs 384 of the 512 TMEM columns per tile): relu(H1) also stays in tensor
                                 memory and layer 2 runs as TS-form MMAs */
@@ -239,12 +243,13 @@ struct SmemT {
     static constexpr int CAND = EPS + (PARTNER ? 2 * 128 * 16 : 0);     // PARTNER: speculative reset candidates [128][28] float + episode mailbox [128] u32
     static constexpr int kCandF = 28;                                   // p3 q4 v3 w3 target3 obs12
     static constexpr int EPI = CAND + (PARTNER ? 128 * kCandF * 4 : 0);
-    static constexpr int TILE_BYTES = EPI + (PARTNER ? 128 * 4 : 0);
+    static constexpr int VAL = EPI + (PARTNER ? 128 * 4 : 0);           // PARTNER: V(s) of the last forward, written by the partners
+    static constexpr int TILE_BYTES = VAL + (PARTNER ? 128 * 4 : 0);
     static constexpr int TILE0 = WEND;
     __host__ __device__ static constexpr int f32_off(int tiles) { return TILE0 + tiles * TILE_BYTES; }   // fp32 constants, see below
     static constexpr int kB3 = 0 /*[32]*/, kLogStd = 32, kMean = 36, kInvStd = 60, kNumF = 84;
-    __host__ __device__ static constexpr int bar_off(int tiles) { return f32_off(tiles) + kNumF * 4; }   // mbarriers (8 B per tile) + tmem base (4 B)
-    __host__ __device__ static constexpr int total(int tiles) { return bar_off(tiles) + 8 * tiles + 16; }
+    __host__ __device__ static constexpr int bar_off(int tiles) { return f32_off(tiles) + kNumF * 4; }   // mbarriers (8 B per tile) + tmem base (4 B) + PARTNER: the critic's mbarrier
+    __host__ __device__ static constexpr int total(int tiles) { return bar_off(tiles) + 8 * tiles + 24; }
 };
 
 // PARTNER (one tile per CTA, 12-D modes): a second warpgroup shares the tile.  Warp w + 4 reads the same 32 TMEM lanes
@@ -286,6 +291,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     const int lwarp = __shfl_sync(0xffffffffu, ltid >> 5, 0);   // warp index within the tile, visibly warp-uniform: warp 0 issues the MMAs
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES)) + tile;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::bar_off(TILES) + 8 * TILES);
+    uint64_t* barC = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES) + 8 * TILES + 8);      // PARTNER: the critic's commits
     unsigned char* tsm = smem + Smem::TILE0 + tile * Smem::TILE_BYTES;   // this tile's A operands
     const int b0 = (blockIdx.x * TILES + tile) * ept;
 
@@ -336,7 +342,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     if (gtid == 0) sF[Smem::kB3 + 16] = params[L.cb3];
     if (DIST == 0 && gtid < kA) sF[Smem::kLogStd + gtid] = params[L.log_std + gtid];
     if (gtid < D) { sF[Smem::kMean + gtid] = params[L.mean + gtid]; sF[Smem::kInvStd + gtid] = params[L.inv_std + gtid]; }
-    if (ltid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (ltid == 0) { mbar_init(bar, 1); if (PARTNER) mbar_init(barC, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (gtid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -443,8 +449,136 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     using DstSmem = std::integral_constant<int, 0>;
     using DstL3 = std::integral_constant<int, kTsHeads ? 1 : 0>;
     using DstL2 = std::integral_constant<int, kTsL2 ? 2 : 0>;
-    // forward pass for the observation in `o`; returns head[Ao] and value
-    auto forward = [&](const float* o, float* head, float& value) {
+    // PARTNER + TS forms: the critic leaves the owners' per-step latency chain.  The env step needs the actor's head only;
+    // V(s) goes to the trajectory (and to the rare timeout bootstrap).  So the layer-2 and head MMAs of the critic are
+    // committed to their own mbarrier (barC): the owners wait for the actor's 9 layer-2 MMAs only, pack relu(H2) while the
+    // critic's 9 run, issue the actor's head and go on to sample and step, while the partners -- who own the critic halves
+    // of the epilogues anyway -- finish the critic behind them, issue its head themselves and leave V(s) in shared memory.
+    // The owner / partner warpgroups synchronise among themselves (named barriers 2 / 3, 128 threads); both meet again at
+    // the tile barrier that opens the next forward, before its layer-1 MMA overwrites the accumulator columns.
+    constexpr bool kSplitCritic = PARTNER && QS_TC_SPLIT_CRITIC != 0 && QS_TC_TS_HEADS != 0 && QS_TC_TS_L2 != 0;
+    uint32_t phaseC = 0;
+    float* sVal = reinterpret_cast<float*>(tsm + Smem::VAL);
+    auto group_sync = [&](int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(128) : "memory"); };
+    // forward pass for the observation in `o`; returns head[Ao] and -- if need_value (split critic: otherwise the partners
+    // keep it in sVal and store it themselves) -- value
+    auto forward = [&](const float* o, float* head, float& value, bool need_value) {
+      if constexpr (kSplitCritic) {
+        if (half == 0) {
+            float x[K1];
+#pragma unroll
+            for (int k = 0; k < K1; ++k) x[k] = k < D ? (o[k] - sF[Smem::kMean + k]) * sF[Smem::kInvStd + k] : (k < D + 2 ? 1.0f : 0.f);
+#pragma unroll
+            for (int c = 0; c < K1 / 8; ++c)
+                *reinterpret_cast<uint4*>(tsm + Smem::A1 + op_offset(128, tid, c)) =
+                    make_uint4(pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
+                               pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
+        }
+        fence_async_smem();
+        fence_before();
+        tile_sync<kTT>(tile);                       // both warpgroups: the previous forward's TMEM reads are done too
+        if (lwarp == 0) {
+            fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < kS1; ++j)
+                    mma_bf16(tmem, make_desc(tbase + Smem::A1 + j * 4096, 16 * 128, 128),
+                             make_desc(sbase + Smem::W1 + j * 8192, 32 * 128, 128), idesc_l1, j > 0);
+                mma_commit(bar);
+                mma_commit(barC);
+            }
+            __syncwarp();
+        }
+        QS_TCP(0);
+        if (half == 0) { mbar_wait(bar, phase); phase ^= 1; } else { mbar_wait(barC, phaseC); phaseC ^= 1; }
+        fence_after();
+        QS_TCP(1);
+        relu_epilogue(DstL2{});                     // owners: actor half -> [256, 320); partners: critic half -> [320, 384)
+        QS_TCP(2);
+        fence_before();
+        tile_sync<kTT>(tile);
+        if (lwarp == 0) {
+            fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    mma_bf16_ts(tmem, tmem + 256u + 8u * (uint32_t)j, make_desc(sbase + Smem::W2A + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+                mma_bf16(tmem, dA1b, make_desc(sbase + Smem::B2A, 16 * 128, 128), idesc_l2, 1u);
+                mma_commit(bar);                    // the actor's layer 2 is all the owners wait for
+            }
+            __syncwarp();
+            asm volatile("bar.arrive 4, 64;" ::: "memory");          // the actor's MMAs are in the pipe: the critic's may follow
+        } else if (lwarp == 4) {
+            // the critic's layer 2 is issued by a PARTNER warp (issuing blocks the thread at the pipe's pace: nine more MMAs
+            // from warp 0 kept the owners' group barrier waiting for it), behind the actor's (in-order pipe)
+            asm volatile("bar.sync 4, 64;" ::: "memory");
+            fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    mma_bf16_ts(tmem + 128u, tmem + 320u + 8u * (uint32_t)j, make_desc(sbase + Smem::W2C + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+                mma_bf16(tmem + 128u, dA1b, make_desc(sbase + Smem::B2C, 16 * 128, 128), idesc_l2, 1u);
+                mma_commit(barC);
+            }
+            __syncwarp();
+        }
+        constexpr uint32_t kHeadA = 64u, kHeadC = 192u;
+        if (half == 0) {
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+            QS_TCP(3);
+            relu_epilogue(DstL3{});                 // actor: relu(H2) in place -> [0, 64)
+            QS_TCP(4);
+            fence_before();
+            group_sync(2);
+            if (lwarp == 0) {
+                fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        mma_bf16_ts(tmem + kHeadA, tmem + 8u * (uint32_t)j, make_desc(sbase + Smem::W3A + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+                    mma_commit(bar);
+                }
+                __syncwarp();
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+            QS_TCP(5);
+            float v[16];
+            tmem_ld16(my_tmem + kHeadA, v);
+#pragma unroll
+            for (int j = 0; j < Ao; ++j) head[j] = v[j] + sF[Smem::kB3 + j];
+        } else {
+            mbar_wait(barC, phaseC); phaseC ^= 1;
+            fence_after();
+            relu_epilogue(DstL3{});                 // critic: relu(H2) in place -> [128, 192)
+            fence_before();
+            group_sync(3);
+            if (lwarp == 4) {
+                fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        mma_bf16_ts(tmem + kHeadC, tmem + 128u + 8u * (uint32_t)j, make_desc(sbase + Smem::W3C + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+                    mma_commit(barC);
+                }
+                __syncwarp();
+            }
+            mbar_wait(barC, phaseC); phaseC ^= 1;
+            fence_after();
+            float w[16];
+            tmem_ld16(my_tmem + kHeadC, w);
+            value = w[0] + sF[Smem::kB3 + 16];
+            sVal[tid] = value;
+        }
+        fence_before();       // the next forward's MMAs overwrite TMEM: order our loads before the coming barrier
+        if (need_value) {     // (CTA-uniform) the owners want V(s) now: timeout bootstrap, last value
+            tile_sync<kTT>(tile);
+            value = sVal[tid];
+        }
+        QS_TCP(6);
+        return;
+      }
         // A1: normalised obs, bf16, K padded D -> K1 with a constant 1 in slots D and D + 1
         if (half == 0) {
             float x[K1];
@@ -592,7 +726,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         if (rb.obs) store_obs_rows(rb.obs + ((size_t)t * n + b0) * D);
         QS_TCP(11);
         float head[Ao], value;
-        forward(obs_, head, value);
+        forward(obs_, head, value, !kSplitCritic);
+        if constexpr (kSplitCritic) {               // the partners computed V(s): they store it (thread tid <-> env tid, as the owners)
+            if (half == 1 && tid < ept && (b0 + tid) < n && rb.value) rb.value[o] = value;
+        }
 
         StepOut so;
         so.reward = 0.f; so.done = 0.f; so.truncated = 0.f; so.finished = false; so.needs_reset = false;
@@ -621,7 +758,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             }
             if (rb.act) reinterpret_cast<float4*>(rb.act)[o] = make_float4(raw[0], raw[1], raw[2], raw[3]);
             if (rb.logp) rb.logp[o] = logp;
-            if (rb.value) rb.value[o] = value;
+            if (!kSplitCritic && rb.value) rb.value[o] = value;
             QS_TCP(7);
             env_step<MODE, true>(P, T, gid, e, act, obs_, tobs, first ? first + b0 + tid : nullptr, n, so);
             need_boot = bootstrap_gamma > 0.f && so.finished && so.truncated != 0.f && so.done == 0.f;
@@ -693,7 +830,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         // SB3 timeout bootstrap: reward += gamma * V(terminal_obs) for truncated-not-terminated episodes
         if (tile_or<kTT>(tile, need_boot)) {
             float h2[Ao], vt;
-            forward(need_boot ? tobs : obs_, h2, vt);
+            forward(need_boot ? tobs : obs_, h2, vt, true);
             if (need_boot) so.reward = fmaf(bootstrap_gamma, vt, so.reward);
         }
         if (owner) {
@@ -704,7 +841,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(10);
     }
 #ifdef QS_TC_PROFILE
-    if (blockIdx.x == 0 && (gtid == 0 || gtid == kM - 1))
+    if (blockIdx.x == 0 && (gtid == 0 || gtid == kM - 1 || (PARTNER && gtid == kM)))
         printf("tcprof tid %d steps %d: A1+sync %lld | L1wait %lld | epi1 %lld | L2 sync+wait %lld | epi2 %lld | L3 sync+wait %lld | head %lld | sample %lld | env %lld | reset %lld | boot+store %lld | obs store %lld (cycles/step)\n",
                gtid, steps, prof_[0] / steps, prof_[1] / steps, prof_[2] / steps, prof_[3] / steps, prof_[4] / steps, prof_[5] / steps,
                prof_[6] / steps, prof_[7] / steps, prof_[8] / steps, prof_[9] / steps, prof_[10] / steps, prof_[11] / steps);
@@ -712,7 +849,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
 
     {
         float head[Ao], value;
-        forward(obs_, head, value);
+        forward(obs_, head, value, true);
         if (rb.last_obs) store_obs_rows(rb.last_obs + (size_t)b0 * D);
         if (owner) {
             if (rb.last_value) rb.last_value[b0 + tid] = value;

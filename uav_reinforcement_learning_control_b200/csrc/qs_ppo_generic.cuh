@@ -65,6 +65,9 @@ ppo_grad_tc_kernel(Batch b, HyperG hp, const float* __restrict__ params, const f
     extern __shared__ __align__(1024) unsigned char smem[];
     const PolicyLayout L = policy_layout(D, DIST);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index, visibly warp-uniform (the shuffle tells ptxas): the issuing warp's descriptors then live in uniform registers
+    // and its tcgen05.mma need no per-lane election loops (a plain `if (tid == 0)` cost 130-240 cycles per MMA of issue)
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     float* sF = reinterpret_cast<float*>(smem + S::F32);
     float* sRed = reinterpret_cast<float*>(smem + S::RED);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::BAR);
@@ -244,33 +247,42 @@ ppo_grad_tc_kernel(Batch b, HyperG hp, const float* __restrict__ params, const f
             const uint32_t cW2 = base, cW1 = base + 128u, cW3 = base + 128u + (uint32_t)K1, cB2 = cW3 + 16u;
             // ---- forward -------------------------------------------------------------------------------------------
             handoff();
-            if (tid == 0) {
+            if (warp_u == 0) {                  // warp-uniform branch + elect.sync: no per-lane election loop around the MMAs
                 fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < kS1; ++j)
-                    mma_bf16(tmem + cW, dk(a0 + j * 4096, 128), dk(W1 + j * 4096, 128), id_kk128, j > 0);
-                mma_commit(bar);
+                    for (int j = 0; j < kS1; ++j)
+                        mma_bf16(tmem + cW, dk(a0 + j * 4096, 128), dk(W1 + j * 4096, 128), id_kk128, j > 0);
+                    mma_commit(bar);
+                }
+                __syncwarp();
             }
             wait_phase();
             epilogue_relu(S::A1);
             handoff();
-            if (tid == 0) {
+            if (warp_u == 0) {                  // warp-uniform branch + elect.sync: no per-lane election loop around the MMAs
                 fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    mma_bf16(tmem + cW, dk(S::A1 + j * 4096, 128), dk(W2 + j * 4096, 128), id_kk128, j > 0);
-                mma_bf16(tmem + cW, dk(a0 + kBiasStep * 4096, 128), dk(B2, 128), id_kk128, 1u);
-                mma_commit(bar);
+                    for (int j = 0; j < 8; ++j)
+                        mma_bf16(tmem + cW, dk(S::A1 + j * 4096, 128), dk(W2 + j * 4096, 128), id_kk128, j > 0);
+                    mma_bf16(tmem + cW, dk(a0 + kBiasStep * 4096, 128), dk(B2, 128), id_kk128, 1u);
+                    mma_commit(bar);
+                }
+                __syncwarp();
             }
             wait_phase();
             epilogue_relu(S::A2);
             handoff();
-            if (tid == 0) {
+            if (warp_u == 0) {                  // warp-uniform branch + elect.sync: no per-lane election loop around the MMAs
                 fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    mma_bf16(tmem + cW, dk(S::A2 + j * 4096, 128), dk(W3 + j * 512, 16), id_kk16, j > 0);
-                mma_commit(bar);
+                    for (int j = 0; j < 8; ++j)
+                        mma_bf16(tmem + cW, dk(S::A2 + j * 4096, 128), dk(W3 + j * 512, 16), id_kk16, j > 0);
+                    mma_commit(bar);
+                }
+                __syncwarp();
             }
             wait_phase();
             // ---- loss gradient w.r.t. the head outputs (fp32, this thread's sample) --------------------------------
@@ -368,40 +380,49 @@ ppo_grad_tc_kernel(Batch b, HyperG hp, const float* __restrict__ params, const f
             }
             // ---- backward ------------------------------------------------------------------------------------------
             handoff();
-            if (tid == 0) {
+            if (warp_u == 0) {                  // warp-uniform branch + elect.sync: no per-lane election loop around the MMAs
                 fence_after();
-                // dH2 = dOUT . W3^T   (B: forward W3 operand [16 x 128], MN-major: 8-hidden groups 256 B apart)
-                mma_bf16(tmem + cW, dk(S::DOUT, 128), dmn(W3, 256u), id_kmn128, 0u);
-                mma_commit(bar);
-                // dW3 += A2^T . dOUT  (not waited for here: the next commit covers it)
+                if (elect_one()) {
+                    // dH2 = dOUT . W3^T   (B: forward W3 operand [16 x 128], MN-major: 8-hidden groups 256 B apart)
+                    mma_bf16(tmem + cW, dk(S::DOUT, 128), dmn(W3, 256u), id_kmn128, 0u);
+                    mma_commit(bar);
+                    // dW3 += A2^T . dOUT  (not waited for here: the next commit covers it)
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    mma_bf16(tmem + cW3, dmn(S::A2 + j * 256, 2048u), dmn(S::DOUT + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
+                    for (int j = 0; j < 8; ++j)
+                        mma_bf16(tmem + cW3, dmn(S::A2 + j * 256, 2048u), dmn(S::DOUT + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
+                }
+                __syncwarp();
             }
             wait_phase();
             epilogue_mask(S::A2, S::D2);
             handoff();
-            if (tid == 0) {
+            if (warp_u == 0) {                  // warp-uniform branch + elect.sync: no per-lane election loop around the MMAs
                 fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)     // dH1 = D2 . W2^T
-                    mma_bf16(tmem + cW, dk(S::D2 + j * 4096, 128), dmn(W2 + j * 256, 2048u), id_kmn128, j > 0);
-                mma_commit(bar);
+                    for (int j = 0; j < 8; ++j)     // dH1 = D2 . W2^T
+                        mma_bf16(tmem + cW, dk(S::D2 + j * 4096, 128), dmn(W2 + j * 256, 2048u), id_kmn128, j > 0);
+                    mma_commit(bar);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)     // dW2 += A1^T . D2
-                    mma_bf16(tmem + cW2, dmn(S::A1 + j * 256, 2048u), dmn(S::D2 + j * 256, 2048u), id_mm128, j > 0 ? 1u : first);
+                    for (int j = 0; j < 8; ++j)     // dW2 += A1^T . D2
+                        mma_bf16(tmem + cW2, dmn(S::A1 + j * 256, 2048u), dmn(S::D2 + j * 256, 2048u), id_mm128, j > 0 ? 1u : first);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)     // db2 (column kBiasK) += D2^T . A0[K step kBiasStep]
-                    mma_bf16(tmem + cB2, dmn(S::D2 + j * 256, 2048u), dmn(a0 + kBiasStep * 4096 + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
+                    for (int j = 0; j < 8; ++j)     // db2 (column kBiasK) += D2^T . A0[K step kBiasStep]
+                        mma_bf16(tmem + cB2, dmn(S::D2 + j * 256, 2048u), dmn(a0 + kBiasStep * 4096 + j * 256, 2048u), id_mm16, j > 0 ? 1u : first);
+                }
+                __syncwarp();
             }
             wait_phase();                       // also covers dW3: A2 may be overwritten now
             epilogue_mask(S::A1, S::A2);        // D1 -> the A2 buffer
             handoff();
-            if (tid == 0) {
+            if (warp_u == 0) {                  // warp-uniform branch + elect.sync: no per-lane election loop around the MMAs
                 fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)     // dW1^T (columns 0..D-1), db1 (column D) += D1^T . A0
-                    mma_bf16(tmem + cW1, dmn(S::A2 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mmK1, j > 0 ? 1u : first);
+                    for (int j = 0; j < 8; ++j)     // dW1^T (columns 0..D-1), db1 (column D) += D1^T . A0
+                        mma_bf16(tmem + cW1, dmn(S::A2 + j * 256, 2048u), dmn(a0 + j * 256, 2048u), id_mmK1, j > 0 ? 1u : first);
+                }
+                __syncwarp();
             }
         }
         cur = nxt;
@@ -409,7 +430,7 @@ ppo_grad_tc_kernel(Batch b, HyperG hp, const float* __restrict__ params, const f
 
     // ---- flush: TMEM accumulators -> this CTA's partial-gradient row --------------------------------------------------
     handoff();
-    if (tid == 0) { fence_after(); mma_commit(bar); }
+    if (warp_u == 0) { fence_after(); if (elect_one()) mma_commit(bar); __syncwarp(); }
     wait_phase();
     const int P = L.total;
     float* out = partial + (size_t)blockIdx.x * partial_stride(P);

@@ -274,7 +274,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     constexpr int kS1 = K1 / 16;                           // layer-1 K = 16 steps
     constexpr int kBiasStep = D / 16, kBiasK = D % 16;     // K step / slot (and slot + 1) that carry the constant 1
     static_assert(D + 2 <= K1 && kBiasK + 1 < 16, "bias slots must fit one K = 16 step");
-    static_assert(!PARTNER || (TILES == 1 && D == 12), "partner warpgroup: one tile per CTA, 12-D observation");
+    static_assert(!PARTNER || TILES == 1, "partner warpgroup: one tile per CTA");
     using Smem = SmemT<K1, PARTNER>;
     constexpr int Ao = DIST == 1 ? 2 * kA : kA;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -712,11 +712,13 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             }
         } else {
             float* stage = reinterpret_cast<float*>(tsm + Smem::OBS);
+            if (half == 0) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) stage[tid * D + k] = obs_[k];
+                for (int k = 0; k < D; ++k) stage[tid * D + k] = obs_[k];
+            }
             tile_sync<kTT>(tile);
             const int rows = min(ept, n - b0);
-            for (int idx = tid; idx < rows * D; idx += kM) dst_tile[idx] = stage[idx];
+            for (int idx = ltid; idx < rows * D; idx += kTT) dst_tile[idx] = stage[idx];      // all of the tile's threads copy
             tile_sync<kTT>(tile);                           // the staging tile is rewritten next step
         }
     };
@@ -891,12 +893,13 @@ inline int launch_rollout_tc_t(const QsParams& P, const Tables& T, int n, float*
     // staging tile) do not fit two tiles into 227 KB of shared memory
     if constexpr (ModeTraits<MODE>::kObsDim == 12) {
         if (n >= 148 * 2 * kM) return launch_rollout_tc_tt<MODE, DIST, 2>(P, T, n, state, params, steps, t0, opt, rb, first, s);
-#if QS_TC_PARTNER
-        // small batches: one tile per CTA plus a partner warpgroup that shortens the per-step latency chain
-        return launch_rollout_tc_tt<MODE, DIST, 1, true>(P, T, n, state, params, steps, t0, opt, rb, first, s);
-#endif
     }
+#if QS_TC_PARTNER
+    // one tile per CTA (small 12-D batches, every 21-D batch) plus a partner warpgroup that shortens the per-step latency chain
+    return launch_rollout_tc_tt<MODE, DIST, 1, true>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+#else
     return launch_rollout_tc_tt<MODE, DIST, 1>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+#endif
 }
 
 inline int launch_rollout_policy_tc(const QsParams& P, const Tables& T, int n, float* state, const QsPolicyDesc& d,

@@ -462,7 +462,9 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     auto group_sync = [&](int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(128) : "memory"); };
     // forward pass for the observation in `o`; returns head[Ao] and -- if need_value (split critic: otherwise the partners
     // keep it in sVal and store it themselves) -- value
-    auto forward = [&](const float* o, float* head, float& value, bool need_value) {
+    // noise_out (plain CTAs, may be null): this step's sampling noise is drawn UNDER the layer-2 MMAs -- Philox + Box-Muller
+    // need only (env id, step index), and the threads would otherwise just wait there
+    auto forward = [&](const float* o, float* head, float& value, bool need_value, float4* noise_out = nullptr, uint32_t noise_ts = 0u) {
       if constexpr (kSplitCritic) {
         if (half == 0) {
             float x[K1];
@@ -641,6 +643,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             }
             __syncwarp();
         }
+        if (noise_out) *noise_out = draw_noise(noise_ts);
         mbar_wait(bar, phase); phase ^= 1;
         fence_after();
         QS_TCP(3);
@@ -728,7 +731,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         if (rb.obs) store_obs_rows(rb.obs + ((size_t)t * n + b0) * D);
         QS_TCP(11);
         float head[Ao], value;
-        forward(obs_, head, value, !kSplitCritic);
+        float4 e4_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+        forward(obs_, head, value, !kSplitCritic, PARTNER ? nullptr : &e4_pre, t0 + (uint32_t)t);
         if constexpr (kSplitCritic) {               // the partners computed V(s): they store it (thread tid <-> env tid, as the owners)
             if (half == 1 && tid < ept && (b0 + tid) < n && rb.value) rb.value[o] = value;
         }
@@ -739,7 +743,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         bool need_boot = false;
         if (owner) {
             // PARTNER: the partner warpgroup drew this step's noise during the previous step
-            const float4 e4 = PARTNER ? sEps[(t & 1) * kM + tid] : draw_noise(t0 + (uint32_t)t);
+            const float4 e4 = PARTNER ? sEps[(t & 1) * kM + tid] : e4_pre;      // plain CTAs: drawn under the layer-2 MMAs (forward)
             const float eps[4] = {e4.x, e4.y, e4.z, e4.w};
             float raw[4], act[4], logp = 0.f;
 #pragma unroll

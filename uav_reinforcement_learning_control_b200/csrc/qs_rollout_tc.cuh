@@ -715,14 +715,24 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             }
         } else {
             float* stage = reinterpret_cast<float*>(tsm + Smem::OBS);
-            if (half == 0) {
+            const int rows = min(ept, n - b0);
+            if constexpr (PARTNER) {
+                // owners only (their own named barrier): the partners are still behind, finishing the critic of the previous
+                // step -- a tile-wide barrier here put the owners back behind them (ncu: `barrier` was the top stall)
+                if (half == 0) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) stage[tid * D + k] = obs_[k];
+                    group_sync(2);
+                    for (int idx = tid; idx < rows * D; idx += kM) dst_tile[idx] = stage[idx];
+                    group_sync(2);                          // the staging tile is rewritten next step
+                }
+            } else {
 #pragma unroll
                 for (int k = 0; k < D; ++k) stage[tid * D + k] = obs_[k];
+                tile_sync<kTT>(tile);
+                for (int idx = tid; idx < rows * D; idx += kM) dst_tile[idx] = stage[idx];
+                tile_sync<kTT>(tile);                       // the staging tile is rewritten next step
             }
-            tile_sync<kTT>(tile);
-            const int rows = min(ept, n - b0);
-            for (int idx = ltid; idx < rows * D; idx += kTT) dst_tile[idx] = stage[idx];      // all of the tile's threads copy
-            tile_sync<kTT>(tile);                           // the staging tile is rewritten next step
         }
     };
 

@@ -413,3 +413,53 @@ def test_rollout_tensor_core_tile_spreading_is_bitwise_neutral(B, monkeypatch):
         for k in outs[0][0]:
             np.testing.assert_array_equal(b[k].view(np.uint32), outs[0][0][k].view(np.uint32), err_msg=k)
         np.testing.assert_array_equal(stn.view(np.uint32), outs[0][1].view(np.uint32))
+
+
+def _form_case(case):
+    from uav_reinforcement_learning_control_b200 import policies, trajectories as TJ
+    if case == "hover_gauss":
+        return Q.EnvConfig.north_star(seed=5, env_id_offset=17, max_episode_steps=6), _random_policy(12, 0, seed=2, scale=0.6), 0, 0.9
+    if case == "hover_tanh":
+        return Q.EnvConfig.north_star(seed=8, env_id_offset=1, max_episode_steps=5), _random_policy(12, 1, seed=3, scale=0.6), 1, 0.9
+    if case == "traj_gym":
+        return (Q.EnvConfig.traj_gym(auto_reset=Q.RESET_RESAMPLE, seed=13, env_id_offset=11, max_episode_steps=7),
+                _random_policy(12, 0, seed=31, scale=0.5), 0, 0.97)
+    if case == "waypoint":
+        return (Q.EnvConfig.waypoint_eval(TJ.default_tables(0.5), auto_reset=Q.RESET_RESAMPLE, seed=9, env_id_offset=3, max_episode_steps=7),
+                _random_policy(12, 0, seed=23, scale=0.8), 0, 0.95)
+    raise KeyError(case)
+
+
+@pytest.mark.parametrize("B", [389, 148 * 256 + 77])
+@pytest.mark.parametrize("case", ["hover_gauss", "hover_tanh", "traj_gym", "waypoint"])
+def test_rollout_tensor_core_cta_forms_are_bitwise_equal(case, B, monkeypatch):
+    """The tcgen05 rollout has three CTA forms: one tile + partner warpgroup (small batches; the form every oracle lock-step
+    test above runs), two plain tiles, and two compact tiles with a partner warpgroup each (batches >= 148 x 256 envs: what
+    BASELINE configs[3] / [4] and the 2^18-env bench legs run).  They issue the same MMAs in the same accumulation order and
+    share the env code, so every recorded plane and the final state must agree to the bit -- which extends the oracle parity
+    of the one-tile form to the large-batch forms, at a batch size the oracle could not step in seconds.  B = 389 forces the
+    forms onto a ragged batch (last CTA: one full, one partial / empty tile); the large B also checks what the default picks."""
+    import torch
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    cfg, params, dist, gamma = _form_case(case)
+    d_params = torch.from_numpy(params).cuda()
+    outs = {}
+    for form in ("1", "2", "3", None):
+        if form is None:
+            monkeypatch.delenv("QS_TC_FORM", raising=False)
+        else:
+            monkeypatch.setenv("QS_TC_FORM", form)
+        eng = Engine(cfg, B, device=0)
+        st = eng.new_state(); eng.reset(st)
+        buf = None
+        for c in range(2):                       # two launches: the second starts from the state the first one stored
+            buf = eng.rollout_policy(st, d_params, T=11, t0=2 + 11 * c, dist=dist, tensor_cores=True, bootstrap_gamma=gamma, buffers=buf)
+        torch.cuda.synchronize()
+        outs[form] = ({k: v.cpu().numpy() for k, v in buf.items()}, st.cpu().numpy())
+    ref_b, ref_st = outs["1"]
+    assert ref_b["done"].sum() + ref_b["trunc"].sum() > B // 4          # resets happened (in-kernel, all three paths)
+    assert np.isfinite(ref_b["value"]).all() and np.isfinite(ref_b["reward"]).all()
+    for form, (b, stn) in outs.items():
+        for k in ref_b:
+            np.testing.assert_array_equal(b[k].view(np.uint32), ref_b[k].view(np.uint32), err_msg=f"form {form}: {k}")
+        np.testing.assert_array_equal(stn.view(np.uint32), ref_st.view(np.uint32), err_msg=f"form {form}: state planes")

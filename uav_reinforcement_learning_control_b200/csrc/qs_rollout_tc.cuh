@@ -40,6 +40,10 @@
 #define QS_TC_SPLIT_CRITIC 1 /* 1 (partner-warpgroup CTAs): the critic's layer-2 / head MMAs and epilogues run BEHIND the actor's, off the
                                 owners' per-step latency chain (own mbarrier, issued / consumed by the partner warpgroup) */
 #endif
+#ifndef QS_TC_PARTNER2
+#define QS_TC_PARTNER2 1     /* 1: large 12-D batches run two COMPACT tiles per CTA, each with its own partner warpgroup (512 threads, 256
+                                tensor-memory columns per tile: see the column plan in the kernel); 0: two plain tiles (256 threads) */
+#endif
 #ifndef QS_TC_TS_L2
 #define QS_TC_TS_L2 1        /* 1 (one-tile CTAs only: needs 384 of the 512 TMEM columns per tile): relu(H1) also stays in tensor
                                 memory and layer 2 runs as TS-form MMAs */
@@ -225,7 +229,9 @@ __device__ __forceinline__ uint32_t op_offset(int rows, int row, int kc) {
 
 // shared-memory map (bytes).  K1 = layer-1 K (observation + 2 bias slots, padded to a multiple of 16): 16 for the
 // 12-D gym observation, 32 for the 21-D raw observation of the brax / mjx modes.
-template <int K1, bool PARTNER = false>
+// COMPACT (two tiles per CTA, each with a partner warpgroup): the actor's activations never pass through shared memory
+// (TS-form layers), so a tile keeps only the critic's layer-2 A operand (A2C); A2A has size 0.
+template <int K1, bool PARTNER = false, bool COMPACT = false>
 struct SmemT {
     static constexpr int W1 = 0;                          // B: [256 x K1] bf16
     static constexpr int W2A = W1 + 256 * K1 * 2;         // B: [128 x 128]
@@ -237,7 +243,7 @@ struct SmemT {
     static constexpr int WEND = B2C + 128 * 16 * 2;       // end of the (shared) B operands
     // per tile: A1 [128 x K1], A2A / A2C [128 x 128] (A2* are also the A operands of L3), and for the 21-D modes a
     // float staging tile for the coalesced trajectory store of the raw observations
-    static constexpr int A1 = 0, A2A = 128 * K1 * 2, A2C = A2A + 128 * 128 * 2;
+    static constexpr int A1 = 0, A2A = 128 * K1 * 2, A2C = A2A + (COMPACT ? 0 : 128 * 128 * 2);
     static constexpr int OBS = A2C + 128 * 128 * 2;
     static constexpr int EPS = OBS + (K1 > 16 ? 128 * 21 * 4 : 0);      // PARTNER: 2 x [128] float4 sampling noise (double buffer)
     static constexpr int CAND = EPS + (PARTNER ? 2 * 128 * 16 : 0);     // PARTNER: speculative reset candidates [128][28] float + episode mailbox [128] u32
@@ -248,8 +254,10 @@ struct SmemT {
     static constexpr int TILE0 = WEND;
     __host__ __device__ static constexpr int f32_off(int tiles) { return TILE0 + tiles * TILE_BYTES; }   // fp32 constants, see below
     static constexpr int kB3 = 0 /*[32]*/, kLogStd = 32, kMean = 36, kInvStd = 60, kNumF = 84;
-    __host__ __device__ static constexpr int bar_off(int tiles) { return f32_off(tiles) + kNumF * 4; }   // mbarriers (8 B per tile) + tmem base (4 B) + PARTNER: the critic's mbarrier
-    __host__ __device__ static constexpr int total(int tiles) { return bar_off(tiles) + 8 * tiles + 24; }
+    // mbarriers: [tiles] the actor's / everybody's | tmem base (4 B, padded to 8) | PARTNER: [tiles] the critic's | COMPACT: [tiles]
+    // "actor's layer 2 complete" for the partner warp that issues the critic's
+    __host__ __device__ static constexpr int bar_off(int tiles) { return f32_off(tiles) + kNumF * 4; }
+    __host__ __device__ static constexpr int total(int tiles) { return bar_off(tiles) + 24 * tiles + 8; }
 };
 
 // PARTNER (one tile per CTA, 12-D modes): a second warpgroup shares the tile.  Warp w + 4 reads the same 32 TMEM lanes
@@ -274,8 +282,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     constexpr int kS1 = K1 / 16;                           // layer-1 K = 16 steps
     constexpr int kBiasStep = D / 16, kBiasK = D % 16;     // K step / slot (and slot + 1) that carry the constant 1
     static_assert(D + 2 <= K1 && kBiasK + 1 < 16, "bias slots must fit one K = 16 step");
-    static_assert(!PARTNER || TILES == 1, "partner warpgroup: one tile per CTA");
-    using Smem = SmemT<K1, PARTNER>;
+    // two tiles + two partner warpgroups (512 threads): the COMPACT tensor-memory plan below, 12-D observations only
+    constexpr bool kCompact = PARTNER && TILES == 2;
+    static_assert(!PARTNER || TILES == 1 || (TILES == 2 && K1 == 16 && QS_TC_TS_HEADS != 0), "partner warpgroups: one tile per CTA, or two compact tiles");
+    using Smem = SmemT<K1, PARTNER, kCompact>;
     constexpr int Ao = DIST == 1 ? 2 * kA : kA;
     extern __shared__ __align__(1024) unsigned char smem[];
     // 256 accumulator columns per tile; one-tile CTAs with TS-form layer 2 also keep relu(H1) in columns [256, 384)
@@ -291,7 +301,9 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     const int lwarp = __shfl_sync(0xffffffffu, ltid >> 5, 0);   // warp index within the tile, visibly warp-uniform: warp 0 issues the MMAs
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES)) + tile;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::bar_off(TILES) + 8 * TILES);
-    uint64_t* barC = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES) + 8 * TILES + 8);      // PARTNER: the critic's commits
+    uint64_t* barC = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES) + 8 * TILES + 8) + tile;          // PARTNER: the critic's commits
+    uint64_t* barX = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(TILES) + 16 * TILES + 8) + tile;         // COMPACT: the actor's layer 2 is complete
+    const int tb = 4 * tile;                                // named barriers of this tile: tb + 1 whole tile, + 2 owners, + 3 partners, + 4 issue hand-off
     unsigned char* tsm = smem + Smem::TILE0 + tile * Smem::TILE_BYTES;   // this tile's A operands
     const int b0 = (blockIdx.x * TILES + tile) * ept;
 
@@ -342,7 +354,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     if (gtid == 0) sF[Smem::kB3 + 16] = params[L.cb3];
     if (DIST == 0 && gtid < kA) sF[Smem::kLogStd + gtid] = params[L.log_std + gtid];
     if (gtid < D) { sF[Smem::kMean + gtid] = params[L.mean + gtid]; sF[Smem::kInvStd + gtid] = params[L.inv_std + gtid]; }
-    if (ltid == 0) { mbar_init(bar, 1); if (PARTNER) mbar_init(barC, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (ltid == 0) { mbar_init(bar, 1); if (PARTNER) mbar_init(barC, 1); if (kCompact) mbar_init(barX, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (gtid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -411,10 +423,11 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     // 2 = tensor memory columns [256, 320) | [320, 384) (TS-form layer 2, one-tile CTAs).  In-place is safe: a thread stores
     // the 16 packed columns of chunk c to [16 c, 16 c + 16) after it has loaded [32 c, 32 c + 32), the one load in flight
     // covers [32 (c + 1), 32 (c + 2)), and lanes are private to the warp that owns them.
-    auto relu_epilogue = [&](auto dst_tag) {
+    // c_first >= 0 (compact tiles): the first of the four 32-column chunks this warpgroup takes
+    auto relu_epilogue = [&](auto dst_tag, int c_first = -1) {
         constexpr int kDst = decltype(dst_tag)::value;
         constexpr int kChunks = PARTNER ? 4 : 8;
-        const int c_lo = PARTNER ? 4 * half : 0;
+        const int c_lo = c_first >= 0 ? c_first : (PARTNER ? 4 * half : 0);
         uint32_t r[2][32];
         tmem_ld32_async(my_tmem + (uint32_t)(c_lo * 32), r[0]);
         tmem_ld_wait(r[0]);
@@ -456,8 +469,9 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     // of the epilogues anyway -- finish the critic behind them, issue its head themselves and leave V(s) in shared memory.
     // The owner / partner warpgroups synchronise among themselves (named barriers 2 / 3, 128 threads); both meet again at
     // the tile barrier that opens the next forward, before its layer-1 MMA overwrites the accumulator columns.
-    constexpr bool kSplitCritic = PARTNER && QS_TC_SPLIT_CRITIC != 0 && QS_TC_TS_HEADS != 0 && QS_TC_TS_L2 != 0;
-    uint32_t phaseC = 0;
+    constexpr bool kSplitCritic = PARTNER && TILES == 1 && QS_TC_SPLIT_CRITIC != 0 && QS_TC_TS_HEADS != 0 && QS_TC_TS_L2 != 0;
+    constexpr bool kCriticBehind = kSplitCritic || kCompact;     // V(s) is produced (and stored) by the partner warpgroup
+    uint32_t phaseC = 0, phaseX = 0;
     float* sVal = reinterpret_cast<float*>(tsm + Smem::VAL);
     auto group_sync = [&](int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(128) : "memory"); };
     // forward pass for the observation in `o`; returns head[Ao] and -- if need_value (split critic: otherwise the partners
@@ -465,6 +479,138 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     // noise_out (plain CTAs, may be null): this step's sampling noise is drawn UNDER the layer-2 MMAs -- Philox + Box-Muller
     // need only (env id, step index), and the threads would otherwise just wait there
     auto forward = [&](const float* o, float* head, float& value, bool need_value, float4* noise_out = nullptr, uint32_t noise_ts = 0u) {
+      if constexpr (kCompact) {
+        // COMPACT tiles (two tiles per CTA, each with a partner warpgroup; 256 tensor-memory columns per tile).  Column plan of a
+        // forward (A = bf16 A operand of a TS-form MMA, two K elements per 32-bit column; D = fp32 accumulator):
+        //   layer 1      D1 actor [0, 128) | D1 critic [128, 256)                    (one N = 256 instruction per K step)
+        //   epilogue 1   owners:   relu(D1 actor)  -> A [0, 64)    in place
+        //                partners: relu(D1 critic) -> shared memory A2C              (the critic's layer 2 is SS form)
+        //   layer 2      actor  (warp 0): D2 [128, 256) <- A [0, 64) . W2A           on the owners' latency chain, TS form
+        //                critic (warp 4): D2 [0, 128)   <- A2C . W2C                 issued only once the actor's layer 2 has
+        //                                  COMPLETED (barX): its accumulator overwrites the actor's A columns
+        //   epilogue 2   owners:   relu(D2 actor)  -> A [128, 192) in place;  head D [192, 208)
+        //                partners: relu(D2 critic) -> A [0, 64)    in place;  head D [64, 80)
+        // Everything the owners wait for is TS form, as in the one-tile split-critic CTAs; only the critic -- which runs behind
+        // the owners' env step anyway -- pays a shared-memory hand-off, and the tile needs 256 columns instead of 384, so an SM
+        // holds two tiles = 16 warps (plain two-tile CTAs: 8 warps, each tile's whole chain on one warpgroup).
+        if (half == 0) {
+            float x[K1];
+#pragma unroll
+            for (int k = 0; k < K1; ++k) x[k] = k < D ? (o[k] - sF[Smem::kMean + k]) * sF[Smem::kInvStd + k] : (k < D + 2 ? 1.0f : 0.f);
+#pragma unroll
+            for (int c = 0; c < K1 / 8; ++c)
+                *reinterpret_cast<uint4*>(tsm + Smem::A1 + op_offset(128, tid, c)) =
+                    make_uint4(pack_bf16(x[8 * c], x[8 * c + 1]), pack_bf16(x[8 * c + 2], x[8 * c + 3]),
+                               pack_bf16(x[8 * c + 4], x[8 * c + 5]), pack_bf16(x[8 * c + 6], x[8 * c + 7]));
+        }
+        fence_async_smem();
+        fence_before();
+        tile_sync<kTT>(tb);                         // both warpgroups: the previous forward's TMEM reads are done too
+        if (lwarp == 0) {
+            fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < kS1; ++j)
+                    mma_bf16(tmem, make_desc(tbase + Smem::A1 + j * 4096, 16 * 128, 128),
+                             make_desc(sbase + Smem::W1 + j * 8192, 32 * 128, 128), idesc_l1, j > 0);
+                mma_commit(bar);
+                mma_commit(barC);
+            }
+            __syncwarp();
+        }
+        QS_TCP(0);
+        if (half == 0) { mbar_wait(bar, phase); phase ^= 1; } else { mbar_wait(barC, phaseC); phaseC ^= 1; }
+        fence_after();
+        QS_TCP(1);
+        if (half == 0) {
+            relu_epilogue(std::integral_constant<int, 1>{}, 0);        // actor: [0, 128) -> A [0, 64) in place
+        } else {
+            relu_epilogue(std::integral_constant<int, 0>{}, 4);        // critic: [128, 256) -> A2C
+            fence_async_smem();
+        }
+        QS_TCP(2);
+        fence_before();
+        tile_sync<kTT>(tb);
+        if (lwarp == 0) {
+            fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    mma_bf16_ts(tmem + 128u, tmem + 8u * (uint32_t)j, make_desc(sbase + Smem::W2A + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+                mma_bf16(tmem + 128u, dA1b, make_desc(sbase + Smem::B2A, 16 * 128, 128), idesc_l2, 1u);
+                mma_commit(bar);                    // the owners wait for this one
+                mma_commit(barX);                   // and the partner warp that issues the critic's layer 2
+            }
+            __syncwarp();
+        } else if (lwarp == 4) {
+            mbar_wait(barX, phaseX); phaseX ^= 1;   // the actor's layer 2 has read its A columns [0, 64)
+            fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    mma_bf16(tmem, make_desc(tbase + Smem::A2C + j * 4096, 16 * 128, 128),
+                             make_desc(sbase + Smem::W2C + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
+                mma_bf16(tmem, dA1b, make_desc(sbase + Smem::B2C, 16 * 128, 128), idesc_l2, 1u);
+                mma_commit(barC);
+            }
+            __syncwarp();
+        }
+        if (half == 0) {
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+            QS_TCP(3);
+            relu_epilogue(std::integral_constant<int, 1>{}, 4);        // actor: relu(H2) in place -> A [128, 192)
+            QS_TCP(4);
+            fence_before();
+            group_sync(tb + 2);
+            if (lwarp == 0) {
+                fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        mma_bf16_ts(tmem + 192u, tmem + 128u + 8u * (uint32_t)j, make_desc(sbase + Smem::W3A + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+                    mma_commit(bar);
+                }
+                __syncwarp();
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+            QS_TCP(5);
+            float v[16];
+            tmem_ld16(my_tmem + 192u, v);
+#pragma unroll
+            for (int j = 0; j < Ao; ++j) head[j] = v[j] + sF[Smem::kB3 + j];
+        } else {
+            mbar_wait(barC, phaseC); phaseC ^= 1;
+            fence_after();
+            relu_epilogue(std::integral_constant<int, 1>{}, 0);        // critic: relu(H2) in place -> A [0, 64)
+            fence_before();
+            group_sync(tb + 3);
+            if (lwarp == 4) {
+                fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        mma_bf16_ts(tmem + 64u, tmem + 8u * (uint32_t)j, make_desc(sbase + Smem::W3C + j * 512, 2 * 128, 128), idesc_l3, j > 0);
+                    mma_commit(barC);
+                }
+                __syncwarp();
+            }
+            mbar_wait(barC, phaseC); phaseC ^= 1;
+            fence_after();
+            float w[16];
+            tmem_ld16(my_tmem + 64u, w);
+            value = w[0] + sF[Smem::kB3 + 16];
+            sVal[tid] = value;
+        }
+        fence_before();       // the next forward's MMAs overwrite TMEM: order our loads before the coming barrier
+        if (need_value) {     // (CTA-uniform per tile) the owners want V(s) now: timeout bootstrap, last value
+            tile_sync<kTT>(tb);
+            value = sVal[tid];
+        }
+        QS_TCP(6);
+        return;
+      }
       if constexpr (kSplitCritic) {
         if (half == 0) {
             float x[K1];
@@ -478,7 +624,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         fence_async_smem();
         fence_before();
-        tile_sync<kTT>(tile);                       // both warpgroups: the previous forward's TMEM reads are done too
+        tile_sync<kTT>(tb);                       // both warpgroups: the previous forward's TMEM reads are done too
         if (lwarp == 0) {
             fence_after();
             if (elect_one()) {
@@ -498,7 +644,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         relu_epilogue(DstL2{});                     // owners: actor half -> [256, 320); partners: critic half -> [320, 384)
         QS_TCP(2);
         fence_before();
-        tile_sync<kTT>(tile);
+        tile_sync<kTT>(tb);
         if (lwarp == 0) {
             fence_after();
             if (elect_one()) {
@@ -509,11 +655,11 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 mma_commit(bar);                    // the actor's layer 2 is all the owners wait for
             }
             __syncwarp();
-            asm volatile("bar.arrive 4, 64;" ::: "memory");          // the actor's MMAs are in the pipe: the critic's may follow
+            asm volatile("bar.arrive %0, 64;" :: "r"(tb + 4) : "memory");          // the actor's MMAs are in the pipe: the critic's may follow
         } else if (lwarp == 4) {
             // the critic's layer 2 is issued by a PARTNER warp (issuing blocks the thread at the pipe's pace: nine more MMAs
             // from warp 0 kept the owners' group barrier waiting for it), behind the actor's (in-order pipe)
-            asm volatile("bar.sync 4, 64;" ::: "memory");
+            asm volatile("bar.sync %0, 64;" :: "r"(tb + 4) : "memory");
             fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -532,7 +678,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             relu_epilogue(DstL3{});                 // actor: relu(H2) in place -> [0, 64)
             QS_TCP(4);
             fence_before();
-            group_sync(2);
+            group_sync(tb + 2);
             if (lwarp == 0) {
                 fence_after();
                 if (elect_one()) {
@@ -555,7 +701,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             fence_after();
             relu_epilogue(DstL3{});                 // critic: relu(H2) in place -> [128, 192)
             fence_before();
-            group_sync(3);
+            group_sync(tb + 3);
             if (lwarp == 4) {
                 fence_after();
                 if (elect_one()) {
@@ -575,7 +721,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         fence_before();       // the next forward's MMAs overwrite TMEM: order our loads before the coming barrier
         if (need_value) {     // (CTA-uniform) the owners want V(s) now: timeout bootstrap, last value
-            tile_sync<kTT>(tile);
+            tile_sync<kTT>(tb);
             value = sVal[tid];
         }
         QS_TCP(6);
@@ -594,7 +740,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         fence_async_smem();
         fence_before();
-        tile_sync<kTT>(tile);
+        tile_sync<kTT>(tb);
         if (lwarp == 0) {
             fence_after();
             if (elect_one()) {
@@ -616,7 +762,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(2);
         if constexpr (!kTsL2) fence_async_smem();
         fence_before();
-        tile_sync<kTT>(tile);
+        tile_sync<kTT>(tb);
         if (lwarp == 0) {
             fence_after();
             if (elect_one()) {
@@ -653,7 +799,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(4);
         if constexpr (!kTsHeads) fence_async_smem();
         fence_before();
-        tile_sync<kTT>(tile);
+        tile_sync<kTT>(tb);
         // heads: N = 16 (B rows/8 = 2 -> LBO 256 B, K step 512 B); TS form: D at columns [64, 80) | [192, 208), the upper
         // (consumed) halves of the accumulator regions whose lower halves now hold the A operands
         constexpr uint32_t kHeadA = kTsHeads ? 64u : 0u, kHeadC = kTsHeads ? 192u : 16u;
@@ -722,16 +868,16 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 if (half == 0) {
 #pragma unroll
                     for (int k = 0; k < D; ++k) stage[tid * D + k] = obs_[k];
-                    group_sync(2);
+                    group_sync(tb + 2);
                     for (int idx = tid; idx < rows * D; idx += kM) dst_tile[idx] = stage[idx];
-                    group_sync(2);                          // the staging tile is rewritten next step
+                    group_sync(tb + 2);                          // the staging tile is rewritten next step
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < D; ++k) stage[tid * D + k] = obs_[k];
-                tile_sync<kTT>(tile);
+                tile_sync<kTT>(tb);
                 for (int idx = tid; idx < rows * D; idx += kM) dst_tile[idx] = stage[idx];
-                tile_sync<kTT>(tile);                       // the staging tile is rewritten next step
+                tile_sync<kTT>(tb);                       // the staging tile is rewritten next step
             }
         }
     };
@@ -742,8 +888,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(11);
         float head[Ao], value;
         float4 e4_pre = make_float4(0.f, 0.f, 0.f, 0.f);
-        forward(obs_, head, value, !kSplitCritic, PARTNER ? nullptr : &e4_pre, t0 + (uint32_t)t);
-        if constexpr (kSplitCritic) {               // the partners computed V(s): they store it (thread tid <-> env tid, as the owners)
+        forward(obs_, head, value, !kCriticBehind, PARTNER ? nullptr : &e4_pre, t0 + (uint32_t)t);
+        if constexpr (kCriticBehind) {              // the partners computed V(s): they store it (thread tid <-> env tid, as the owners)
             if (half == 1 && tid < ept && (b0 + tid) < n && rb.value) rb.value[o] = value;
         }
 
@@ -774,7 +920,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             }
             if (rb.act) reinterpret_cast<float4*>(rb.act)[o] = make_float4(raw[0], raw[1], raw[2], raw[3]);
             if (rb.logp) rb.logp[o] = logp;
-            if (!kSplitCritic && rb.value) rb.value[o] = value;
+            if (!kCriticBehind && rb.value) rb.value[o] = value;
             QS_TCP(7);
             env_step<MODE, true>(P, T, gid, e, act, obs_, tobs, first ? first + b0 + tid : nullptr, n, so);
             need_boot = bootstrap_gamma > 0.f && so.finished && so.truncated != 0.f && so.done == 0.f;
@@ -801,7 +947,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                     d[5] = make_float4(o[4], o[5], o[6], o[7]);
                     d[6] = make_float4(o[8], o[9], o[10], o[11]);
                 }
-                tile_sync<kTT>(tile);                                      // candidates of this step are in place
+                tile_sync<kTT>(tb);                                      // candidates of this step are in place
                 if (so.needs_reset) {                                      // (owners only; e.episode was advanced by env_step)
                     const float4* d = reinterpret_cast<const float4*>(sCand + tid * Smem::kCandF);
                     const float4 c0 = d[0], c1 = d[1], c2 = d[2], c3 = d[3], c4 = d[4], c5 = d[5], c6 = d[6];
@@ -844,7 +990,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         QS_TCP(9);
         // SB3 timeout bootstrap: reward += gamma * V(terminal_obs) for truncated-not-terminated episodes
-        if (tile_or<kTT>(tile, need_boot)) {
+        if (tile_or<kTT>(tb, need_boot)) {
             float h2[Ao], vt;
             forward(need_boot ? tobs : obs_, h2, vt, true);
             if (need_boot) so.reward = fmaf(bootstrap_gamma, vt, so.reward);
@@ -885,7 +1031,7 @@ inline int launch_rollout_tc_tt(const QsParams& P, const Tables& T, int n, float
                                 uint32_t t0, const RolloutOpts& opt, const RolloutBuffers& rb, const float* first,
                                 cudaStream_t s) {
     auto kern = rollout_policy_tc_kernel<MODE, DIST, TILES, PARTNER>;
-    using Smem = SmemT<(ModeTraits<MODE>::kObsDim + 2 <= 16) ? 16 : 32, PARTNER>;
+    using Smem = SmemT<(ModeTraits<MODE>::kObsDim + 2 <= 16) ? 16 : 32, PARTNER, PARTNER && TILES == 2>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total(TILES));
     if (ce != cudaSuccess) return (int)ce;
     int ept = kM;                                    // envs per tile; QS_TC_EPT: test / tuning override (see the kernel)
@@ -905,8 +1051,16 @@ inline int launch_rollout_tc_t(const QsParams& P, const Tables& T, int n, float*
                                cudaStream_t s) {
     // two tiles per CTA only when that still gives every SM a CTA; the 21-D modes (K1 = 32 operands + the observation
     // staging tile) do not fit two tiles into 227 KB of shared memory
+    // QS_TC_FORM (test / tuning override; every form records bitwise the same trajectories, tests/test_gpu_rollout.py):
+    // 1 = one tile + partner warpgroup, 2 = two plain tiles, 3 = two compact tiles with a partner warpgroup each
+    const char* fo = getenv("QS_TC_FORM");
+    const int form = fo ? atoi(fo) : 0;
     if constexpr (ModeTraits<MODE>::kObsDim == 12) {
-        if (n >= 148 * 2 * kM) return launch_rollout_tc_tt<MODE, DIST, 2>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+        const bool big = n >= 148 * 2 * kM;
+#if QS_TC_PARTNER && QS_TC_PARTNER2 && QS_TC_TS_HEADS
+        if (form == 3 || (form == 0 && big)) return launch_rollout_tc_tt<MODE, DIST, 2, true>(P, T, n, state, params, steps, t0, opt, rb, first, s);
+#endif
+        if (form == 2 || (form == 0 && big)) return launch_rollout_tc_tt<MODE, DIST, 2>(P, T, n, state, params, steps, t0, opt, rb, first, s);
     }
 #if QS_TC_PARTNER
     // one tile per CTA (small 12-D batches, every 21-D batch) plus a partner warpgroup that shortens the per-step latency chain

@@ -44,6 +44,9 @@
 #define QS_TC_PARTNER2 1     /* 1: large 12-D batches run two COMPACT tiles per CTA, each with its own partner warpgroup (512 threads, 256
                                 tensor-memory columns per tile: see the column plan in the kernel); 0: two plain tiles (256 threads) */
 #endif
+#ifndef QS_TC_X_AFTER_HEAD
+#define QS_TC_X_AFTER_HEAD 1 /* compact tiles: the critic's layer 2 is issued after the actor's head (1) / layer 2 (0) has completed */
+#endif
 #ifndef QS_TC_TS_L2
 #define QS_TC_TS_L2 1        /* 1 (one-tile CTAs only: needs 384 of the 512 TMEM columns per tile): relu(H1) also stays in tensor
                                 memory and layer 2 runs as TS-form MMAs */
@@ -196,6 +199,24 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t r[32]) {
                    "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                  :: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t r[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t r[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+// 8 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_relu_bf16_u(uint32_t lo, uint32_t hi) {
     return pack_relu_bf16(__uint_as_float(lo), __uint_as_float(hi));
 }
@@ -250,7 +271,8 @@ struct SmemT {
     static constexpr int kCandF = 28;                                   // p3 q4 v3 w3 target3 obs12
     static constexpr int EPI = CAND + (PARTNER ? 128 * kCandF * 4 : 0);
     static constexpr int VAL = EPI + (PARTNER ? 128 * 4 : 0);           // PARTNER: V(s) of the last forward, written by the partners
-    static constexpr int TILE_BYTES = VAL + (PARTNER ? 128 * 4 : 0);
+    static constexpr int SCR = VAL + (PARTNER ? 128 * 4 : 0);           // COMPACT: 4 x WarpResetScratch (576 B) of the owner warps
+    static constexpr int TILE_BYTES = SCR + (COMPACT ? 4 * 576 : 0);
     static constexpr int TILE0 = WEND;
     __host__ __device__ static constexpr int f32_off(int tiles) { return TILE0 + tiles * TILE_BYTES; }   // fp32 constants, see below
     static constexpr int kB3 = 0 /*[32]*/, kLogStd = 32, kMean = 36, kInvStd = 60, kNumF = 84;
@@ -397,7 +419,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     // candidate up from shared memory instead of running the ~310-instruction reset on the owners' critical path.
     float* sCand = reinterpret_cast<float*>(tsm + Smem::CAND);
     uint32_t* sEpi = reinterpret_cast<uint32_t*>(tsm + Smem::EPI);
-    const bool spec_reset = PARTNER && kGym && P.auto_reset == QS_RESET_RESAMPLE && !P.waypoint_mode;   // CTA-uniform
+    // compact tiles are the THROUGHPUT form (16 warps share the SM's issue slots): finished envs are re-sampled by their owner warps
+    // (warp-cooperative, as in plain tiles).  Speculative candidates from the partners -- every step, or refreshed lazily only
+    // after an env consumed its candidate -- were measured slower there (profiles/README.md: issue slots / 128-register cap).
+    const bool spec_reset = PARTNER && !kCompact && kGym && P.auto_reset == QS_RESET_RESAMPLE && !P.waypoint_mode;   // CTA-uniform
     Env e;
     float obs_[D];
     if (owner) {
@@ -423,11 +448,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     // 2 = tensor memory columns [256, 320) | [320, 384) (TS-form layer 2, one-tile CTAs).  In-place is safe: a thread stores
     // the 16 packed columns of chunk c to [16 c, 16 c + 16) after it has loaded [32 c, 32 c + 32), the one load in flight
     // covers [32 (c + 1), 32 (c + 2)), and lanes are private to the warp that owns them.
-    // c_first >= 0 (compact tiles): the first of the four 32-column chunks this warpgroup takes
-    auto relu_epilogue = [&](auto dst_tag, int c_first = -1) {
+    auto relu_epilogue = [&](auto dst_tag) {
         constexpr int kDst = decltype(dst_tag)::value;
         constexpr int kChunks = PARTNER ? 4 : 8;
-        const int c_lo = c_first >= 0 ? c_first : (PARTNER ? 4 * half : 0);
+        const int c_lo = PARTNER ? 4 * half : 0;
         uint32_t r[2][32];
         tmem_ld32_async(my_tmem + (uint32_t)(c_lo * 32), r[0]);
         tmem_ld_wait(r[0]);
@@ -456,6 +480,31 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             if (i + 1 < kChunks) tmem_ld_wait(r[(i + 1) & 1]);
         }
         if constexpr (kDst != 0) tmem_st_wait();
+    };
+    // compact tiles (128 registers per thread): the same epilogue over 128 accumulator columns starting at `src`, in eight
+    // 16-column chunks (32 registers in flight instead of 64).  to_tmem: packed bf16 -> tensor-memory columns [dst, dst + 64)
+    // (in place when dst == src: chunk i is stored to [dst + 8 i, + 8) after [src + 16 i, + 16) was loaded, the load in flight
+    // covers [src + 16 (i + 1), + 16)); else -> shared memory A2C.
+    auto relu_epilogue_c = [&](bool to_tmem, uint32_t src, uint32_t dst) {
+        uint32_t r[2][16];
+        tmem_ld16_async(my_tmem + src, r[0]);
+        tmem_ld_wait16(r[0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i + 1 < 8) tmem_ld16_async(my_tmem + src + (uint32_t)((i + 1) * 16), r[(i + 1) & 1]);
+            const uint32_t* v = r[i & 1];
+            uint32_t pk[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pk[q] = pack_relu_bf16_u(v[2 * q], v[2 * q + 1]);
+            if (to_tmem) {
+                tmem_st8(my_tmem + dst + (uint32_t)(8 * i), pk);
+            } else {
+                *reinterpret_cast<uint4*>(tsm + Smem::A2C + op_offset(128, tid, 2 * i)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(tsm + Smem::A2C + op_offset(128, tid, 2 * i + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            if (i + 1 < 8) tmem_ld_wait16(r[(i + 1) & 1]);
+        }
+        if (to_tmem) tmem_st_wait();
     };
     constexpr bool kTsHeads = QS_TC_TS_HEADS != 0;
     constexpr bool kTsL2 = QS_TC_TS_L2 != 0 && kTsHeads && TILES == 1;
@@ -486,8 +535,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         //   epilogue 1   owners:   relu(D1 actor)  -> A [0, 64)    in place
         //                partners: relu(D1 critic) -> shared memory A2C              (the critic's layer 2 is SS form)
         //   layer 2      actor  (warp 0): D2 [128, 256) <- A [0, 64) . W2A           on the owners' latency chain, TS form
-        //                critic (warp 4): D2 [0, 128)   <- A2C . W2C                 issued only once the actor's layer 2 has
-        //                                  COMPLETED (barX): its accumulator overwrites the actor's A columns
+        //                critic (warp 4): D2 [0, 128)   <- A2C . W2C                 issued only once the actor's HEAD has
+        //                                  completed (barX): its accumulator overwrites the actor's A columns
         //   epilogue 2   owners:   relu(D2 actor)  -> A [128, 192) in place;  head D [192, 208)
         //                partners: relu(D2 critic) -> A [0, 64)    in place;  head D [64, 80)
         // Everything the owners wait for is TS form, as in the one-tile split-critic CTAs; only the critic -- which runs behind
@@ -523,9 +572,9 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         fence_after();
         QS_TCP(1);
         if (half == 0) {
-            relu_epilogue(std::integral_constant<int, 1>{}, 0);        // actor: [0, 128) -> A [0, 64) in place
+            relu_epilogue_c(true, 0u, 0u);          // actor: [0, 128) -> A [0, 64) in place
         } else {
-            relu_epilogue(std::integral_constant<int, 0>{}, 4);        // critic: [128, 256) -> A2C
+            relu_epilogue_c(false, 128u, 0u);       // critic: [128, 256) -> A2C
             fence_async_smem();
         }
         QS_TCP(2);
@@ -538,12 +587,16 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 for (int j = 0; j < 8; ++j)
                     mma_bf16_ts(tmem + 128u, tmem + 8u * (uint32_t)j, make_desc(sbase + Smem::W2A + j * 4096, 16 * 128, 128), idesc_l2, j > 0);
                 mma_bf16(tmem + 128u, dA1b, make_desc(sbase + Smem::B2A, 16 * 128, 128), idesc_l2, 1u);
-                mma_commit(bar);                    // the owners wait for this one
-                mma_commit(barX);                   // and the partner warp that issues the critic's layer 2
+                mma_commit(bar);
+                if (QS_TC_X_AFTER_HEAD == 0) mma_commit(barX);
             }
             __syncwarp();
-        } else if (lwarp == 4) {
-            mbar_wait(barX, phaseX); phaseX ^= 1;   // the actor's layer 2 has read its A columns [0, 64)
+        }
+        if (lwarp == 4) {
+            // issued only once the actor's HEAD has completed (barX): the critic's accumulator overwrites the A columns [0, 64)
+            // the actor's layer 2 reads, and the critic's nine SS-form MMAs must not sit in the in-order tensor pipe in front of
+            // the head MMAs the owners are about to wait for (measured: "L3 sync + wait" 1240 vs 560 cycles per step)
+            mbar_wait(barX, phaseX); phaseX ^= 1;
             fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -559,7 +612,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             mbar_wait(bar, phase); phase ^= 1;
             fence_after();
             QS_TCP(3);
-            relu_epilogue(std::integral_constant<int, 1>{}, 4);        // actor: relu(H2) in place -> A [128, 192)
+            relu_epilogue_c(true, 128u, 128u);      // actor: relu(H2) in place -> A [128, 192)
             QS_TCP(4);
             fence_before();
             group_sync(tb + 2);
@@ -570,6 +623,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                     for (int j = 0; j < 8; ++j)
                         mma_bf16_ts(tmem + 192u, tmem + 128u + 8u * (uint32_t)j, make_desc(sbase + Smem::W3A + j * 512, 2 * 128, 128), idesc_l3, j > 0);
                     mma_commit(bar);
+                    if (QS_TC_X_AFTER_HEAD != 0) mma_commit(barX);               // the critic may start
                 }
                 __syncwarp();
             }
@@ -583,7 +637,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         } else {
             mbar_wait(barC, phaseC); phaseC ^= 1;
             fence_after();
-            relu_epilogue(std::integral_constant<int, 1>{}, 0);        // critic: relu(H2) in place -> A [0, 64)
+            relu_epilogue_c(true, 0u, 0u);          // critic: relu(H2) in place -> A [0, 64)
             fence_before();
             group_sync(tb + 3);
             if (lwarp == 4) {
@@ -656,9 +710,12 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             }
             __syncwarp();
             asm volatile("bar.arrive %0, 64;" :: "r"(tb + 4) : "memory");          // the actor's MMAs are in the pipe: the critic's may follow
-        } else if (lwarp == 4) {
-            // the critic's layer 2 is issued by a PARTNER warp (issuing blocks the thread at the pipe's pace: nine more MMAs
-            // from warp 0 kept the owners' group barrier waiting for it), behind the actor's (in-order pipe)
+        }
+        // the critic's layer 2 is issued by a PARTNER warp (issuing blocks the thread at the pipe's pace: nine more MMAs
+        // from warp 0 kept the owners' group barrier waiting for it), behind the actor's layer 2 (in-order pipe).  Holding it
+        // back until the actor's HEAD is in the pipe too -- what the compact tiles do -- measured slower here (2.23e9 -> 2.10e9
+        // at 8192 envs): with one tile per SM the pipe is mostly idle and the partners' chain is what gets longer.
+        auto issue_critic_l2 = [&]() {              // warp 4
             asm volatile("bar.sync %0, 64;" :: "r"(tb + 4) : "memory");
             fence_after();
             if (elect_one()) {
@@ -669,7 +726,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 mma_commit(barC);
             }
             __syncwarp();
-        }
+        };
+        if (lwarp == 4) issue_critic_l2();
         constexpr uint32_t kHeadA = 64u, kHeadC = 192u;
         if (half == 0) {
             mbar_wait(bar, phase); phase ^= 1;
@@ -984,7 +1042,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 // of this step and the first epilogue of the next forward (which every warp reaches only after the
                 // tile barrier that follows the A1 store, i.e. after all warps have left this block).
                 warp_autoreset_smem<MODE>(P, P.env_id_offset + (uint32_t)(b0 + warp * 32), e, obs_, so.needs_reset,
-                                          reinterpret_cast<WarpResetScratch*>(tsm + Smem::A2A)[warp]);
+                                          reinterpret_cast<WarpResetScratch*>(tsm + (kCompact ? Smem::SCR : Smem::A2A))[warp]);
             }
           }
         }

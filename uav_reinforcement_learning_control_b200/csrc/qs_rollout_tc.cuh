@@ -986,6 +986,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         if (PARTNER && half == 1 && t + 1 < steps)                         // next step's noise, off the owners' critical path
             sEps[((t + 1) & 1) * kM + tid] = draw_noise(t0 + (uint32_t)(t + 1));
+        bool any_boot = false;
         if constexpr (PARTNER && kGym) {
             if (spec_reset) {
                 if (half == 1) {
@@ -1005,7 +1006,9 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                     d[5] = make_float4(o[4], o[5], o[6], o[7]);
                     d[6] = make_float4(o[8], o[9], o[10], o[11]);
                 }
-                tile_sync<kTT>(tb);                                      // candidates of this step are in place
+                // candidates of this step are in place; the same tile-wide barrier carries the "somebody needs the timeout
+                // bootstrap" vote of the step (one barrier per step fewer than a separate tile_or below)
+                any_boot = tile_or<kTT>(tb, need_boot);
                 if (so.needs_reset) {                                      // (owners only; e.episode was advanced by env_step)
                     const float4* d = reinterpret_cast<const float4*>(sCand + tid * Smem::kCandF);
                     const float4 c0 = d[0], c1 = d[1], c2 = d[2], c3 = d[3], c4 = d[4], c5 = d[5], c6 = d[6];
@@ -1048,7 +1051,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         }
         QS_TCP(9);
         // SB3 timeout bootstrap: reward += gamma * V(terminal_obs) for truncated-not-terminated episodes
-        if (tile_or<kTT>(tb, need_boot)) {
+        if (spec_reset ? any_boot : tile_or<kTT>(tb, need_boot)) {
             float h2[Ao], vt;
             forward(need_boot ? tobs : obs_, h2, vt, true);
             if (need_boot) so.reward = fmaf(bootstrap_gamma, vt, so.reward);

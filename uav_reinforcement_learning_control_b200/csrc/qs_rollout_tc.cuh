@@ -44,6 +44,9 @@
 #define QS_TC_PARTNER2 1     /* 1: large 12-D batches run two COMPACT tiles per CTA, each with its own partner warpgroup (512 threads, 256
                                 tensor-memory columns per tile: see the column plan in the kernel); 0: two plain tiles (256 threads) */
 #endif
+#ifndef QS_TC_SPEC_IN_FORWARD
+#define QS_TC_SPEC_IN_FORWARD 1
+#endif
 #ifndef QS_TC_X_AFTER_HEAD
 #define QS_TC_X_AFTER_HEAD 1 /* compact tiles: the critic's layer 2 is issued after the actor's head (1) / layer 2 (0) has completed */
 #endif
@@ -519,8 +522,32 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     // The owner / partner warpgroups synchronise among themselves (named barriers 2 / 3, 128 threads); both meet again at
     // the tile barrier that opens the next forward, before its layer-1 MMA overwrites the accumulator columns.
     constexpr bool kSplitCritic = PARTNER && TILES == 1 && QS_TC_SPLIT_CRITIC != 0 && QS_TC_TS_HEADS != 0 && QS_TC_TS_L2 != 0;
+    // split-critic CTAs draw the reset candidates INSIDE the forward (behind the critic's layer-2 issue, while the owners wait for
+    // the actor's layer 2 / head) rather than next to the owners' env step, where the two warps of a scheduler compete
+    constexpr bool kSpecInForward = kSplitCritic && QS_TC_SPEC_IN_FORWARD != 0;
     constexpr bool kCriticBehind = kSplitCritic || kCompact;     // V(s) is produced (and stored) by the partner warpgroup
     uint32_t phaseC = 0, phaseX = 0;
+    // speculative reset candidates (partner warpgroup, gym modes): the state env `tid` WOULD be reset to for its next episode
+    int pending_noise_t = -1;               // kSpecInForward: step index whose noise the partners draw inside the coming forward
+    auto spec_candidates = [&]() {
+        if constexpr (PARTNER && kGym) {
+            // speculative reset of env `tid` for its next episode (all 128 lanes busy, no divergence)
+            Env r;
+            r.episode = sEpi[tid] + 1u;
+            r.wp_idx = 0; r.wp_reached = 0; r.laps = 0;
+            float rpy[3], o[D];
+            reset_env<MODE>(P, T, gid, r, rpy);
+            compute_obs<MODE>(P, r, rpy, o);
+            float4* d = reinterpret_cast<float4*>(sCand + tid * Smem::kCandF);
+            d[0] = make_float4(r.b.p[0], r.b.p[1], r.b.p[2], r.b.q[0]);
+            d[1] = make_float4(r.b.q[1], r.b.q[2], r.b.q[3], r.b.v[0]);
+            d[2] = make_float4(r.b.v[1], r.b.v[2], r.b.w[0], r.b.w[1]);
+            d[3] = make_float4(r.b.w[2], r.target[0], r.target[1], r.target[2]);
+            d[4] = make_float4(o[0], o[1], o[2], o[3]);
+            d[5] = make_float4(o[4], o[5], o[6], o[7]);
+            d[6] = make_float4(o[8], o[9], o[10], o[11]);
+        }
+    };
     float* sVal = reinterpret_cast<float*>(tsm + Smem::VAL);
     auto group_sync = [&](int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(128) : "memory"); };
     // forward pass for the observation in `o`; returns head[Ao] and -- if need_value (split critic: otherwise the partners
@@ -728,6 +755,13 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             __syncwarp();
         };
         if (lwarp == 4) issue_critic_l2();
+        if (kSpecInForward && half == 1) {
+            if (spec_reset) spec_candidates();
+            if (pending_noise_t >= 0) {             // the NEXT step's sampling noise (double-buffered: read one forward later)
+                sEps[(pending_noise_t & 1) * kM + tid] = draw_noise(t0 + (uint32_t)pending_noise_t);
+                pending_noise_t = -1;
+            }
+        }
         constexpr uint32_t kHeadA = 64u, kHeadC = 192u;
         if (half == 0) {
             mbar_wait(bar, phase); phase ^= 1;
@@ -946,6 +980,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         QS_TCP(11);
         float head[Ao], value;
         float4 e4_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kSpecInForward && t + 1 < steps) pending_noise_t = t + 1;
         forward(obs_, head, value, !kCriticBehind, PARTNER ? nullptr : &e4_pre, t0 + (uint32_t)t);
         if constexpr (kCriticBehind) {              // the partners computed V(s): they store it (thread tid <-> env tid, as the owners)
             if (half == 1 && tid < ept && (b0 + tid) < n && rb.value) rb.value[o] = value;
@@ -984,28 +1019,12 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             need_boot = bootstrap_gamma > 0.f && so.finished && so.truncated != 0.f && so.done == 0.f;
             if constexpr (ModeTraits<MODE>::kBrax) need_boot = bootstrap_gamma > 0.f && so.truncated != 0.f;
         }
-        if (PARTNER && half == 1 && t + 1 < steps)                         // next step's noise, off the owners' critical path
+        if (PARTNER && !kSpecInForward && half == 1 && t + 1 < steps)      // next step's noise, off the owners' critical path
             sEps[((t + 1) & 1) * kM + tid] = draw_noise(t0 + (uint32_t)(t + 1));
         bool any_boot = false;
         if constexpr (PARTNER && kGym) {
             if (spec_reset) {
-                if (half == 1) {
-                    // speculative reset of env `tid` for its next episode (all 128 lanes busy, no divergence)
-                    Env r;
-                    r.episode = sEpi[tid] + 1u;
-                    r.wp_idx = 0; r.wp_reached = 0; r.laps = 0;
-                    float rpy[3], o[D];
-                    reset_env<MODE>(P, T, gid, r, rpy);
-                    compute_obs<MODE>(P, r, rpy, o);
-                    float4* d = reinterpret_cast<float4*>(sCand + tid * Smem::kCandF);
-                    d[0] = make_float4(r.b.p[0], r.b.p[1], r.b.p[2], r.b.q[0]);
-                    d[1] = make_float4(r.b.q[1], r.b.q[2], r.b.q[3], r.b.v[0]);
-                    d[2] = make_float4(r.b.v[1], r.b.v[2], r.b.w[0], r.b.w[1]);
-                    d[3] = make_float4(r.b.w[2], r.target[0], r.target[1], r.target[2]);
-                    d[4] = make_float4(o[0], o[1], o[2], o[3]);
-                    d[5] = make_float4(o[4], o[5], o[6], o[7]);
-                    d[6] = make_float4(o[8], o[9], o[10], o[11]);
-                }
+                if (half == 1 && !kSpecInForward) spec_candidates();
                 // candidates of this step are in place; the same tile-wide barrier carries the "somebody needs the timeout
                 // bootstrap" vote of the step (one barrier per step fewer than a separate tile_or below)
                 any_boot = tile_or<kTT>(tb, need_boot);

@@ -4,8 +4,12 @@
 // ppo_train.train, train_brax_ppo.py:589-620, and SB3 collect_rollouts, train.py:133-137), but the three
 // dense layers of the 2x128 actor and critic run on the 5th-generation tensor cores:
 //
-//   * one CTA = 2 independent tiles of 128 threads = 128 envs (one UMMA M-tile) sharing the weights in smem;
-//     within a tile thread i owns env i (state in registers) AND TMEM lane i, so after an MMA every thread reads exactly its own env's activations with tcgen05.ld 32x32b;
+//   * a tile = 128 envs = one UMMA M-tile; within a tile thread i owns env i (state in registers) AND TMEM lane i, so after an
+//     MMA every thread reads exactly its own env's activations with tcgen05.ld 32x32b.  Three CTA forms share this file and
+//     record bitwise the same trajectories (tests/test_gpu_rollout.py): ONE tile + a partner warpgroup (256 threads; small
+//     batches, where the per-step latency chain is everything: the partners take the critic, the noise and speculative reset
+//     candidates off the owners' chain), TWO COMPACT tiles with a partner warpgroup each (512 threads, 256 TMEM columns per
+//     tile; large 12-D batches: 16 warps per SM), and two plain tiles (256 threads; the A/B reference, QS_TC_FORM=2);
 //   * operands are bf16 in shared memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte
 //     core matrices, SBO = 128 B between row groups, LBO = rows/8 * 128 B between 16-byte K chunks), written
 //     by the owners themselves: a warp's 16-byte stores for one K chunk are 512 contiguous bytes;

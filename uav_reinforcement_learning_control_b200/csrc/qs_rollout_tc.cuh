@@ -282,7 +282,7 @@ struct SmemT {
     static constexpr int TILE_BYTES = SCR + (COMPACT ? 4 * 576 : 0);
     static constexpr int TILE0 = WEND;
     __host__ __device__ static constexpr int f32_off(int tiles) { return TILE0 + tiles * TILE_BYTES; }   // fp32 constants, see below
-    static constexpr int kB3 = 0 /*[32]*/, kLogStd = 32, kMean = 36, kInvStd = 60, kNumF = 84;
+    static constexpr int kB3 = 0 /*[32]*/, kLogStd = 32, kMean = 36, kInvStd = 60, kStd = 84 /*[4] exp(log_std)*/, kNumF = 88;
     // mbarriers: [tiles] the actor's / everybody's | tmem base (4 B, padded to 8) | PARTNER: [tiles] the critic's | COMPACT: [tiles]
     // "actor's layer 2 complete" for the partner warp that issues the critic's
     __host__ __device__ static constexpr int bar_off(int tiles) { return f32_off(tiles) + kNumF * 4; }
@@ -381,7 +381,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
     __syncthreads();
     if (gtid < Ao) sF[Smem::kB3 + gtid] = params[L.ab3 + gtid];
     if (gtid == 0) sF[Smem::kB3 + 16] = params[L.cb3];
-    if (DIST == 0 && gtid < kA) sF[Smem::kLogStd + gtid] = params[L.log_std + gtid];
+    if (DIST == 0 && gtid < kA) {
+        sF[Smem::kLogStd + gtid] = params[L.log_std + gtid];
+        sF[Smem::kStd + gtid] = expf(params[L.log_std + gtid]);          // once per launch instead of per env-step
+    }
     if (gtid < D) { sF[Smem::kMean + gtid] = params[L.mean + gtid]; sF[Smem::kInvStd + gtid] = params[L.inv_std + gtid]; }
     if (ltid == 0) { mbar_init(bar, 1); if (PARTNER) mbar_init(barC, 1); if (kCompact) mbar_init(barX, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (gtid < 32) {
@@ -1004,7 +1007,7 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                 const float z = deterministic ? 0.f : eps[j];
                 if constexpr (DIST == 0) {
                     const float ls = sF[Smem::kLogStd + j];
-                    raw[j] = fmaf(expf(ls), z, head[j]);
+                    raw[j] = fmaf(sF[Smem::kStd + j], z, head[j]);
                     logp += -0.5f * z * z - ls - 0.9189385332046727f;
                     act[j] = clamp_(raw[j], -1.0f, 1.0f);
                 } else {

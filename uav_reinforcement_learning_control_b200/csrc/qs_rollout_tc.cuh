@@ -1119,6 +1119,7 @@ inline int launch_rollout_tc_tt(const QsParams& P, const Tables& T, int n, float
                                 cudaStream_t s) {
     auto kern = rollout_policy_tc_kernel<MODE, DIST, TILES, PARTNER>;
     using Smem = SmemT<(ModeTraits<MODE>::kObsDim + 2 <= 16) ? 16 : 32, PARTNER, PARTNER && TILES == 2>;
+    static_assert(Smem::total(TILES) <= 227 * 1024, "the CTA form does not fit the 227 KB of shared memory an sm_100 CTA can opt into");
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total(TILES));
     if (ce != cudaSuccess) return (int)ce;
     int ept = kM;                                    // envs per tile; QS_TC_EPT: test / tuning override (see the kernel)

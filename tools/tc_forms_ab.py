@@ -16,6 +16,9 @@ cases = [(8192, 256, ("1", "3", "2")), (1 << 18, 32, ("2", "3")), (1 << 20, 32, 
 for nb, T, forms in cases:
     eng = Engine(Q.EnvConfig.north_star(seed=1), nb, device=0)
     params = make_policy_params(eng, torch, dev, seed=0)
+    if os.environ.get("QS_AB_CALM_POLICY"):      # zero network, sigma = exp(-4): long episodes, few resets per step
+        params[:-28] = 0.0
+        params[-28:-24] = -4.0
     for rnd in range(2):
         for form in forms:
             os.environ["QS_TC_FORM"] = form
@@ -31,5 +34,6 @@ for nb, T, forms in cases:
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
-            print(f"{nb} envs x {T} steps, form {form}: {ms:.3f} ms, {nb * T / ms / 1e3:.3e} env-steps/s", flush=True)
+            fin = float(buf["done"].sum() + buf["trunc"].sum()) / (nb * T)
+            print(f"{nb} envs x {T} steps, form {form}: {ms:.3f} ms, {nb * T / ms / 1e3:.3e} M env-steps/s, episodes finished per env-step {fin:.4f}", flush=True)
     del eng

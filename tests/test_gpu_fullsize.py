@@ -126,6 +126,53 @@ def test_rollout_config_8192x1024_identities():
         assert float(b["obs"][:, :, 0:3].abs().max()) <= 1.0 + 1e-5 and float(b["reward"].min()) >= 0.0
 
 
+@pytest.mark.parametrize("waypoints", [False, True], ids=["hover", "waypoint"])
+def test_rollout_large_batch_forms_bitwise_equal_at_full_size(waypoints, monkeypatch):
+    """The 2^18-env rollout legs (BASELINE.json configs[3] and the large-batch throughput leg) at full size: the compact
+    two-tile CTAs the launcher picks there, the plain two-tile CTAs and the launcher's default record bitwise the same
+    trajectories over 48 steps (two chained launches), with the same episode-end identities as the 8192-env test.  Together
+    with the small-batch test in test_gpu_rollout.py (all forms == the one-tile form == the oracle lock-step) this is the
+    parity statement for the batch sizes the oracle cannot step."""
+    import torch
+    from uav_reinforcement_learning_control_b200 import policies, trajectories as TJ
+    from uav_reinforcement_learning_control_b200.engine import Engine
+    from bench import make_policy_params
+    B, T = 1 << 18, 24
+    if waypoints:
+        cfg = Q.EnvConfig.waypoint_eval(TJ.default_tables(0.5), auto_reset=Q.RESET_RESAMPLE, seed=3, battery=True)
+    else:
+        cfg = Q.EnvConfig.north_star(seed=3, max_episode_steps=17)
+    outs = {}
+    for form in ("2", "3", None):
+        if form is None:
+            monkeypatch.delenv("QS_TC_FORM", raising=False)
+        else:
+            monkeypatch.setenv("QS_TC_FORM", form)
+        eng = Engine(cfg, B, device=0)
+        st = eng.new_state(); eng.reset(st)
+        if waypoints:
+            p = torch.from_numpy(policies.pd_waypoint_policy(log_std=-3.5)).cuda()
+        else:
+            p = make_policy_params(eng, torch, torch.device("cuda"), seed=0)
+        epi0 = st[26].view(torch.int32).clone()
+        b = eng.rollout_policy(st, p, T=T, t0=0, dist=0, tensor_cores=True, bootstrap_gamma=0.9)
+        ends = torch.maximum(b["done"], b["trunc"]).sum(0)
+        b = eng.rollout_policy(st, p, T=T, t0=T, dist=0, tensor_cores=True, bootstrap_gamma=0.9, buffers=b)
+        ends = ends + torch.maximum(b["done"], b["trunc"]).sum(0)
+        torch.cuda.synchronize()
+        if not waypoints:          # (a closed lap ends an episode without a done / truncated flag)
+            assert torch.equal((st[26].view(torch.int32) - epi0).to(torch.float32), ends)
+        outs[form] = ({k: v.clone() for k, v in b.items()}, st.clone())
+        eng.close()
+    ref_b, ref_st = outs["2"]
+    for k in ("obs", "act", "logp", "value", "reward", "last_value"):
+        assert bool(torch.isfinite(ref_b[k]).all()), k
+    for form, (b, stn) in outs.items():
+        for k in ref_b:
+            assert torch.equal(b[k].view(torch.int32), ref_b[k].view(torch.int32)), (form, k)
+        assert torch.equal(stn.view(torch.int32), ref_st.view(torch.int32)), form
+
+
 def test_empty_and_bad_arguments_fail_loudly():
     import torch
     from uav_reinforcement_learning_control_b200.engine import Engine, QuadSimError

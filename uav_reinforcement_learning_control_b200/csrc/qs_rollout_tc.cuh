@@ -52,7 +52,8 @@
 #define QS_TC_SPEC_IN_FORWARD 1
 #endif
 #ifndef QS_TC_X_AFTER_HEAD
-#define QS_TC_X_AFTER_HEAD 1 /* compact tiles: the critic's layer 2 is issued after the actor's head (1) / layer 2 (0) has completed */
+#define QS_TC_X_AFTER_HEAD 2 /* compact tiles: the critic's layer 2 is issued once the actor's head has been ISSUED (2: named barrier between the
+                                two issuing warps), has COMPLETED (1: mbarrier barX), or right after the actor's layer 2 completed (0) */
 #endif
 #ifndef QS_TC_TS_L2
 #define QS_TC_TS_L2 1        /* 1 (one-tile CTAs only: needs 384 of the 512 TMEM columns per tile): relu(H1) also stays in tensor
@@ -569,8 +570,8 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
         //   epilogue 1   owners:   relu(D1 actor)  -> A [0, 64)    in place
         //                partners: relu(D1 critic) -> shared memory A2C              (the critic's layer 2 is SS form)
         //   layer 2      actor  (warp 0): D2 [128, 256) <- A [0, 64) . W2A           on the owners' latency chain, TS form
-        //                critic (warp 4): D2 [0, 128)   <- A2C . W2C                 issued only once the actor's HEAD has
-        //                                  completed (barX): its accumulator overwrites the actor's A columns
+        //                critic (warp 4): D2 [0, 128)   <- A2C . W2C                 issued only once the actor's HEAD is in the
+        //                                  pipe (named barrier): its accumulator overwrites the actor's (dead) A columns
         //   epilogue 2   owners:   relu(D2 actor)  -> A [128, 192) in place;  head D [192, 208)
         //                partners: relu(D2 critic) -> A [0, 64)    in place;  head D [64, 80)
         // Everything the owners wait for is TS form, as in the one-tile split-critic CTAs; only the critic -- which runs behind
@@ -627,10 +628,12 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
             __syncwarp();
         }
         if (lwarp == 4) {
-            // issued only once the actor's HEAD has completed (barX): the critic's accumulator overwrites the A columns [0, 64)
-            // the actor's layer 2 reads, and the critic's nine SS-form MMAs must not sit in the in-order tensor pipe in front of
-            // the head MMAs the owners are about to wait for (measured: "L3 sync + wait" 1240 vs 560 cycles per step)
-            mbar_wait(barX, phaseX); phaseX ^= 1;
+            // issued only once the actor's HEAD is in the pipe: the critic's accumulator overwrites the A columns [0, 64) the
+            // actor's layer 2 reads -- that layer has completed by then, the owners waited for it before their second epilogue
+            // -- and the critic's nine SS-form MMAs must not sit in the in-order tensor pipe in front of the head MMAs the owners
+            // are about to wait for (measured: "L3 sync + wait" 1240 vs 560 cycles per step)
+            if (QS_TC_X_AFTER_HEAD == 2) asm volatile("bar.sync %0, 64;" :: "r"(tb + 4) : "memory");
+            else { mbar_wait(barX, phaseX); phaseX ^= 1; }
             fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -657,9 +660,10 @@ rollout_policy_tc_kernel(const __grid_constant__ QsParams P, Tables T, int n, fl
                     for (int j = 0; j < 8; ++j)
                         mma_bf16_ts(tmem + 192u, tmem + 128u + 8u * (uint32_t)j, make_desc(sbase + Smem::W3A + j * 512, 2 * 128, 128), idesc_l3, j > 0);
                     mma_commit(bar);
-                    if (QS_TC_X_AFTER_HEAD != 0) mma_commit(barX);               // the critic may start
+                    if (QS_TC_X_AFTER_HEAD == 1) mma_commit(barX);               // the critic may start
                 }
                 __syncwarp();
+                if (QS_TC_X_AFTER_HEAD == 2) asm volatile("bar.arrive %0, 64;" :: "r"(tb + 4) : "memory");
             }
             mbar_wait(bar, phase); phase ^= 1;
             fence_after();
